@@ -1,0 +1,148 @@
+/*
+ * rnnt_b200.h -- C ABI of librnnt_b200.so: the B200-native (sm_100a) fused
+ * JointNet + RNN-T loss path.  Plain pointers and sizes only; no torch types.
+ *
+ * What it replaces in the reference (YooSungHyun/RNNTransducer):
+ *   - networks/transducer.py:54-71   JointNet.joint (repeat/cat/GELU/Linear)
+ *   - model.py:39,57,74              Warp_RNNTLoss(blank, reduction)(acts, labels, act_lens, label_lens)
+ *   - model.py:31,57                 Torch_RNNTLoss(...) (same call, fp16 path)
+ * The reference binds those through warp-transducer's C API (rnnt.h:
+ * get_workspace_size / compute_rnnt_loss, rnntStatus_t) and torchaudio's
+ * torch.ops.torchaudio.rnnt_loss_forward; the entry points below are what a
+ * ctypes/cffi binding of this path binds instead (INTEGRATION.md shows it).
+ *
+ * Conventions (all entry points):
+ *   - every pointer is a DEVICE pointer on the caller's current CUDA device
+ *     unless named host_*; the library never allocates device memory and holds
+ *     no global state (re-entrant: autograd calls *_bwd from another thread);
+ *   - `stream` is a cudaStream_t passed as void*; every call only enqueues work
+ *     and returns (no host synchronisation, CUDA-graph capturable);
+ *   - lengths stay on the device: act_lens[B], label_lens[B] are int32 device
+ *     arrays and are never read by the host (reference README.md:65 complaint);
+ *   - lattice planes are [B, T, U1] row-major fp32 with U1 = max_label_len + 1;
+ *     entries outside an utterance's (T_b, U_b + 1) box are left untouched by
+ *     forward calls and are written as exact zeros in gradient outputs;
+ *   - return value: rnntb200_status_t, modelled on warp-transducer's
+ *     rnntStatus_t; 0 = success.  rnntb200_status_string() names it.
+ *   - There is NO CPU fallback anywhere in this library.
+ */
+#ifndef RNNT_B200_H_
+#define RNNT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RNNTB200_VERSION 100 /* major*100 + minor */
+
+#if defined(__GNUC__)
+#define RNNTB200_API __attribute__((visibility("default")))
+#else
+#define RNNTB200_API
+#endif
+
+typedef enum {
+    RNNTB200_STATUS_SUCCESS = 0,
+    RNNTB200_STATUS_MEMOPS_FAILED = 1,
+    RNNTB200_STATUS_INVALID_VALUE = 2,
+    RNNTB200_STATUS_EXECUTION_FAILED = 3,
+    RNNTB200_STATUS_UNKNOWN_ERROR = 4
+} rnntb200_status_t;
+
+/* element type of logits / activations handed in by the caller */
+typedef enum { RNNTB200_F32 = 0, RNNTB200_F16 = 1, RNNTB200_BF16 = 2 } rnntb200_dtype_t;
+
+/* joint function.  CONCAT_GELU is the reference's joint (transducer.py:64-69):
+ *   logits = fc(gelu_tanh([enc_t ; dec_u])), fc.weight [V, He+Hd].
+ * ADD_TANH is the north_star's alternative: logits = fc(tanh(enc_t + dec_u)), fc.weight [V, H]
+ * (semantics of torchaudio.models.rnnt._Joiner(activation="tanh")). */
+typedef enum { RNNTB200_JOINT_CONCAT_GELU = 0, RNNTB200_JOINT_ADD_TANH = 1 } rnntb200_joint_mode_t;
+
+/* arithmetic of the H x V contraction in ADD_TANH mode */
+typedef enum {
+    RNNTB200_GEMM_FP32 = 0, /* CUDA-core FFMA, fp32 parity tolerance                  */
+    RNNTB200_GEMM_BF16 = 1, /* tcgen05 kind::f16 (bf16 in, fp32 accumulate in TMEM)    */
+    RNNTB200_GEMM_TF32X3 = 2 /* tcgen05 kind::tf32, 3-pass split, fp32-class accuracy   */
+} rnntb200_gemm_t;
+
+RNNTB200_API int rnntb200_version(void);
+RNNTB200_API const char* rnntb200_status_string(int status);
+
+/* ------------------------------------------------------------------------------------------
+ * Lattice sweeps (alpha and beta in ONE launch, one CTA per utterance and direction).
+ *   lp2   [B,T,U1] float2 = (log p(blank | t,u), log p(y_{u+1} | t,u)), natural log
+ *   alpha, beta [B,T,U1] fp32 out (natural log);  costs[B] = -beta(0,0) = -log P(y|x)
+ *   ll_alpha[B] optional (may be NULL): alpha(T-1,U) + lp_blank(T-1,U), a cross-check of costs.
+ * Replaces warp-transducer compute_alphas/compute_betas and torchaudio's
+ * ComputeAlphasBetasCosts.  Requires U1 <= 1024. */
+RNNTB200_API int rnntb200_lattice_sweep(const void* lp2, const int32_t* act_lens, const int32_t* label_lens,
+                           int B, int T, int U1, float* alpha, float* beta, float* costs,
+                           float* ll_alpha, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Dense-logits RNNTLoss (compat path: `loss(logits, labels, act_lens, label_lens)`, model.py:57).
+ *   logits [B,T,U1,V] contiguous, dtype in {F32,F16,BF16}; labels [B,U1-1] int32 zero padded.
+ * fwd: per-cell log-sum-exp -> lp2, lse; sweeps -> alpha, beta, costs.
+ * bwd: grad_logits[b,t,u,v] = grad_costs[b] * d cost_b / d logits (SURVEY.md 8(a) closed form),
+ *      same dtype as logits, padded cells written as 0.  Softmax is recomputed from logits + lse. */
+RNNTB200_API int rnntb200_loss_dense_fwd(const void* logits, int dtype, const int32_t* labels,
+                            const int32_t* act_lens, const int32_t* label_lens, int B, int T,
+                            int U1, int V, int blank, float* costs, void* lp2, float* lse,
+                            float* alpha, float* beta, void* stream);
+
+RNNTB200_API int rnntb200_loss_dense_bwd(const void* logits, int dtype, const int32_t* labels,
+                            const int32_t* act_lens, const int32_t* label_lens, int B, int T,
+                            int U1, int V, int blank, const float* lse, const float* alpha,
+                            const float* beta, const float* costs, const float* grad_costs,
+                            void* grad_logits, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused joint + loss, CONCAT_GELU (reference-exact) mode, factorised:
+ *   fc(gelu([e_t;d_u])) = P_enc[t,:] + P_dec[u,:],
+ *   P_enc = gelu(enc) W[:, :He]^T + bias  [B,T,V],   P_dec = gelu(dec) W[:, He:]^T  [B,U1,V]
+ * (two small projections done by the caller or by rnntb200_project_*).  The [B,T,U1,V] logits
+ * are never formed.
+ * fwd: per-cell V-wide add + log-sum-exp -> lp2, lse; sweeps -> alpha, beta, costs.
+ * bwd: d_penc[B,T,V] = sum_u g, d_pdec[B,U1,V] = sum_t g with g = grad_costs[b] * dcost/dlogits;
+ *      both fully written (zeros outside the valid box).  `deterministic` != 0 selects the
+ *      two-pass reduction through `workspace` (rnntb200_joint_cg_bwd_workspace_bytes) instead of
+ *      fp32 atomics for d_pdec. */
+RNNTB200_API int rnntb200_joint_cg_fwd(const float* penc, const float* pdec, const int32_t* labels,
+                          const int32_t* act_lens, const int32_t* label_lens, int B, int T, int U1,
+                          int V, int blank, float* costs, void* lp2, float* lse, float* alpha,
+                          float* beta, void* stream);
+
+RNNTB200_API size_t rnntb200_joint_cg_bwd_workspace_bytes(int B, int T, int U1, int V, int deterministic);
+
+RNNTB200_API int rnntb200_joint_cg_bwd(const float* penc, const float* pdec, const int32_t* labels,
+                          const int32_t* act_lens, const int32_t* label_lens, int B, int T, int U1,
+                          int V, int blank, const float* lse, const float* alpha, const float* beta,
+                          const float* costs, const float* grad_costs, float* d_penc, float* d_pdec,
+                          int deterministic, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused joint + loss, ADD_TANH mode: logits(t,u,:) = tanh(enc_t + dec_u) W^T + bias, the one
+ * dense H x V contraction per lattice cell.  enc [B,T,H], dec [B,U1,H], weight [V,H], bias [V].
+ * fwd emits lp2 / lse only; bwd recomputes the logits tile, forms g and feeds it straight into
+ * dgrad (g W (1 - z^2)) and wgrad (g^T z): d_enc [B,T,H], d_dec [B,U1,H], d_weight [V,H],
+ * d_bias [V]; all four are fully overwritten. */
+RNNTB200_API int rnntb200_joint_at_fwd(const float* enc, const float* dec, const float* weight,
+                          const float* bias, int gemm, const int32_t* labels,
+                          const int32_t* act_lens, const int32_t* label_lens, int B, int T, int U1,
+                          int V, int H, int blank, float* costs, void* lp2, float* lse, float* alpha,
+                          float* beta, void* stream);
+
+RNNTB200_API int rnntb200_joint_at_bwd(const float* enc, const float* dec, const float* weight,
+                          const float* bias, int gemm, const int32_t* labels,
+                          const int32_t* act_lens, const int32_t* label_lens, int B, int T, int U1,
+                          int V, int H, int blank, const float* lse, const float* alpha,
+                          const float* beta, const float* costs, const float* grad_costs,
+                          float* d_enc, float* d_dec, float* d_weight, float* d_bias, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RNNT_B200_H_ */

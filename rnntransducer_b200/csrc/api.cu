@@ -1,0 +1,108 @@
+// api.cu -- extern "C" entry points of librnnt_b200.so (see include/rnnt_b200.h).
+// Argument validation only touches host-visible scalars: lengths and labels stay on the device.
+#include "common.cuh"
+
+using namespace rnntb200;
+
+namespace {
+
+inline bool bad_shape(int B, int T, int U1, int V, int blank) {
+    return B < 0 || T <= 0 || U1 <= 0 || V <= 0 || blank < 0 || blank >= V;
+}
+inline bool bad_dtype(int dtype) {
+    return dtype != RNNTB200_F32 && dtype != RNNTB200_F16 && dtype != RNNTB200_BF16;
+}
+
+}  // namespace
+
+extern "C" {
+
+RNNTB200_API int rnntb200_version(void) { return RNNTB200_VERSION; }
+
+RNNTB200_API const char* rnntb200_status_string(int status) {
+    switch (status) {
+        case RNNTB200_STATUS_SUCCESS: return "rnntb200: success";
+        case RNNTB200_STATUS_MEMOPS_FAILED: return "rnntb200: cuda memcpy or memset failed";
+        case RNNTB200_STATUS_INVALID_VALUE: return "rnntb200: invalid value";
+        case RNNTB200_STATUS_EXECUTION_FAILED: return "rnntb200: kernel launch or execution failed";
+        default: return "rnntb200: unknown error";
+    }
+}
+
+RNNTB200_API int rnntb200_lattice_sweep(const void* lp2, const int32_t* act_lens, const int32_t* label_lens,
+                           int B, int T, int U1, float* alpha, float* beta, float* costs,
+                           float* ll_alpha, void* stream) {
+    if (B < 0 || T <= 0 || U1 <= 0) return RNNTB200_STATUS_INVALID_VALUE;
+    if (B > 0 && (!lp2 || !act_lens || !label_lens || !alpha || !beta || !costs))
+        return RNNTB200_STATUS_INVALID_VALUE;
+    return launch_lattice_sweep((const float2*)lp2, act_lens, label_lens, B, T, U1, alpha, beta,
+                                costs, ll_alpha, (cudaStream_t)stream);
+}
+
+RNNTB200_API int rnntb200_loss_dense_fwd(const void* logits, int dtype, const int32_t* labels,
+                            const int32_t* act_lens, const int32_t* label_lens, int B, int T,
+                            int U1, int V, int blank, float* costs, void* lp2, float* lse,
+                            float* alpha, float* beta, void* stream) {
+    if (bad_shape(B, T, U1, V, blank) || bad_dtype(dtype)) return RNNTB200_STATUS_INVALID_VALUE;
+    if (B > 0 && (!logits || !act_lens || !label_lens || !costs || !lp2 || !lse || !alpha || !beta))
+        return RNNTB200_STATUS_INVALID_VALUE;
+    if (B > 0 && U1 > 1 && !labels) return RNNTB200_STATUS_INVALID_VALUE;
+    cudaStream_t s = (cudaStream_t)stream;
+    int st = launch_dense_lse(logits, dtype, labels, act_lens, label_lens, B, T, U1, V, blank,
+                              (float2*)lp2, lse, s);
+    if (st != RNNTB200_STATUS_SUCCESS) return st;
+    return launch_lattice_sweep((const float2*)lp2, act_lens, label_lens, B, T, U1, alpha, beta,
+                                costs, nullptr, s);
+}
+
+RNNTB200_API int rnntb200_loss_dense_bwd(const void* logits, int dtype, const int32_t* labels,
+                            const int32_t* act_lens, const int32_t* label_lens, int B, int T,
+                            int U1, int V, int blank, const float* lse, const float* alpha,
+                            const float* beta, const float* costs, const float* grad_costs,
+                            void* grad_logits, void* stream) {
+    if (bad_shape(B, T, U1, V, blank) || bad_dtype(dtype)) return RNNTB200_STATUS_INVALID_VALUE;
+    if (B > 0 && (!logits || !act_lens || !label_lens || !lse || !alpha || !beta || !costs ||
+                  !grad_costs || !grad_logits))
+        return RNNTB200_STATUS_INVALID_VALUE;
+    if (B > 0 && U1 > 1 && !labels) return RNNTB200_STATUS_INVALID_VALUE;
+    return launch_dense_grad(logits, dtype, labels, act_lens, label_lens, B, T, U1, V, blank, lse,
+                             alpha, beta, costs, grad_costs, grad_logits, (cudaStream_t)stream);
+}
+
+RNNTB200_API int rnntb200_joint_cg_fwd(const float* penc, const float* pdec, const int32_t* labels,
+                          const int32_t* act_lens, const int32_t* label_lens, int B, int T, int U1,
+                          int V, int blank, float* costs, void* lp2, float* lse, float* alpha,
+                          float* beta, void* stream) {
+    if (bad_shape(B, T, U1, V, blank)) return RNNTB200_STATUS_INVALID_VALUE;
+    if (B > 0 && (!penc || !pdec || !act_lens || !label_lens || !costs || !lp2 || !lse || !alpha || !beta))
+        return RNNTB200_STATUS_INVALID_VALUE;
+    if (B > 0 && U1 > 1 && !labels) return RNNTB200_STATUS_INVALID_VALUE;
+    cudaStream_t s = (cudaStream_t)stream;
+    int st = launch_cg_lse(penc, pdec, labels, act_lens, label_lens, B, T, U1, V, blank, (float2*)lp2,
+                           lse, s);
+    if (st != RNNTB200_STATUS_SUCCESS) return st;
+    return launch_lattice_sweep((const float2*)lp2, act_lens, label_lens, B, T, U1, alpha, beta,
+                                costs, nullptr, s);
+}
+
+RNNTB200_API size_t rnntb200_joint_cg_bwd_workspace_bytes(int B, int T, int U1, int V, int deterministic) {
+    if (B <= 0 || T <= 0 || U1 <= 0 || V <= 0) return 0;
+    return cg_grad_workspace_bytes(B, T, U1, V, deterministic);
+}
+
+RNNTB200_API int rnntb200_joint_cg_bwd(const float* penc, const float* pdec, const int32_t* labels,
+                          const int32_t* act_lens, const int32_t* label_lens, int B, int T, int U1,
+                          int V, int blank, const float* lse, const float* alpha, const float* beta,
+                          const float* costs, const float* grad_costs, float* d_penc, float* d_pdec,
+                          int deterministic, void* workspace, size_t workspace_bytes, void* stream) {
+    if (bad_shape(B, T, U1, V, blank)) return RNNTB200_STATUS_INVALID_VALUE;
+    if (B > 0 && (!penc || !pdec || !act_lens || !label_lens || !lse || !alpha || !beta || !costs ||
+                  !grad_costs || !d_penc || !d_pdec))
+        return RNNTB200_STATUS_INVALID_VALUE;
+    if (B > 0 && U1 > 1 && !labels) return RNNTB200_STATUS_INVALID_VALUE;
+    return launch_cg_grad(penc, pdec, labels, act_lens, label_lens, B, T, U1, V, blank, lse, alpha,
+                          beta, costs, grad_costs, d_penc, d_pdec, deterministic, workspace,
+                          workspace_bytes, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,98 @@
+// common.cuh -- shared device helpers for librnnt_b200 (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/rnnt_b200.h"
+
+namespace rnntb200 {
+
+// Finite stand-in for log(0): keeps every logaddexp branch-free and NaN-free
+// (NEG + NEG stays finite, exp2(NEG - x) == 0).
+constexpr float kNegInf = -1.0e30f;
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+__device__ __forceinline__ float fast_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fast_lg2(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// log2(2^a + 2^b), base-2 log domain: 1 MUFU.EX2 + 1 MUFU.LG2 on the dependent chain.
+__device__ __forceinline__ float logaddexp2(float a, float b) {
+    const float m = fmaxf(a, b);
+    const float d = -fabsf(a - b);
+    return m + fast_lg2(1.0f + fast_ex2(d));
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <typename T>
+__device__ __forceinline__ float to_f32(T v);
+template <>
+__device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
+template <>
+__device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T>
+__device__ __forceinline__ T from_f32(float v);
+template <>
+__device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
+template <>
+__device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+inline int status_from_cuda(cudaError_t e) {
+    if (e == cudaSuccess) return RNNTB200_STATUS_SUCCESS;
+    if (e == cudaErrorInvalidValue || e == cudaErrorInvalidConfiguration) return RNNTB200_STATUS_INVALID_VALUE;
+    if (e == cudaErrorMemoryAllocation) return RNNTB200_STATUS_MEMOPS_FAILED;
+    return RNNTB200_STATUS_EXECUTION_FAILED;
+}
+
+// After a launch: report launch-configuration errors without synchronising.
+inline int launch_status() { return status_from_cuda(cudaGetLastError()); }
+
+// ---- internal launchers (defined in the .cu files, called from api.cu) ------------------------
+int launch_lattice_sweep(const float2* lp2, const int32_t* act_lens, const int32_t* label_lens, int B,
+                         int T, int U1, float* alpha, float* beta, float* costs, float* ll_alpha,
+                         cudaStream_t stream);
+
+int launch_dense_lse(const void* logits, int dtype, const int32_t* labels, const int32_t* act_lens,
+                     const int32_t* label_lens, int B, int T, int U1, int V, int blank, float2* lp2,
+                     float* lse, cudaStream_t stream);
+int launch_dense_grad(const void* logits, int dtype, const int32_t* labels, const int32_t* act_lens,
+                      const int32_t* label_lens, int B, int T, int U1, int V, int blank,
+                      const float* lse, const float* alpha, const float* beta, const float* costs,
+                      const float* grad_costs, void* grad_logits, cudaStream_t stream);
+
+int launch_cg_lse(const float* penc, const float* pdec, const int32_t* labels, const int32_t* act_lens,
+                  const int32_t* label_lens, int B, int T, int U1, int V, int blank, float2* lp2,
+                  float* lse, cudaStream_t stream);
+int launch_cg_grad(const float* penc, const float* pdec, const int32_t* labels, const int32_t* act_lens,
+                   const int32_t* label_lens, int B, int T, int U1, int V, int blank, const float* lse,
+                   const float* alpha, const float* beta, const float* costs, const float* grad_costs,
+                   float* d_penc, float* d_pdec, int deterministic, void* workspace,
+                   size_t workspace_bytes, cudaStream_t stream);
+size_t cg_grad_workspace_bytes(int B, int T, int U1, int V, int deterministic);
+
+}  // namespace rnntb200

@@ -1,0 +1,208 @@
+"""RNNTLoss drop-in (reference call sites: model.py:31,39 construct; model.py:57,74 call).
+
+    loss_fn = RNNTLoss(blank=0, reduction="mean")
+    loss = loss_fn(acts, labels, act_lens, label_lens)
+
+``acts`` is either a dense ``[B,T,U+1,V]`` logits tensor (the reference's own calling convention)
+or the lazy :class:`~rnntransducer_b200.joint.JointLogits` handle returned by our ``JointNet``; in
+the second case joint and loss run fused and the logits are never materialised.
+
+The functional spelling the north_star names -- ``rnnt_loss(acts, labels, act_lens, label_lens,
+blank, reduction)`` -- is warp-transducer's ``_RNNT.apply`` argument order.
+
+Everything runs through the C ABI of ``librnnt_b200.so`` (ctypes, raw device pointers, the
+caller's stream).  CPU tensors are rejected: there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+_DTYPES = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _validate(acts_shape, acts_device, labels, act_lens, label_lens, blank, require_cuda=True):
+    """Host-side checks that need no device sync (mirrors the oracle's messages)."""
+    if require_cuda and acts_device.type != "cuda":
+        raise RuntimeError("rnntransducer_b200: inputs must be CUDA tensors (there is no CPU fallback)")
+    B, T, U1, V = acts_shape
+    if labels.dtype != torch.int32:
+        raise RuntimeError("labels must be int32")
+    if act_lens.dtype != torch.int32 or label_lens.dtype != torch.int32:
+        raise RuntimeError("act_lens and label_lens must be int32")
+    for name, t in (("labels", labels), ("act_lens", act_lens), ("label_lens", label_lens)):
+        if t.device != acts_device:
+            raise RuntimeError(f"{name} must be on the same device as acts ({acts_device})")
+    if labels.dim() != 2 or labels.shape[0] != B:
+        raise RuntimeError("labels must be [B, U]")
+    if labels.shape[1] + 1 != U1:
+        raise RuntimeError(f"acts dim 2 must be labels.shape[1] + 1 (got {U1} vs {labels.shape[1]} + 1)")
+    if act_lens.shape != (B,) or label_lens.shape != (B,):
+        raise RuntimeError("act_lens and label_lens must be [B]")
+    if not 0 <= blank < V:
+        raise RuntimeError(f"blank must be in [0, {V}), got {blank}")
+    if T <= 0:
+        raise RuntimeError("acts must have at least one frame")
+
+
+def check_lengths(act_lens, label_lens, T, U1):
+    """Optional debug check (DEVICE SYNC): the oracle's max(act_lens)==T / max(label_lens)+1==U1."""
+    if int(act_lens.max()) > T or int(act_lens.min()) < 1:
+        raise RuntimeError("act_lens out of range")
+    if int(label_lens.max()) + 1 > U1 or int(label_lens.min()) < 0:
+        raise RuntimeError("label_lens out of range")
+
+
+class _DenseRNNT(torch.autograd.Function):
+    """costs[B] = -log P(y|x) from dense logits (K5 front-end + alpha/beta sweeps; K4 gradient)."""
+
+    @staticmethod
+    def forward(ctx, acts, labels, act_lens, label_lens, blank):
+        if acts.dtype not in _DTYPES:
+            raise RuntimeError("acts must be float32, float16 or bfloat16")
+        _validate(acts.shape, acts.device, labels, act_lens, label_lens, blank)
+        acts = acts.contiguous()
+        labels = labels.contiguous()
+        B, T, U1, V = acts.shape
+        dev = acts.device
+        f32 = dict(device=dev, dtype=torch.float32)
+        costs = torch.empty(B, **f32)
+        lp2 = torch.empty(B, T, U1, 2, **f32)
+        lse, alpha, beta = (torch.empty(B, T, U1, **f32) for _ in range(3))
+        lib = _lib.load()
+        with torch.cuda.device(dev):
+            _lib.check(lib.rnntb200_loss_dense_fwd(
+                _ptr(acts), _DTYPES[acts.dtype], _ptr(labels), _ptr(act_lens), _ptr(label_lens),
+                B, T, U1, V, blank, _ptr(costs), _ptr(lp2), _ptr(lse), _ptr(alpha), _ptr(beta),
+                _stream()), "rnntb200_loss_dense_fwd")
+        ctx.save_for_backward(acts, labels, act_lens, label_lens, lse, alpha, beta, costs)
+        ctx.blank = blank
+        return costs
+
+    @staticmethod
+    def backward(ctx, grad_costs):
+        acts, labels, act_lens, label_lens, lse, alpha, beta, costs = ctx.saved_tensors
+        B, T, U1, V = acts.shape
+        grad_costs = grad_costs.contiguous().to(torch.float32)
+        grad = torch.empty_like(acts)
+        lib = _lib.load()
+        with torch.cuda.device(acts.device):
+            _lib.check(lib.rnntb200_loss_dense_bwd(
+                _ptr(acts), _DTYPES[acts.dtype], _ptr(labels), _ptr(act_lens), _ptr(label_lens),
+                B, T, U1, V, ctx.blank, _ptr(lse), _ptr(alpha), _ptr(beta), _ptr(costs),
+                _ptr(grad_costs), _ptr(grad), _stream()), "rnntb200_loss_dense_bwd")
+        return grad, None, None, None, None
+
+
+class _ConcatGeluRNNT(torch.autograd.Function):
+    """costs[B] from the factorised reference joint: logits(t,u) = penc[t] + pdec[u]."""
+
+    @staticmethod
+    def forward(ctx, penc, pdec, labels, act_lens, label_lens, blank, deterministic):
+        B, T, V = penc.shape
+        U1 = pdec.shape[1]
+        _validate((B, T, U1, V), penc.device, labels, act_lens, label_lens, blank)
+        penc = penc.contiguous().float()
+        pdec = pdec.contiguous().float()
+        labels = labels.contiguous()
+        f32 = dict(device=penc.device, dtype=torch.float32)
+        costs = torch.empty(B, **f32)
+        lp2 = torch.empty(B, T, U1, 2, **f32)
+        lse, alpha, beta = (torch.empty(B, T, U1, **f32) for _ in range(3))
+        lib = _lib.load()
+        with torch.cuda.device(penc.device):
+            _lib.check(lib.rnntb200_joint_cg_fwd(
+                _ptr(penc), _ptr(pdec), _ptr(labels), _ptr(act_lens), _ptr(label_lens), B, T, U1, V,
+                blank, _ptr(costs), _ptr(lp2), _ptr(lse), _ptr(alpha), _ptr(beta), _stream()),
+                "rnntb200_joint_cg_fwd")
+        ctx.save_for_backward(penc, pdec, labels, act_lens, label_lens, lse, alpha, beta, costs)
+        ctx.blank, ctx.deterministic = blank, bool(deterministic)
+        return costs
+
+    @staticmethod
+    def backward(ctx, grad_costs):
+        penc, pdec, labels, act_lens, label_lens, lse, alpha, beta, costs = ctx.saved_tensors
+        B, T, V = penc.shape
+        U1 = pdec.shape[1]
+        grad_costs = grad_costs.contiguous().to(torch.float32)
+        d_penc = torch.empty_like(penc)
+        d_pdec = torch.empty_like(pdec)
+        lib = _lib.load()
+        det = int(ctx.deterministic)
+        ws_bytes = lib.rnntb200_joint_cg_bwd_workspace_bytes(B, T, U1, V, det)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=penc.device) if ws_bytes else None
+        with torch.cuda.device(penc.device):
+            _lib.check(lib.rnntb200_joint_cg_bwd(
+                _ptr(penc), _ptr(pdec), _ptr(labels), _ptr(act_lens), _ptr(label_lens), B, T, U1, V,
+                ctx.blank, _ptr(lse), _ptr(alpha), _ptr(beta), _ptr(costs), _ptr(grad_costs),
+                _ptr(d_penc), _ptr(d_pdec), det, _ptr(ws), ws_bytes, _stream()),
+                "rnntb200_joint_cg_bwd")
+        return d_penc, d_pdec, None, None, None, None, None
+
+
+def _reduce(costs, reduction, warp_compat):
+    if reduction == "none":
+        return costs
+    if reduction == "sum":
+        out = costs.sum()
+    elif reduction == "mean":
+        out = costs.sum() / costs.shape[0]  # warp-transducer: mean over B only
+    else:
+        raise ValueError(f"reduction must be 'none', 'mean' or 'sum', got {reduction!r}")
+    # warp-transducer returns shape (1,) for mean/sum (model.py:88 torch.cat's them);
+    # torchaudio returns a 0-d tensor (model.py:85).
+    return out.reshape(1) if warp_compat else out
+
+
+def rnnt_costs(acts, labels, act_lens, label_lens, blank=0, deterministic=False):
+    """Per-utterance costs [B] (differentiable).  ``acts``: dense logits or a JointLogits handle."""
+    from .joint import JointLogits  # local import: joint imports loss
+    if isinstance(acts, JointLogits):
+        return acts.costs(labels, act_lens, label_lens, blank, deterministic)
+    if acts.dim() != 4:
+        raise RuntimeError("acts must be [B, T, U+1, V]")
+    return _DenseRNNT.apply(acts, labels, act_lens, label_lens, int(blank))
+
+
+def rnnt_loss(acts, labels, act_lens, label_lens, blank=0, reduction="mean", warp_compat=True,
+              deterministic=False):
+    """Functional form, warp-transducer argument order (north_star)."""
+    costs = rnnt_costs(acts, labels, act_lens, label_lens, blank, deterministic)
+    return _reduce(costs, reduction, warp_compat)
+
+
+class RNNTLoss(torch.nn.Module):
+    """Drop-in for ``warprnnt_pytorch.RNNTLoss`` / ``torchaudio.transforms.RNNTLoss`` as the
+    reference uses them (model.py:31,39): ``RNNTLoss(blank, reduction)(acts, labels, act_lens,
+    label_lens)``.
+
+    warp_compat=True (default) keeps warp-transducer's ``(1,)`` result shape for mean/sum, which
+    ``validation_epoch_end`` relies on (model.py:83-88); False gives torchaudio's 0-d tensor.
+    """
+
+    def __init__(self, blank: int = 0, reduction: str = "mean", warp_compat: bool = True,
+                 deterministic: bool = False, check_lengths: bool = False):
+        super().__init__()
+        if reduction not in ("none", "mean", "sum"):
+            raise ValueError(f"reduction must be 'none', 'mean' or 'sum', got {reduction!r}")
+        self.blank = int(blank)
+        self.reduction = reduction
+        self.warp_compat = warp_compat
+        self.deterministic = deterministic
+        self.check_lengths = check_lengths  # debug only: costs a device sync
+
+    def forward(self, acts, labels, act_lens, label_lens):
+        if self.check_lengths:
+            shape = acts.shape
+            check_lengths(act_lens, label_lens, shape[1], shape[2])
+        return rnnt_loss(acts, labels, act_lens, label_lens, self.blank, self.reduction,
+                         self.warp_compat, self.deterministic)
