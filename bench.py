@@ -1,0 +1,487 @@
+#!/usr/bin/env python
+"""bench.py -- fused joint + RNN-T loss, forward + backward, in lattice cells/s (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--cfg 2] [--mode concat_gelu|add_tanh] [--gemm fp32|bf16] [--ragged] [--eager]
+
+One "step" = one pass of the hot path over one synthetic batch: joint + log-softmax + alpha/beta
+sweeps + gradient w.r.t. enc, dec, fc.weight, fc.bias (reduction="mean"), i.e. what
+``loss = RNNTLoss(...)(JointNet(...)(...), ...); loss.backward()`` costs from the encoder /
+predictor outputs down (reference model.py:56-57, networks/transducer.py:54-71).
+
+Default workload at N=1: BASELINE.json configs[1] -- KsponSpeech-shaped batch B=32, T=400, U=80,
+V=73, joint H=512, fp32, full-length utterances, the reference's own joint (concat -> GELU ->
+Linear).  Under torchrun every rank runs that batch with its own seed (weak scaling; utterances
+are independent) and the only exchange is the all-reduce of the fc gradients DDP would do.
+
+Printed keys (one JSON line on rank 0): the base contract plus
+  roofline      dominant kernel, algorithmic bytes per launch / CUDA-event duration vs measured HBM peak
+  kernels       the same for every kernel of the step
+  cpu_baseline  the CPU oracle port (reference joint restated in torch + C/OpenMP warp-transducer
+                restatement) timed on this box's host cores on a bounded sample of the workload
+  e2e           same metric through the public API with HOST (pinned) inputs, H2D + D2H in the timing
+``--impl reference`` times that CPU path alone (rank 0 only) and prints the same line shape.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "joint+RNNT-loss fwd+bwd lattice cells/s"
+UNIT = "cells/s"
+FALLBACK_HBM_GBS = 6650.0  # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=100)
+    p.add_argument("--warmup", type=int, default=10)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--cfg", type=int, default=2, choices=[1, 2, 3, 4])
+    p.add_argument("--mode", default="concat_gelu", choices=["concat_gelu", "add_tanh"])
+    p.add_argument("--gemm", default=None, choices=["fp32", "bf16"])
+    p.add_argument("--ragged", action="store_true")
+    p.add_argument("--eager", action="store_true", help="do not replay the step from a CUDA graph")
+    p.add_argument("--deterministic", action="store_true")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU work for cpu_baseline")
+    return p.parse_args()
+
+
+def hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def workload_config(args, world):
+    from rnntransducer_b200 import synthetic
+    c = synthetic.CONFIGS[args.cfg]
+    gemm = args.gemm or ("fp32" if args.mode == "concat_gelu" or args.cfg == 2 else "bf16")
+    return c, gemm, {
+        "workload": f"BASELINE cfg{args.cfg}: B={c['B']} T={c['T']} U={c['U']} V={c['V']} H={c['H']} per GPU, "
+                    f"{'ragged' if args.ragged else 'full-length'} utterances, fwd+bwd",
+        "joint": args.mode, "gemm": gemm, "B_per_gpu": c["B"], "global_batch": c["B"] * world,
+        "T": c["T"], "U": c["U"], "V": c["V"], "H": c["H"], "ragged": bool(args.ragged),
+        "reduction": "mean", "parallelism": f"dp{world} (utterances sharded, fc grads all-reduced)",
+        "l2": "flushed between timed steps (256 MiB write)",
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+class ClockSampler:
+    """Samples SM clock + throttle reasons of one GPU during the timed region (pynvml)."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown",
+               0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, index, period=0.01):
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _sample(self):
+        try:
+            self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+            try:
+                mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            except Exception:
+                mask = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            for bit, name in self.REASONS.items():
+                if mask & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def _run(self):
+        while not self._stop.is_set():
+            self._sample()
+            self._stop.wait(self.period)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *exc):
+        if self._thr is not None:
+            self._sample()
+            self._stop.set()
+            self._thr.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unsampled"]}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm (the oracle port: reference joint restated + warp-transducer CPU restatement)
+def cpu_step_factory(batch, n_utt, mode):
+    """Returns (fn, cells) where fn() runs joint + loss + backward on the first n_utt utterances."""
+    import torch
+    from oracle import joint_ref
+    from rnntransducer_b200 import synthetic
+    sl = slice(0, n_utt)
+    enc, dec = batch["enc"][sl].contiguous(), batch["dec"][sl].contiguous()
+    labels = batch["labels"][sl].contiguous().numpy()
+    al, ll = batch["act_lens"][sl].contiguous().numpy(), batch["label_lens"][sl].contiguous().numpy()
+    cells = synthetic.count_cells(batch["act_lens"][sl], batch["label_lens"][sl])
+
+    def fn():
+        return joint_ref.joint_loss_fwd_bwd(enc, dec, batch["weight"], batch["bias"], labels, al, ll, 0,
+                                            "mean", mode, num_threads=0)
+    return fn, cells
+
+
+def time_cpu(batch, mode, target_seconds, reps=2, max_utt=None):
+    """Bounded sample: calibrate on 1 utterance, then take as many utterances as fit the budget."""
+    import torch
+    from oracle import warp_cpu
+    warp_cpu.build()
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B = batch["enc"].shape[0]
+    fn1, _ = cpu_step_factory(batch, 1, mode)
+    t0 = time.perf_counter()
+    fn1()
+    t1 = time.perf_counter() - t0
+    n = int(max(1, min(B if max_utt is None else max_utt, target_seconds / max(t1, 1e-3) / reps)))
+    fn, cells = cpu_step_factory(batch, n, mode)
+    best = float("inf")
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        fn()
+        best = min(best, time.perf_counter() - t0)
+    return dict(value=cells / best, unit=UNIT, cores=cores, kind="port",
+                sample=f"first {n} of {B} utterances of the same batch ({cells} cells), joint restated in "
+                       f"torch CPU ({cores} threads) + oracle/warp_cpu.c OpenMP over utterances "
+                       f"({min(cores, n)} threads), fwd+bwd, best of {reps}",
+                seconds=best, utterances=n)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    from rnntransducer_b200 import synthetic
+    c, gemm, config = workload_config(args, world)
+    batch = synthetic.make_batch(c["B"], c["T"], c["U"], c["V"], c["H"], mode=args.mode,
+                                 ragged=args.ragged, seed=1234 + args.cfg)
+    import torch
+    from oracle import warp_cpu
+    warp_cpu.build()
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    # size the per-step sample so that (steps + warmup) steps end within ~2 minutes
+    fn1, _ = cpu_step_factory(batch, 1, args.mode)
+    t0 = time.perf_counter()
+    fn1()
+    t1 = time.perf_counter() - t0
+    per_step = 120.0 / max(args.steps + args.warmup, 1)
+    n = int(max(1, min(c["B"], per_step / max(t1, 1e-3))))
+    fn, cells = cpu_step_factory(batch, n, args.mode)
+    for _ in range(args.warmup):
+        fn()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fn()
+    total = time.perf_counter() - t0
+    value = cells * args.steps / total
+    sample = (f"each step = first {n} of {c['B']} utterances of the workload batch ({cells} cells): reference "
+              f"joint restated in torch CPU ({cores} threads) + oracle/warp_cpu.c (C/OpenMP restatement of "
+              f"warp-transducer's CPU loss, {min(cores, n)} threads), fwd+bwd")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": config,
+        "utterances_per_s": n * args.steps / total,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "warprnnt_pytorch (the reference's fp32 loss) is not installable offline and the reference "
+                "is pure Python, so the reference arm is the CPU oracle port (DESIGN.md)",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import rnntransducer_b200 as rb
+    from rnntransducer_b200 import _lib, synthetic
+    from rnntransducer_b200.joint_add_tanh import GEMMS
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl ours) needs a CUDA device: there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()  # fails loudly when the CUDA extension is missing
+
+    c, gemm, config = workload_config(args, world)
+    mode, det = args.mode, bool(args.deterministic)
+    B, T, U, V, H = c["B"], c["T"], c["U"], c["V"], c["H"]
+    U1 = U + 1
+    host = synthetic.make_batch(B, T, U, V, H, mode=mode, ragged=args.ragged, seed=1234 + args.cfg + rank)
+    cells = synthetic.count_cells(host["act_lens"], host["label_lens"])
+    pinned = {k: host[k].pin_memory() for k in ("enc", "dec", "labels", "act_lens", "label_lens")}
+    st = {k: v.to(dev) for k, v in host.items()}  # static device buffers (graph inputs)
+    for k in ("enc", "dec", "weight", "bias"):
+        st[k].requires_grad_(True)
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def zero_grads():
+        for k in ("enc", "dec", "weight", "bias"):
+            st[k].grad = None
+
+    out = {}
+
+    def step():
+        loss = rb.joint_rnnt_loss(st["enc"], st["dec"], st["weight"], st["bias"], st["labels"],
+                                  st["act_lens"], st["label_lens"], 0, "mean", mode, gemm,
+                                  deterministic=det)
+        loss.backward()
+        out["loss"] = loss.detach()
+
+    # eager warm-up (also JITs nothing: the library is prebuilt) on a side stream, then capture
+    graph = None
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            zero_grads()
+            step()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    if not args.eager:
+        zero_grads()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            step()
+
+    def run_step():
+        if graph is not None:
+            graph.replay()
+        else:
+            zero_grads()
+            step()
+        if world > 1:  # what DDP does with the gradients our kernels produce
+            dist.all_reduce(st["weight"].grad)
+            dist.all_reduce(st["bias"].grad)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+        for e0, e1 in ev:
+            flush_buf.zero_()  # evict the working set from L2 (outside the timed bracket)
+            e0.record()
+            fn()
+            e1.record()
+        torch.cuda.synchronize()
+        return sum(e0.elapsed_time(e1) for e0, e1 in ev)  # ms
+
+    for _ in range(max(args.warmup, 3)):
+        flush_buf.zero_()
+        run_step()
+    barrier()
+    with ClockSampler(local_rank) as clocks:
+        total_ms = timed(run_step, args.steps)
+    barrier()
+
+    # ---- end to end through the public API with host inputs ------------------------------------
+    loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
+    h2d = sum(pinned[k].numel() * pinned[k].element_size() for k in pinned)
+
+    def e2e_step():
+        with torch.no_grad():
+            for k in pinned:
+                st[k].copy_(pinned[k], non_blocking=True)
+        run_step()
+        loss_host.copy_(out["loss"].reshape(1), non_blocking=True)
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    e2e_ms = 0.0
+    t_wall = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_ms += timed(e2e_step, 1)  # synchronises every step: the caller reads the loss
+    e2e_wall = time.perf_counter() - t_wall
+    barrier()
+    loss_value = float(loss_host[0])
+
+    if world > 1:
+        t = torch.tensor([total_ms, e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_ms = float(t[0]), float(t[1])
+        cells_t = torch.tensor([cells], device=dev, dtype=torch.float64)
+        dist.all_reduce(cells_t)
+        total_cells = float(cells_t[0])
+    else:
+        total_cells = float(cells)
+
+    # ---- per-kernel timing through the C ABI (rank 0): roofline -------------------------------
+    kernels, roofline = {}, None
+    if rank == 0:
+        kernels = per_kernel(lib, st, mode, GEMMS[gemm], det, B, T, U1, V, H, cells, flush_buf)
+        peak, peak_src = hbm_peak()
+        for k in kernels.values():
+            k["GBps"] = k["bytes"] / (k["us"] * 1e-6) / 1e9
+            k["frac_hbm"] = k["GBps"] / peak
+        top = max((k for k in kernels.values() if k.get("ours")), key=lambda k: k["us"])
+        roofline = {"kernel": top["name"], "bound": "hbm", "achieved": top["GBps"], "peak": peak,
+                    "unit": "GB/s", "frac": top["frac_hbm"], "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": top["bytes"], "us_per_launch": top["us"]}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    launches = {"concat_gelu": 3 + int(det), "add_tanh": 3}[mode]
+    line = {
+        "metric": METRIC, "value": total_cells * args.steps / (total_ms * 1e-3), "unit": UNIT,
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32" if gemm == "fp32" else "bf16 GEMM / f32 lattice",
+        "data": "synthetic", "config": config,
+        "utterances_per_s": B * world * args.steps / (total_ms * 1e-3),
+        "cells_per_step": total_cells, "loss": loss_value,
+        "cuda_graph": graph is not None,
+        "clocks": clocks.summary(),
+        "e2e": {"value": total_cells * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps,
+                "wall_ms_per_step_incl_flush": 1e3 * e2e_wall / args.steps},
+        "gpu_launches": launches * args.steps,
+        "roofline": roofline, "kernels": kernels,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = time_cpu(host, mode, args.cpu_seconds)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def per_kernel(lib, st, mode, gemm, det, B, T, U1, V, H, cells, flush_buf, iters=20):
+    """Times each kernel of the step by itself (CUDA events on the launching stream, L2 flushed
+    between launches).  `bytes` = algorithmic bytes per launch (DESIGN.md / SURVEY 8(d))."""
+    import torch
+    import torch.nn.functional as F
+    from rnntransducer_b200 import _lib
+    dev = st["enc"].device
+    f32 = dict(device=dev, dtype=torch.float32)
+    stream = torch.cuda.current_stream().cuda_stream
+    p = lambda t: t.data_ptr()
+    lp2 = torch.empty(B, T, U1, 2, **f32)
+    lse, alpha, beta = (torch.empty(B, T, U1, **f32) for _ in range(3))
+    costs, gcosts = torch.empty(B, **f32), torch.full((B,), 1.0 / B, **f32)
+    lab, al, ll = st["labels"], st["act_lens"], st["label_lens"]
+    res = {}
+
+    def bench(name, fn, nbytes, ours=True):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        tot = 0.0
+        for _ in range(iters):
+            flush_buf.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            tot += e0.elapsed_time(e1)
+        res[name] = {"name": name, "us": 1e3 * tot / iters, "bytes": int(nbytes), "ours": ours}
+
+    with torch.no_grad():
+        enc, dec, w, b = st["enc"].detach(), st["dec"].detach(), st["weight"].detach(), st["bias"].detach()
+        if mode == "concat_gelu":
+            He = enc.shape[-1]
+            proj = lambda: (F.linear(F.gelu(enc, approximate="tanh"), w[:, :He], b),
+                            F.linear(F.gelu(dec, approximate="tanh"), w[:, He:]))
+            penc, pdec = proj()
+            penc, pdec = penc.contiguous(), pdec.contiguous()
+            d_penc, d_pdec = torch.empty_like(penc), torch.empty_like(pdec)
+            ws_bytes = lib.rnntb200_joint_cg_bwd_workspace_bytes(B, T, U1, V, int(det))
+            ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+            io = 4 * V * B * (T + U1)
+            bench("torch_projections(gelu+linear x2, library)", proj,
+                  4 * (enc.numel() + dec.numel() + w.numel()) + io, ours=False)
+            bench("cg_lse_kernel", lambda: _lib.check(lib.rnntb200_joint_cg_logprobs(
+                p(penc), p(pdec), p(lab), p(al), p(ll), B, T, U1, V, 0, p(lp2), p(lse), stream)),
+                12 * cells + io)
+            bench("lattice_sweep_kernel", lambda: _lib.check(lib.rnntb200_lattice_sweep(
+                p(lp2), p(al), p(ll), B, T, U1, p(alpha), p(beta), p(costs), None, stream)), 24 * cells)
+            bench("cg_grad_kernel", lambda: _lib.check(lib.rnntb200_joint_cg_bwd(
+                p(penc), p(pdec), p(lab), p(al), p(ll), B, T, U1, V, 0, p(lse), p(alpha), p(beta),
+                p(costs), p(gcosts), p(d_penc), p(d_pdec), int(det), p(ws), ws_bytes, stream)),
+                12 * cells + 2 * io)
+        else:
+            d_enc, d_dec = torch.empty_like(enc), torch.empty_like(dec)
+            d_w, d_b = torch.empty_like(w), torch.empty_like(b)
+            io = 4 * H * B * (T + U1) + 4 * V * (H + 1)
+            bench("at_lse_kernel", lambda: _lib.check(lib.rnntb200_joint_at_logprobs(
+                p(enc), p(dec), p(w), p(b), gemm, p(lab), p(al), p(ll), B, T, U1, V, H, 0, p(lp2),
+                p(lse), stream)), 12 * cells + io)
+            bench("lattice_sweep_kernel", lambda: _lib.check(lib.rnntb200_lattice_sweep(
+                p(lp2), p(al), p(ll), B, T, U1, p(alpha), p(beta), p(costs), None, stream)), 24 * cells)
+            bench("at_grad_kernel", lambda: _lib.check(lib.rnntb200_joint_at_bwd(
+                p(enc), p(dec), p(w), p(b), gemm, p(lab), p(al), p(ll), B, T, U1, V, H, 0, p(lse),
+                p(alpha), p(beta), p(costs), p(gcosts), p(d_enc), p(d_dec), p(d_w), p(d_b), stream)),
+                12 * cells + 2 * io)
+            for k in ("at_lse_kernel", "at_grad_kernel"):
+                passes = 1 if k == "at_lse_kernel" else 3  # fwd | recompute + dgrad + wgrad
+                res[k]["flops"] = 2.0 * H * V * cells * passes
+                res[k]["TFLOPs"] = res[k]["flops"] / (res[k]["us"] * 1e-6) / 1e12
+    return res
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

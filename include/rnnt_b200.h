@@ -142,6 +142,24 @@ RNNTB200_API int rnntb200_joint_at_bwd(const float* enc, const float* dec, const
                           const float* beta, const float* costs, const float* grad_costs,
                           float* d_enc, float* d_dec, float* d_weight, float* d_bias, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Stage entry points: the per-cell front-ends alone (no sweep), so that each kernel can be
+ * timed and profiled by itself (bench.py's per-kernel roofline) or composed by a caller that
+ * batches several front-ends before one sweep.  Same arguments as the *_fwd calls above;
+ * outputs: lp2 [B,T,U1] float2 and lse [B,T,U1]. */
+RNNTB200_API int rnntb200_dense_logprobs(const void* logits, int dtype, const int32_t* labels,
+                            const int32_t* act_lens, const int32_t* label_lens, int B, int T,
+                            int U1, int V, int blank, void* lp2, float* lse, void* stream);
+
+RNNTB200_API int rnntb200_joint_cg_logprobs(const float* penc, const float* pdec, const int32_t* labels,
+                               const int32_t* act_lens, const int32_t* label_lens, int B, int T,
+                               int U1, int V, int blank, void* lp2, float* lse, void* stream);
+
+RNNTB200_API int rnntb200_joint_at_logprobs(const float* enc, const float* dec, const float* weight,
+                               const float* bias, int gemm, const int32_t* labels,
+                               const int32_t* act_lens, const int32_t* label_lens, int B, int T,
+                               int U1, int V, int H, int blank, void* lp2, float* lse, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,6 +13,10 @@ inline bool bad_dtype(int dtype) {
     return dtype != RNNTB200_F32 && dtype != RNNTB200_F16 && dtype != RNNTB200_BF16;
 }
 
+inline bool bad_gemm(int gemm) {
+    return gemm != RNNTB200_GEMM_FP32 && gemm != RNNTB200_GEMM_BF16 && gemm != RNNTB200_GEMM_TF32X3;
+}
+
 }  // namespace
 
 extern "C" {
@@ -103,6 +107,72 @@ RNNTB200_API int rnntb200_joint_cg_bwd(const float* penc, const float* pdec, con
     return launch_cg_grad(penc, pdec, labels, act_lens, label_lens, B, T, U1, V, blank, lse, alpha,
                           beta, costs, grad_costs, d_penc, d_pdec, deterministic, workspace,
                           workspace_bytes, (cudaStream_t)stream);
+}
+
+RNNTB200_API int rnntb200_joint_at_fwd(const float* enc, const float* dec, const float* weight,
+                          const float* bias, int gemm, const int32_t* labels,
+                          const int32_t* act_lens, const int32_t* label_lens, int B, int T, int U1,
+                          int V, int H, int blank, float* costs, void* lp2, float* lse, float* alpha,
+                          float* beta, void* stream) {
+    if (bad_shape(B, T, U1, V, blank) || H <= 0 || bad_gemm(gemm)) return RNNTB200_STATUS_INVALID_VALUE;
+    if (B > 0 && (!enc || !dec || !weight || !bias || !act_lens || !label_lens || !costs || !lp2 ||
+                  !lse || !alpha || !beta))
+        return RNNTB200_STATUS_INVALID_VALUE;
+    if (B > 0 && U1 > 1 && !labels) return RNNTB200_STATUS_INVALID_VALUE;
+    cudaStream_t s = (cudaStream_t)stream;
+    int st = launch_at_lse(enc, dec, weight, bias, gemm, labels, act_lens, label_lens, B, T, U1, V, H,
+                           blank, (float2*)lp2, lse, s);
+    if (st != RNNTB200_STATUS_SUCCESS) return st;
+    return launch_lattice_sweep((const float2*)lp2, act_lens, label_lens, B, T, U1, alpha, beta,
+                                costs, nullptr, s);
+}
+
+RNNTB200_API int rnntb200_joint_at_bwd(const float* enc, const float* dec, const float* weight,
+                          const float* bias, int gemm, const int32_t* labels,
+                          const int32_t* act_lens, const int32_t* label_lens, int B, int T, int U1,
+                          int V, int H, int blank, const float* lse, const float* alpha,
+                          const float* beta, const float* costs, const float* grad_costs,
+                          float* d_enc, float* d_dec, float* d_weight, float* d_bias, void* stream) {
+    if (bad_shape(B, T, U1, V, blank) || H <= 0 || bad_gemm(gemm)) return RNNTB200_STATUS_INVALID_VALUE;
+    if (B > 0 && (!enc || !dec || !weight || !bias || !act_lens || !label_lens || !lse || !alpha ||
+                  !beta || !costs || !grad_costs || !d_enc || !d_dec || !d_weight || !d_bias))
+        return RNNTB200_STATUS_INVALID_VALUE;
+    if (B > 0 && U1 > 1 && !labels) return RNNTB200_STATUS_INVALID_VALUE;
+    return launch_at_grad(enc, dec, weight, bias, gemm, labels, act_lens, label_lens, B, T, U1, V, H,
+                          blank, lse, alpha, beta, costs, grad_costs, d_enc, d_dec, d_weight, d_bias,
+                          (cudaStream_t)stream);
+}
+
+RNNTB200_API int rnntb200_dense_logprobs(const void* logits, int dtype, const int32_t* labels,
+                            const int32_t* act_lens, const int32_t* label_lens, int B, int T,
+                            int U1, int V, int blank, void* lp2, float* lse, void* stream) {
+    if (bad_shape(B, T, U1, V, blank) || bad_dtype(dtype)) return RNNTB200_STATUS_INVALID_VALUE;
+    if (B > 0 && (!logits || !act_lens || !label_lens || !lp2 || !lse)) return RNNTB200_STATUS_INVALID_VALUE;
+    if (B > 0 && U1 > 1 && !labels) return RNNTB200_STATUS_INVALID_VALUE;
+    return launch_dense_lse(logits, dtype, labels, act_lens, label_lens, B, T, U1, V, blank,
+                            (float2*)lp2, lse, (cudaStream_t)stream);
+}
+
+RNNTB200_API int rnntb200_joint_cg_logprobs(const float* penc, const float* pdec, const int32_t* labels,
+                               const int32_t* act_lens, const int32_t* label_lens, int B, int T,
+                               int U1, int V, int blank, void* lp2, float* lse, void* stream) {
+    if (bad_shape(B, T, U1, V, blank)) return RNNTB200_STATUS_INVALID_VALUE;
+    if (B > 0 && (!penc || !pdec || !act_lens || !label_lens || !lp2 || !lse)) return RNNTB200_STATUS_INVALID_VALUE;
+    if (B > 0 && U1 > 1 && !labels) return RNNTB200_STATUS_INVALID_VALUE;
+    return launch_cg_lse(penc, pdec, labels, act_lens, label_lens, B, T, U1, V, blank, (float2*)lp2,
+                         lse, (cudaStream_t)stream);
+}
+
+RNNTB200_API int rnntb200_joint_at_logprobs(const float* enc, const float* dec, const float* weight,
+                               const float* bias, int gemm, const int32_t* labels,
+                               const int32_t* act_lens, const int32_t* label_lens, int B, int T,
+                               int U1, int V, int H, int blank, void* lp2, float* lse, void* stream) {
+    if (bad_shape(B, T, U1, V, blank) || H <= 0 || bad_gemm(gemm)) return RNNTB200_STATUS_INVALID_VALUE;
+    if (B > 0 && (!enc || !dec || !weight || !bias || !act_lens || !label_lens || !lp2 || !lse))
+        return RNNTB200_STATUS_INVALID_VALUE;
+    if (B > 0 && U1 > 1 && !labels) return RNNTB200_STATUS_INVALID_VALUE;
+    return launch_at_lse(enc, dec, weight, bias, gemm, labels, act_lens, label_lens, B, T, U1, V, H,
+                         blank, (float2*)lp2, lse, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -95,4 +95,13 @@ int launch_cg_grad(const float* penc, const float* pdec, const int32_t* labels, 
                    size_t workspace_bytes, cudaStream_t stream);
 size_t cg_grad_workspace_bytes(int B, int T, int U1, int V, int deterministic);
 
+int launch_at_lse(const float* enc, const float* dec, const float* weight, const float* bias, int gemm,
+                  const int32_t* labels, const int32_t* act_lens, const int32_t* label_lens, int B,
+                  int T, int U1, int V, int H, int blank, float2* lp2, float* lse, cudaStream_t stream);
+int launch_at_grad(const float* enc, const float* dec, const float* weight, const float* bias, int gemm,
+                   const int32_t* labels, const int32_t* act_lens, const int32_t* label_lens, int B,
+                   int T, int U1, int V, int H, int blank, const float* lse, const float* alpha,
+                   const float* beta, const float* costs, const float* grad_costs, float* d_enc,
+                   float* d_dec, float* d_weight, float* d_bias, cudaStream_t stream);
+
 }  // namespace rnntb200

@@ -1,0 +1,18 @@
+#!/bin/bash
+# One GPU-box visit: parity tests, bench, ncu launch list + one full capture of the named kernel.
+# usage: scripts/gpu_check.sh <tag> [kernel-regex] [extra bench args]
+TAG=${1:-r1}; KREGEX=${2:-lattice_sweep}; shift 2 || true
+OUT=gpurun_out; mkdir -p $OUT
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > $OUT/${TAG}_gpu.csv 2>&1
+python -m pytest tests -m gpu -q --timeout 600 > $OUT/${TAG}_pytest.log 2>&1; echo "pytest exit $?" >> $OUT/${TAG}_pytest.log
+tail -15 $OUT/${TAG}_pytest.log
+python bench.py --steps 100 --warmup 10 "$@" > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo "bench exit $?"
+tail -c 3000 $OUT/${TAG}_bench.json; tail -5 $OUT/${TAG}_bench.err
+python bench.py --steps 50 --warmup 5 --eager --no-cpu-baseline "$@" > $OUT/${TAG}_bench_eager.json 2> $OUT/${TAG}_bench_eager.err
+python bench.py --steps 3 --warmup 3 --no-cpu-baseline "$@" > $OUT/${TAG}_plain.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/${TAG}_launches.csv \
+    python bench.py --steps 3 --warmup 3 --no-cpu-baseline "$@" > $OUT/${TAG}_ncu_launches.log 2>&1
+python bench.py --steps 3 --warmup 3 --no-cpu-baseline "$@" > $OUT/${TAG}_plain2.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:$KREGEX -s 6 -c 2 -f -o $OUT/${TAG}_prof \
+    python bench.py --steps 3 --warmup 3 --no-cpu-baseline "$@" > $OUT/${TAG}_ncu_full.log 2>&1
+ls -la $OUT | tail -20

@@ -1,0 +1,147 @@
+"""GPU parity: fused joint + RNN-T loss in the reference's own joint (concat -> GELU(tanh) ->
+Linear(2H -> V), networks/transducer.py:54-71), evaluated in factorised form without ever forming
+the [B,T,U1,V] logits.  Checked against
+  - golden vectors produced by the reference's JointNet.joint + torchaudio CPU loss + autograd
+    (oracle/gen_golden.py),
+  - the CPU restatement oracle/joint_ref.py + oracle/warp_cpu.c on seeded inputs,
+  - our own dense path at BASELINE cfg-2 size (size-independent cross-check).
+Tolerances: loss 1e-5 relative, gradients 1e-4 absolute (north_star).
+"""
+import numpy as np
+import pytest
+import torch
+
+import rnntransducer_b200 as rb
+from conftest import load_golden
+from oracle import joint_ref
+from rnntransducer_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+
+LOSS_RTOL = 1e-5
+GRAD_ATOL = 1e-4
+
+
+def to_cuda(d):
+    return {k: (torch.from_numpy(np.ascontiguousarray(v)) if isinstance(v, np.ndarray) else v).cuda()
+            for k, v in d.items() if isinstance(v, (np.ndarray, torch.Tensor)) and np.ndim(v) > 0}
+
+
+def fused_step(d, reduction="mean", deterministic=False, mode="concat_gelu", gemm="fp32"):
+    t = {k: d[k].clone().requires_grad_(True) for k in ("enc", "dec", "weight", "bias")}
+    costs = rb.joint_rnnt_costs(t["enc"], t["dec"], t["weight"], t["bias"], d["labels"], d["act_lens"],
+                                d["label_lens"], 0, mode, gemm, deterministic)
+    loss = {"mean": costs.mean(), "sum": costs.sum()}[reduction]
+    loss.backward()
+    out = dict(costs=costs.detach().cpu().numpy(), loss=float(loss))
+    out.update({"d_" + k: v.grad.cpu().numpy() for k, v in t.items()})
+    return out
+
+
+@pytest.mark.parametrize("deterministic", [False, True])
+@pytest.mark.parametrize("name", ["joint_small_full.npz", "joint_small_ragged.npz"])
+def test_fused_matches_reference_jointnet_golden(cuda_lib, name, deterministic):
+    g = load_golden(name)
+    r = fused_step(to_cuda(g), deterministic=deterministic)
+    np.testing.assert_allclose(r["costs"], g["costs"], rtol=LOSS_RTOL)
+    np.testing.assert_allclose(r["loss"], float(g["loss"]), rtol=LOSS_RTOL)
+    for k in ("d_enc", "d_dec", "d_weight", "d_bias"):
+        np.testing.assert_allclose(r[k], g[k], atol=GRAD_ATOL, err_msg=k)
+
+
+@pytest.mark.parametrize("name,ragged", [("joint_cfg1.npz", False), ("joint_cfg1_ragged.npz", True)])
+def test_fused_cfg1_matches_reference_golden(cuda_lib, name, ragged):
+    """BASELINE cfg 1 (B=4,T=100,U=20,V=73,H=320): inputs regenerated from the seed, outputs are
+    the sub-sampled reference results stored by gen_golden.py."""
+    g = load_golden(name)
+    c = synthetic.CONFIGS[1]
+    d = synthetic.make_batch(c["B"], c["T"], c["U"], c["V"], c["H"], ragged=ragged, seed=int(g["seed"]),
+                             device="cuda")
+    r = fused_step(d)
+    st, sh = int(g["stride_t"]), int(g["stride_h"])
+    np.testing.assert_allclose(r["costs"], g["costs"], rtol=LOSS_RTOL)
+    np.testing.assert_allclose(r["d_bias"], g["d_bias"], atol=GRAD_ATOL)
+    np.testing.assert_allclose(r["d_weight"][:, ::sh], g["d_weight"], atol=GRAD_ATOL)
+    np.testing.assert_allclose(r["d_enc"][:, ::st, ::sh], g["d_enc"], atol=GRAD_ATOL)
+    np.testing.assert_allclose(r["d_dec"][:, :, ::sh], g["d_dec"], atol=GRAD_ATOL)
+
+
+@pytest.mark.parametrize("shape", [(3, 33, 9, 73, 48), (2, 20, 40, 130, 24), (5, 8, 3, 5, 16)])
+def test_fused_matches_cpu_restatement(cuda_lib, oracle_lib, shape):
+    B, T, U, V, H = shape
+    d = synthetic.make_batch(B, T, U, V, H, ragged=True, seed=77 + V)
+    if B >= 3:
+        d["label_lens"][1] = 0
+        d["labels"][1] = 0
+        d["act_lens"][2] = 1
+    ref = joint_ref.joint_loss_fwd_bwd(d["enc"], d["dec"], d["weight"], d["bias"], d["labels"].numpy(),
+                                       d["act_lens"].numpy(), d["label_lens"].numpy(), 0, "mean")
+    for det in (False, True):
+        r = fused_step({k: v.cuda() for k, v in d.items()}, deterministic=det)
+        np.testing.assert_allclose(r["costs"], ref["costs"], rtol=LOSS_RTOL)
+        for k in ("d_enc", "d_dec", "d_weight", "d_bias"):
+            np.testing.assert_allclose(r[k], ref[k], atol=GRAD_ATOL, err_msg=k)
+
+
+def test_deterministic_mode_is_bit_reproducible(cuda_lib):
+    d = synthetic.make_batch(4, 64, 17, 73, 32, ragged=True, seed=5, device="cuda")
+    a = fused_step(d, deterministic=True)
+    b = fused_step(d, deterministic=True)
+    for k in ("costs", "d_enc", "d_dec", "d_weight", "d_bias"):
+        assert np.array_equal(a[k], b[k]), k
+
+
+def test_full_size_cfg2_fused_vs_dense_path(cuda_lib):
+    """BASELINE cfg 2 at full size: the fused path (no logits in HBM) against our dense-logits path
+    fed by the eager joint (303 MB logits), plus size-independent properties."""
+    c = synthetic.CONFIGS[2]
+    d = synthetic.make_batch(c["B"], c["T"], c["U"], c["V"], c["H"], ragged=True, seed=1236, device="cuda")
+    fused = fused_step(d)
+    t = {k: d[k].clone().requires_grad_(True) for k in ("enc", "dec", "weight", "bias")}
+    logits = rb.joint_dense(t["enc"], t["dec"], t["weight"], t["bias"])
+    costs = rb.rnnt_costs(logits, d["labels"], d["act_lens"], d["label_lens"])
+    costs.mean().backward()
+    np.testing.assert_allclose(fused["costs"], costs.detach().cpu().numpy(), rtol=LOSS_RTOL)
+    for k in ("enc", "dec", "weight", "bias"):
+        np.testing.assert_allclose(fused["d_" + k], t[k].grad.cpu().numpy(), atol=GRAD_ATOL, err_msg=k)
+    # sum_v g = 0 per cell  =>  the bias gradient sums to zero
+    assert abs(float(fused["d_bias"].sum())) < 1e-4
+    # frames past an utterance's length receive exactly zero gradient
+    al = d["act_lens"].cpu().numpy()
+    for b in range(c["B"]):
+        assert np.all(fused["d_enc"][b, al[b]:] == 0)
+
+
+def test_jointnet_module_end_to_end(cuda_lib):
+    """The reference call shape (model.py:49,56-57): logits = net(...); loss = RNNTLoss(...)(logits,
+    targets, tensor_audio_lengths, target_lengths); loss.backward().  Fused (lazy handle) against
+    fused=False (dense logits into the same loss)."""
+    g = load_golden("jointnet_fwd.npz")
+    ep = dict(input_size=8, hidden_size=12, output_size=16, num_layers=2, rnn_type="gru",
+              dropout=0.0, bidirectional=True)
+    dp = dict(embedding_size=11, pad_token_id=0, hidden_size=12, output_size=16, num_layers=2,
+              rnn_type="lstm", dropout=0.0)
+    sd = {k[len("sd__"):]: torch.from_numpy(v) for k, v in g.items() if k.startswith("sd__")}
+    audio = torch.from_numpy(g["audio"]).cuda()
+    texts = torch.from_numpy(g["texts"]).cuda()
+    audio_lengths, text_lengths = g["audio_lengths"].tolist(), g["text_lengths"].tolist()
+    targets = texts[:, 1:].to(torch.int32).contiguous()
+    act_lens = torch.tensor(audio_lengths, dtype=torch.int32, device="cuda")
+    label_lens = torch.tensor([n - 1 for n in text_lengths], dtype=torch.int32, device="cuda")
+    loss_fn = rb.RNNTLoss(blank=0, reduction="mean")
+    results = {}
+    for fused in (True, False):
+        net = rb.JointNet(dict(ep), dict(dp), 11, fused=fused).cuda().train()
+        net.load_state_dict(sd)
+        logits = net(audio, audio_lengths, texts, text_lengths)
+        assert isinstance(logits, rb.JointLogits) == fused
+        assert tuple(logits.shape) == (3, 14, 5, 11)
+        loss = loss_fn(logits, targets, act_lens, label_lens)
+        assert loss.shape == (1,)
+        loss.backward()
+        results[fused] = (float(loss), {n: p.grad.clone() for n, p in net.named_parameters()})
+        if fused:  # the handle still materialises to the reference logits when asked
+            np.testing.assert_allclose(logits.materialize().detach().cpu().numpy(), g["logits"], atol=1e-5)
+    assert abs(results[True][0] - results[False][0]) < 1e-5 * abs(results[False][0])
+    for n, gr in results[False][1].items():
+        torch.testing.assert_close(results[True][1][n], gr, atol=1e-4, rtol=1e-3, msg=n)
