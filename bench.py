@@ -412,7 +412,8 @@ def per_kernel(lib, st, mode, gemm, det, B, T, U1, V, H, cells, flush_buf, iters
     stream = torch.cuda.current_stream().cuda_stream
     p = lambda t: t.data_ptr()
     lp2 = torch.empty(B, T, U1, 2, **f32)
-    lse, alpha, beta = (torch.empty(B, T, U1, **f32) for _ in range(3))
+    lse = torch.empty(B, T, U1, **f32)
+    alpha, beta = (torch.empty(B, T, U1, device=dev, dtype=torch.int32) for _ in range(2))  # Q16 planes
     costs, gcosts = torch.empty(B, **f32), torch.full((B,), 1.0 / B, **f32)
     lab, al, ll = st["labels"], st["act_lens"], st["label_lens"]
     res = {}
@@ -453,7 +454,7 @@ def per_kernel(lib, st, mode, gemm, det, B, T, U1, V, H, cells, flush_buf, iters
                 p(lp2), p(al), p(ll), B, T, U1, p(alpha), p(beta), p(costs), None, stream)), 24 * cells)
             bench("cg_grad_kernel", lambda: _lib.check(lib.rnntb200_joint_cg_bwd(
                 p(penc), p(pdec), p(lab), p(al), p(ll), B, T, U1, V, 0, p(lse), p(alpha), p(beta),
-                p(costs), p(gcosts), p(d_penc), p(d_pdec), int(det), p(ws), ws_bytes, stream)),
+                p(gcosts), p(d_penc), p(d_pdec), int(det), p(ws), ws_bytes, stream)),
                 12 * cells + 2 * io)
         else:
             d_enc, d_dec = torch.empty_like(enc), torch.empty_like(dec)
@@ -465,8 +466,8 @@ def per_kernel(lib, st, mode, gemm, det, B, T, U1, V, H, cells, flush_buf, iters
             bench("lattice_sweep_kernel", lambda: _lib.check(lib.rnntb200_lattice_sweep(
                 p(lp2), p(al), p(ll), B, T, U1, p(alpha), p(beta), p(costs), None, stream)), 24 * cells)
             bench("at_grad_kernel", lambda: _lib.check(lib.rnntb200_joint_at_bwd(
-                p(enc), p(dec), p(w), p(b), gemm, p(lab), p(al), p(ll), B, T, U1, V, H, 0, p(lse),
-                p(alpha), p(beta), p(costs), p(gcosts), p(d_enc), p(d_dec), p(d_w), p(d_b), stream)),
+                p(enc), p(dec), p(w), p(b), gemm, p(lab), p(al), p(ll), B, T, U1, V, H, 0, p(lp2), p(lse),
+                p(alpha), p(beta), p(gcosts), p(d_enc), p(d_dec), p(d_w), p(d_b), stream)),
                 12 * cells + 2 * io)
             for k in ("at_lse_kernel", "at_grad_kernel"):
                 passes = 1 if k == "at_lse_kernel" else 3  # fwd | recompute + dgrad + wgrad

@@ -19,7 +19,13 @@
  *     and returns (no host synchronisation, CUDA-graph capturable);
  *   - lengths stay on the device: act_lens[B], label_lens[B] are int32 device
  *     arrays and are never read by the host (reference README.md:65 complaint);
- *   - lattice planes are [B, T, U1] row-major fp32 with U1 = max_label_len + 1;
+ *   - lattice planes are [B, T, U1] row-major, 4 bytes per cell, U1 = max_label_len + 1:
+ *       lp2   float2  (log p(blank|t,u), log p(y_{u+1}|t,u)), natural log
+ *       lse   float   log-sum-exp of the cell's logits, natural log
+ *       alpha, beta   rnntb200_q16_t: base-2 log in Q16 fixed point (int32), i.e.
+ *                     ln(alpha) = q * ln(2) / 65536.  Fixed point keeps 1.5e-5 resolution at
+ *                     any magnitude, so alpha + beta - log P(y|x) is formed exactly in integers
+ *                     by the gradient kernels; beta[b,0,0] is log2 P(y|x) of utterance b.
  *     entries outside an utterance's (T_b, U_b + 1) box are left untouched by
  *     forward calls and are written as exact zeros in gradient outputs;
  *   - return value: rnntb200_status_t, modelled on warp-transducer's
@@ -55,6 +61,9 @@ typedef enum {
 /* element type of logits / activations handed in by the caller */
 typedef enum { RNNTB200_F32 = 0, RNNTB200_F16 = 1, RNNTB200_BF16 = 2 } rnntb200_dtype_t;
 
+/* alpha / beta plane element: log2(value) * 65536, rounded (see conventions above) */
+typedef int32_t rnntb200_q16_t;
+
 /* joint function.  CONCAT_GELU is the reference's joint (transducer.py:64-69):
  *   logits = fc(gelu_tanh([enc_t ; dec_u])), fc.weight [V, He+Hd].
  * ADD_TANH is the north_star's alternative: logits = fc(tanh(enc_t + dec_u)), fc.weight [V, H]
@@ -74,13 +83,13 @@ RNNTB200_API const char* rnntb200_status_string(int status);
 /* ------------------------------------------------------------------------------------------
  * Lattice sweeps (alpha and beta in ONE launch, one CTA per utterance and direction).
  *   lp2   [B,T,U1] float2 = (log p(blank | t,u), log p(y_{u+1} | t,u)), natural log
- *   alpha, beta [B,T,U1] fp32 out (natural log);  costs[B] = -beta(0,0) = -log P(y|x)
- *   ll_alpha[B] optional (may be NULL): alpha(T-1,U) + lp_blank(T-1,U), a cross-check of costs.
+ *   alpha, beta [B,T,U1] Q16 out;  costs[B] = -ln beta(0,0) = -log P(y|x), fp32 natural log
+ *   ll_alpha[B] optional (may be NULL): ln(alpha(T-1,U) p_blank(T-1,U)), a cross-check of -costs.
  * Replaces warp-transducer compute_alphas/compute_betas and torchaudio's
  * ComputeAlphasBetasCosts.  Requires U1 <= 1024. */
 RNNTB200_API int rnntb200_lattice_sweep(const void* lp2, const int32_t* act_lens, const int32_t* label_lens,
-                           int B, int T, int U1, float* alpha, float* beta, float* costs,
-                           float* ll_alpha, void* stream);
+                           int B, int T, int U1, rnntb200_q16_t* alpha, rnntb200_q16_t* beta,
+                           float* costs, float* ll_alpha, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Dense-logits RNNTLoss (compat path: `loss(logits, labels, act_lens, label_lens)`, model.py:57).
@@ -91,12 +100,12 @@ RNNTB200_API int rnntb200_lattice_sweep(const void* lp2, const int32_t* act_lens
 RNNTB200_API int rnntb200_loss_dense_fwd(const void* logits, int dtype, const int32_t* labels,
                             const int32_t* act_lens, const int32_t* label_lens, int B, int T,
                             int U1, int V, int blank, float* costs, void* lp2, float* lse,
-                            float* alpha, float* beta, void* stream);
+                            rnntb200_q16_t* alpha, rnntb200_q16_t* beta, void* stream);
 
 RNNTB200_API int rnntb200_loss_dense_bwd(const void* logits, int dtype, const int32_t* labels,
                             const int32_t* act_lens, const int32_t* label_lens, int B, int T,
-                            int U1, int V, int blank, const float* lse, const float* alpha,
-                            const float* beta, const float* costs, const float* grad_costs,
+                            int U1, int V, int blank, const float* lse, const rnntb200_q16_t* alpha,
+                            const rnntb200_q16_t* beta, const float* grad_costs,
                             void* grad_logits, void* stream);
 
 /* ------------------------------------------------------------------------------------------
@@ -112,16 +121,17 @@ RNNTB200_API int rnntb200_loss_dense_bwd(const void* logits, int dtype, const in
  *      fp32 atomics for d_pdec. */
 RNNTB200_API int rnntb200_joint_cg_fwd(const float* penc, const float* pdec, const int32_t* labels,
                           const int32_t* act_lens, const int32_t* label_lens, int B, int T, int U1,
-                          int V, int blank, float* costs, void* lp2, float* lse, float* alpha,
-                          float* beta, void* stream);
+                          int V, int blank, float* costs, void* lp2, float* lse,
+                          rnntb200_q16_t* alpha, rnntb200_q16_t* beta, void* stream);
 
 RNNTB200_API size_t rnntb200_joint_cg_bwd_workspace_bytes(int B, int T, int U1, int V, int deterministic);
 
 RNNTB200_API int rnntb200_joint_cg_bwd(const float* penc, const float* pdec, const int32_t* labels,
                           const int32_t* act_lens, const int32_t* label_lens, int B, int T, int U1,
-                          int V, int blank, const float* lse, const float* alpha, const float* beta,
-                          const float* costs, const float* grad_costs, float* d_penc, float* d_pdec,
-                          int deterministic, void* workspace, size_t workspace_bytes, void* stream);
+                          int V, int blank, const float* lse, const rnntb200_q16_t* alpha,
+                          const rnntb200_q16_t* beta, const float* grad_costs, float* d_penc,
+                          float* d_pdec, int deterministic, void* workspace, size_t workspace_bytes,
+                          void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Fused joint + loss, ADD_TANH mode: logits(t,u,:) = tanh(enc_t + dec_u) W^T + bias, the one
@@ -132,15 +142,16 @@ RNNTB200_API int rnntb200_joint_cg_bwd(const float* penc, const float* pdec, con
 RNNTB200_API int rnntb200_joint_at_fwd(const float* enc, const float* dec, const float* weight,
                           const float* bias, int gemm, const int32_t* labels,
                           const int32_t* act_lens, const int32_t* label_lens, int B, int T, int U1,
-                          int V, int H, int blank, float* costs, void* lp2, float* lse, float* alpha,
-                          float* beta, void* stream);
+                          int V, int H, int blank, float* costs, void* lp2, float* lse,
+                          rnntb200_q16_t* alpha, rnntb200_q16_t* beta, void* stream);
 
 RNNTB200_API int rnntb200_joint_at_bwd(const float* enc, const float* dec, const float* weight,
                           const float* bias, int gemm, const int32_t* labels,
                           const int32_t* act_lens, const int32_t* label_lens, int B, int T, int U1,
-                          int V, int H, int blank, const float* lse, const float* alpha,
-                          const float* beta, const float* costs, const float* grad_costs,
-                          float* d_enc, float* d_dec, float* d_weight, float* d_bias, void* stream);
+                          int V, int H, int blank, const void* lp2, const float* lse,
+                          const rnntb200_q16_t* alpha, const rnntb200_q16_t* beta,
+                          const float* grad_costs, float* d_enc, float* d_dec, float* d_weight,
+                          float* d_bias, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Stage entry points: the per-cell front-ends alone (no sweep), so that each kernel can be

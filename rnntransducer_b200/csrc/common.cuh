@@ -62,6 +62,12 @@ __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2hal
 template <>
 __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
+// alpha / beta planes hold Q16 fixed-point base-2 logs (see lattice.cu).  log2 of the lattice
+// occupancy ratio alpha * beta / P(y|x), formed exactly in integers before going to float.
+__device__ __forceinline__ float q16_log2_ratio(int aq, int bq, int llq) {
+    return (float)((long long)aq + (long long)bq - (long long)llq) * (1.0f / 65536.0f);
+}
+
 inline int status_from_cuda(cudaError_t e) {
     if (e == cudaSuccess) return RNNTB200_STATUS_SUCCESS;
     if (e == cudaErrorInvalidValue || e == cudaErrorInvalidConfiguration) return RNNTB200_STATUS_INVALID_VALUE;
@@ -74,7 +80,7 @@ inline int launch_status() { return status_from_cuda(cudaGetLastError()); }
 
 // ---- internal launchers (defined in the .cu files, called from api.cu) ------------------------
 int launch_lattice_sweep(const float2* lp2, const int32_t* act_lens, const int32_t* label_lens, int B,
-                         int T, int U1, float* alpha, float* beta, float* costs, float* ll_alpha,
+                         int T, int U1, int32_t* alpha, int32_t* beta, float* costs, float* ll_alpha,
                          cudaStream_t stream);
 
 int launch_dense_lse(const void* logits, int dtype, const int32_t* labels, const int32_t* act_lens,
@@ -82,7 +88,7 @@ int launch_dense_lse(const void* logits, int dtype, const int32_t* labels, const
                      float* lse, cudaStream_t stream);
 int launch_dense_grad(const void* logits, int dtype, const int32_t* labels, const int32_t* act_lens,
                       const int32_t* label_lens, int B, int T, int U1, int V, int blank,
-                      const float* lse, const float* alpha, const float* beta, const float* costs,
+                      const float* lse, const int32_t* alpha, const int32_t* beta,
                       const float* grad_costs, void* grad_logits, cudaStream_t stream);
 
 int launch_cg_lse(const float* penc, const float* pdec, const int32_t* labels, const int32_t* act_lens,
@@ -90,7 +96,7 @@ int launch_cg_lse(const float* penc, const float* pdec, const int32_t* labels, c
                   float* lse, cudaStream_t stream);
 int launch_cg_grad(const float* penc, const float* pdec, const int32_t* labels, const int32_t* act_lens,
                    const int32_t* label_lens, int B, int T, int U1, int V, int blank, const float* lse,
-                   const float* alpha, const float* beta, const float* costs, const float* grad_costs,
+                   const int32_t* alpha, const int32_t* beta, const float* grad_costs,
                    float* d_penc, float* d_pdec, int deterministic, void* workspace,
                    size_t workspace_bytes, cudaStream_t stream);
 size_t cg_grad_workspace_bytes(int B, int T, int U1, int V, int deterministic);
@@ -100,8 +106,8 @@ int launch_at_lse(const float* enc, const float* dec, const float* weight, const
                   int T, int U1, int V, int H, int blank, float2* lp2, float* lse, cudaStream_t stream);
 int launch_at_grad(const float* enc, const float* dec, const float* weight, const float* bias, int gemm,
                    const int32_t* labels, const int32_t* act_lens, const int32_t* label_lens, int B,
-                   int T, int U1, int V, int H, int blank, const float* lse, const float* alpha,
-                   const float* beta, const float* costs, const float* grad_costs, float* d_enc,
+                   int T, int U1, int V, int H, int blank, const float2* lp2, const float* lse,
+                   const int32_t* alpha, const int32_t* beta, const float* grad_costs, float* d_enc,
                    float* d_dec, float* d_weight, float* d_bias, cudaStream_t stream);
 
 }  // namespace rnntb200

@@ -125,9 +125,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32)
 dense_grad_kernel(const T* __restrict__ logits, const int32_t* __restrict__ labels,
                   const int32_t* __restrict__ act_lens, const int32_t* __restrict__ label_lens,
                   long long cells, int T_, int U1, int V, int blank, const float* __restrict__ lse,
-                  const float* __restrict__ alpha, const float* __restrict__ beta,
-                  const float* __restrict__ costs, const float* __restrict__ grad_costs,
-                  T* __restrict__ grad) {
+                  const int32_t* __restrict__ alpha, const int32_t* __restrict__ beta,
+                  const float* __restrict__ grad_costs, T* __restrict__ grad) {
     const int lane = threadIdx.x & 31;
     const long long warp = (long long)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
     const long long c0 = warp * kRows;
@@ -145,19 +144,19 @@ dense_grad_kernel(const T* __restrict__ logits, const int32_t* __restrict__ labe
         }
         const T* row = logits + c * V;
         const int Tb = __ldg(act_lens + k.b), Ub = __ldg(label_lens + k.b);
-        const float a = alpha[c], be = beta[c], z = lse[c];
-        const float cost = costs[k.b], gc = grad_costs[k.b];
-        const float c_all = (a + be + cost - z) * kLog2e;  // log2 of occupancy / partition
+        const int aq = alpha[c], llq = beta[(long long)k.b * T_ * U1];  // beta(0,0) = log2 P(y|x)
+        const float z2 = lse[c] * kLog2e, gc = grad_costs[k.b];
+        const float c_all = q16_log2_ratio(aq, beta[c], llq) - z2;  // log2(occupancy / partition)
         // corrections at the blank and label columns
         float corr_b = 0.f, corr_l = 0.f;
         int y = -1;
-        const float lb = to_f32<T>(row[blank]) - z;
-        if (k.t < Tb - 1) corr_b = fast_ex2((a + lb + beta[c + U1] + cost) * kLog2e);
-        else if (k.u == Ub) corr_b = fast_ex2((a + lb + cost) * kLog2e);
+        const float lb2 = to_f32<T>(row[blank]) * kLog2e - z2;
+        if (k.t < Tb - 1) corr_b = fast_ex2(q16_log2_ratio(aq, beta[c + U1], llq) + lb2);
+        else if (k.u == Ub) corr_b = fast_ex2(q16_log2_ratio(aq, 0, llq) + lb2);
         if (k.u < Ub) {
             y = __ldg(labels + (size_t)k.b * (U1 - 1) + k.u);
-            const float ll = to_f32<T>(row[y]) - z;
-            corr_l = fast_ex2((a + ll + beta[c + 1] + cost) * kLog2e);
+            const float ll2 = to_f32<T>(row[y]) * kLog2e - z2;
+            corr_l = fast_ex2(q16_log2_ratio(aq, beta[c + 1], llq) + ll2);
         }
         for (int v = lane; v < V; v += 32) {
             float gv = fast_ex2(fmaf(to_f32<T>(row[v]), kLog2e, c_all));
@@ -191,13 +190,13 @@ int launch_lse_t(const T* logits, const int32_t* labels, const int32_t* act_lens
 template <typename T>
 int launch_grad_t(const T* logits, const int32_t* labels, const int32_t* act_lens,
                   const int32_t* label_lens, int B, int T_, int U1, int V, int blank, const float* lse,
-                  const float* alpha, const float* beta, const float* costs, const float* grad_costs,
+                  const int32_t* alpha, const int32_t* beta, const float* grad_costs,
                   T* grad, cudaStream_t stream) {
     const long long cells = (long long)B * T_ * U1;
     const long long warps = (cells + kRows - 1) / kRows;
     const unsigned grid = (unsigned)((warps + kWarpsPerCta - 1) / kWarpsPerCta);
     dense_grad_kernel<T><<<grid, kWarpsPerCta * 32, 0, stream>>>(
-        logits, labels, act_lens, label_lens, cells, T_, U1, V, blank, lse, alpha, beta, costs,
+        logits, labels, act_lens, label_lens, cells, T_, U1, V, blank, lse, alpha, beta,
         grad_costs, grad);
     return launch_status();
 }
@@ -221,16 +220,16 @@ int launch_dense_lse(const void* logits, int dtype, const int32_t* labels, const
 
 int launch_dense_grad(const void* logits, int dtype, const int32_t* labels, const int32_t* act_lens,
                       const int32_t* label_lens, int B, int T, int U1, int V, int blank,
-                      const float* lse, const float* alpha, const float* beta, const float* costs,
+                      const float* lse, const int32_t* alpha, const int32_t* beta,
                       const float* grad_costs, void* grad_logits, cudaStream_t stream) {
     if ((long long)B * T * U1 == 0) return RNNTB200_STATUS_SUCCESS;
     switch (dtype) {
         case RNNTB200_F32:
-            return launch_grad_t((const float*)logits, labels, act_lens, label_lens, B, T, U1, V, blank, lse, alpha, beta, costs, grad_costs, (float*)grad_logits, stream);
+            return launch_grad_t((const float*)logits, labels, act_lens, label_lens, B, T, U1, V, blank, lse, alpha, beta, grad_costs, (float*)grad_logits, stream);
         case RNNTB200_F16:
-            return launch_grad_t((const __half*)logits, labels, act_lens, label_lens, B, T, U1, V, blank, lse, alpha, beta, costs, grad_costs, (__half*)grad_logits, stream);
+            return launch_grad_t((const __half*)logits, labels, act_lens, label_lens, B, T, U1, V, blank, lse, alpha, beta, grad_costs, (__half*)grad_logits, stream);
         case RNNTB200_BF16:
-            return launch_grad_t((const __nv_bfloat16*)logits, labels, act_lens, label_lens, B, T, U1, V, blank, lse, alpha, beta, costs, grad_costs, (__nv_bfloat16*)grad_logits, stream);
+            return launch_grad_t((const __nv_bfloat16*)logits, labels, act_lens, label_lens, B, T, U1, V, blank, lse, alpha, beta, grad_costs, (__nv_bfloat16*)grad_logits, stream);
     }
     return RNNTB200_STATUS_INVALID_VALUE;
 }

@@ -88,8 +88,8 @@ __global__ void __launch_bounds__(256)
 cg_grad_kernel(const float* __restrict__ penc, const float* __restrict__ pdec,
                const int32_t* __restrict__ labels, const int32_t* __restrict__ act_lens,
                const int32_t* __restrict__ label_lens, int T, int U1, int V, int blank,
-               const float* __restrict__ lse, const float* __restrict__ alpha,
-               const float* __restrict__ beta, const float* __restrict__ costs,
+               const float* __restrict__ lse, const int32_t* __restrict__ alpha,
+               const int32_t* __restrict__ beta,
                const float* __restrict__ grad_costs, float* __restrict__ d_penc,
                float* __restrict__ d_pdec, float* __restrict__ partial /* deterministic slabs or null */) {
     __shared__ CellScalars sc[kGT][kGUC];
@@ -98,7 +98,8 @@ cg_grad_kernel(const float* __restrict__ penc, const float* __restrict__ pdec,
     const int tile = blockIdx.x;
     const int t0 = tile * kGT;
     const int Tb = min(__ldg(act_lens + b), T), Ub = min(__ldg(label_lens + b), U1 - 1);
-    const float cost = costs[b], gc = grad_costs[b];
+    const float gc = grad_costs[b];
+    const int llq = beta[(size_t)b * T * U1];  // beta(0,0) = log2 P(y|x), Q16
     const int n_tiles = gridDim.x;
     // deterministic mode: slab [b][tile][U1][V]
     float* slab = partial ? partial + ((size_t)b * n_tiles + tile) * U1 * V : nullptr;
@@ -135,17 +136,18 @@ cg_grad_kernel(const float* __restrict__ penc, const float* __restrict__ pdec,
                 s.corr_l = 0.f;
                 if (t < Tb && u <= Ub) {
                     const size_t c = ((size_t)b * T + t) * U1 + u;
-                    const float a = alpha[c], z = lse[c];
-                    s.c_all = (a + beta[c] + cost - z) * kLog2e;
+                    const int aq = alpha[c];
+                    const float z2 = lse[c] * kLog2e;
+                    s.c_all = q16_log2_ratio(aq, beta[c], llq) - z2;
                     const float* per = penc + ((size_t)b * T + t) * V;
                     const float* pdr = pdec + ((size_t)b * U1 + u) * V;
-                    const float lb = per[blank] + pdr[blank] - z;
-                    if (t < Tb - 1) s.corr_b = fast_ex2((a + lb + beta[c + U1] + cost) * kLog2e);
-                    else if (u == Ub) s.corr_b = fast_ex2((a + lb + cost) * kLog2e);
+                    const float lb2 = (per[blank] + pdr[blank]) * kLog2e - z2;
+                    if (t < Tb - 1) s.corr_b = fast_ex2(q16_log2_ratio(aq, beta[c + U1], llq) + lb2);
+                    else if (u == Ub) s.corr_b = fast_ex2(q16_log2_ratio(aq, 0, llq) + lb2);
                     if (u < Ub) {
                         const int y = __ldg(labels + (size_t)b * (U1 - 1) + u);
-                        const float ll = per[y] + pdr[y] - z;
-                        s.corr_l = fast_ex2((a + ll + beta[c + 1] + cost) * kLog2e);
+                        const float ll2 = (per[y] + pdr[y]) * kLog2e - z2;
+                        s.corr_l = fast_ex2(q16_log2_ratio(aq, beta[c + 1], llq) + ll2);
                     }
                 }
                 sc[r][uu] = s;
@@ -225,7 +227,7 @@ size_t cg_grad_workspace_bytes(int B, int T, int U1, int V, int deterministic) {
 
 int launch_cg_grad(const float* penc, const float* pdec, const int32_t* labels, const int32_t* act_lens,
                    const int32_t* label_lens, int B, int T, int U1, int V, int blank, const float* lse,
-                   const float* alpha, const float* beta, const float* costs, const float* grad_costs,
+                   const int32_t* alpha, const int32_t* beta, const float* grad_costs,
                    float* d_penc, float* d_pdec, int deterministic, void* workspace,
                    size_t workspace_bytes, cudaStream_t stream) {
     if ((long long)B * T * U1 == 0) return RNNTB200_STATUS_SUCCESS;
@@ -242,7 +244,7 @@ int launch_cg_grad(const float* penc, const float* pdec, const int32_t* labels, 
     const int threads = min(256, ((V + 31) / 32) * 32);
     dim3 grid(n_tiles, B);
     cg_grad_kernel<<<grid, threads, 0, stream>>>(penc, pdec, labels, act_lens, label_lens, T, U1, V,
-                                                 blank, lse, alpha, beta, costs, grad_costs, d_penc,
+                                                 blank, lse, alpha, beta, grad_costs, d_penc,
                                                  d_pdec, partial);
     int st = launch_status();
     if (st != RNNTB200_STATUS_SUCCESS || !deterministic) return st;

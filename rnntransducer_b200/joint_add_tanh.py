@@ -36,22 +36,23 @@ class _AddTanhRNNT(torch.autograd.Function):
         f32 = dict(device=enc.device, dtype=torch.float32)
         costs = torch.empty(B, **f32)
         lp2 = torch.empty(B, T, U1, 2, **f32)
-        lse, alpha, beta = (torch.empty(B, T, U1, **f32) for _ in range(3))
+        lse = torch.empty(B, T, U1, **f32)
+        alpha, beta = (torch.empty(B, T, U1, device=enc.device, dtype=torch.int32) for _ in range(2))
         lib = _lib.load()
         with torch.cuda.device(enc.device):
             _lib.check(lib.rnntb200_joint_at_fwd(
                 _ptr(enc), _ptr(dec), _ptr(weight), _ptr(bias), gemm, _ptr(labels), _ptr(act_lens),
                 _ptr(label_lens), B, T, U1, V, H, blank, _ptr(costs), _ptr(lp2), _ptr(lse),
                 _ptr(alpha), _ptr(beta), _stream()), "rnntb200_joint_at_fwd")
-        ctx.save_for_backward(enc, dec, weight, bias, labels, act_lens, label_lens, lse, alpha, beta,
-                              costs)
+        ctx.save_for_backward(enc, dec, weight, bias, labels, act_lens, label_lens, lp2, lse, alpha,
+                              beta)
         ctx.blank, ctx.gemm = blank, gemm
         return costs
 
     @staticmethod
     def backward(ctx, grad_costs):
-        (enc, dec, weight, bias, labels, act_lens, label_lens, lse, alpha, beta,
-         costs) = ctx.saved_tensors
+        (enc, dec, weight, bias, labels, act_lens, label_lens, lp2, lse, alpha,
+         beta) = ctx.saved_tensors
         B, T, H = enc.shape
         U1 = dec.shape[1]
         V = weight.shape[0]
@@ -62,8 +63,8 @@ class _AddTanhRNNT(torch.autograd.Function):
         with torch.cuda.device(enc.device):
             _lib.check(lib.rnntb200_joint_at_bwd(
                 _ptr(enc), _ptr(dec), _ptr(weight), _ptr(bias), ctx.gemm, _ptr(labels),
-                _ptr(act_lens), _ptr(label_lens), B, T, U1, V, H, ctx.blank, _ptr(lse), _ptr(alpha),
-                _ptr(beta), _ptr(costs), _ptr(grad_costs), _ptr(d_enc), _ptr(d_dec), _ptr(d_w),
+                _ptr(act_lens), _ptr(label_lens), B, T, U1, V, H, ctx.blank, _ptr(lp2), _ptr(lse),
+                _ptr(alpha), _ptr(beta), _ptr(grad_costs), _ptr(d_enc), _ptr(d_dec), _ptr(d_w),
                 _ptr(d_b), _stream()), "rnntb200_joint_at_bwd")
         return d_enc, d_dec, d_w, d_b, None, None, None, None, None
 

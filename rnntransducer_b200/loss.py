@@ -77,20 +77,21 @@ class _DenseRNNT(torch.autograd.Function):
         f32 = dict(device=dev, dtype=torch.float32)
         costs = torch.empty(B, **f32)
         lp2 = torch.empty(B, T, U1, 2, **f32)
-        lse, alpha, beta = (torch.empty(B, T, U1, **f32) for _ in range(3))
+        lse = torch.empty(B, T, U1, **f32)
+        alpha, beta = (torch.empty(B, T, U1, device=dev, dtype=torch.int32) for _ in range(2))  # Q16
         lib = _lib.load()
         with torch.cuda.device(dev):
             _lib.check(lib.rnntb200_loss_dense_fwd(
                 _ptr(acts), _DTYPES[acts.dtype], _ptr(labels), _ptr(act_lens), _ptr(label_lens),
                 B, T, U1, V, blank, _ptr(costs), _ptr(lp2), _ptr(lse), _ptr(alpha), _ptr(beta),
                 _stream()), "rnntb200_loss_dense_fwd")
-        ctx.save_for_backward(acts, labels, act_lens, label_lens, lse, alpha, beta, costs)
+        ctx.save_for_backward(acts, labels, act_lens, label_lens, lse, alpha, beta)
         ctx.blank = blank
         return costs
 
     @staticmethod
     def backward(ctx, grad_costs):
-        acts, labels, act_lens, label_lens, lse, alpha, beta, costs = ctx.saved_tensors
+        acts, labels, act_lens, label_lens, lse, alpha, beta = ctx.saved_tensors
         B, T, U1, V = acts.shape
         grad_costs = grad_costs.contiguous().to(torch.float32)
         grad = torch.empty_like(acts)
@@ -98,7 +99,7 @@ class _DenseRNNT(torch.autograd.Function):
         with torch.cuda.device(acts.device):
             _lib.check(lib.rnntb200_loss_dense_bwd(
                 _ptr(acts), _DTYPES[acts.dtype], _ptr(labels), _ptr(act_lens), _ptr(label_lens),
-                B, T, U1, V, ctx.blank, _ptr(lse), _ptr(alpha), _ptr(beta), _ptr(costs),
+                B, T, U1, V, ctx.blank, _ptr(lse), _ptr(alpha), _ptr(beta),
                 _ptr(grad_costs), _ptr(grad), _stream()), "rnntb200_loss_dense_bwd")
         return grad, None, None, None, None
 
@@ -117,20 +118,21 @@ class _ConcatGeluRNNT(torch.autograd.Function):
         f32 = dict(device=penc.device, dtype=torch.float32)
         costs = torch.empty(B, **f32)
         lp2 = torch.empty(B, T, U1, 2, **f32)
-        lse, alpha, beta = (torch.empty(B, T, U1, **f32) for _ in range(3))
+        lse = torch.empty(B, T, U1, **f32)
+        alpha, beta = (torch.empty(B, T, U1, device=penc.device, dtype=torch.int32) for _ in range(2))
         lib = _lib.load()
         with torch.cuda.device(penc.device):
             _lib.check(lib.rnntb200_joint_cg_fwd(
                 _ptr(penc), _ptr(pdec), _ptr(labels), _ptr(act_lens), _ptr(label_lens), B, T, U1, V,
                 blank, _ptr(costs), _ptr(lp2), _ptr(lse), _ptr(alpha), _ptr(beta), _stream()),
                 "rnntb200_joint_cg_fwd")
-        ctx.save_for_backward(penc, pdec, labels, act_lens, label_lens, lse, alpha, beta, costs)
+        ctx.save_for_backward(penc, pdec, labels, act_lens, label_lens, lse, alpha, beta)
         ctx.blank, ctx.deterministic = blank, bool(deterministic)
         return costs
 
     @staticmethod
     def backward(ctx, grad_costs):
-        penc, pdec, labels, act_lens, label_lens, lse, alpha, beta, costs = ctx.saved_tensors
+        penc, pdec, labels, act_lens, label_lens, lse, alpha, beta = ctx.saved_tensors
         B, T, V = penc.shape
         U1 = pdec.shape[1]
         grad_costs = grad_costs.contiguous().to(torch.float32)
@@ -143,7 +145,7 @@ class _ConcatGeluRNNT(torch.autograd.Function):
         with torch.cuda.device(penc.device):
             _lib.check(lib.rnntb200_joint_cg_bwd(
                 _ptr(penc), _ptr(pdec), _ptr(labels), _ptr(act_lens), _ptr(label_lens), B, T, U1, V,
-                ctx.blank, _ptr(lse), _ptr(alpha), _ptr(beta), _ptr(costs), _ptr(grad_costs),
+                ctx.blank, _ptr(lse), _ptr(alpha), _ptr(beta), _ptr(grad_costs),
                 _ptr(d_penc), _ptr(d_pdec), det, _ptr(ws), ws_bytes, _stream()),
                 "rnntb200_joint_cg_bwd")
         return d_penc, d_pdec, None, None, None, None, None

