@@ -413,7 +413,7 @@ def per_kernel(lib, st, mode, gemm, det, B, T, U1, V, H, cells, flush_buf, iters
     p = lambda t: t.data_ptr()
     lp2 = torch.empty(B, T, U1, 2, **f32)
     lse = torch.empty(B, T, U1, **f32)
-    alpha, beta = (torch.empty(B, T, U1, device=dev, dtype=torch.int32) for _ in range(2))  # Q16 planes
+    alpha, beta = (torch.empty(B, T, U1, device=dev, dtype=torch.int32) for _ in range(2))  # e16m16 planes
     costs, gcosts = torch.empty(B, **f32), torch.full((B,), 1.0 / B, **f32)
     lab, al, ll = st["labels"], st["act_lens"], st["label_lens"]
     res = {}
@@ -460,14 +460,16 @@ def per_kernel(lib, st, mode, gemm, det, B, T, U1, V, H, cells, flush_buf, iters
             d_enc, d_dec = torch.empty_like(enc), torch.empty_like(dec)
             d_w, d_b = torch.empty_like(w), torch.empty_like(b)
             io = 4 * H * B * (T + U1) + 4 * V * (H + 1)
+            ws_bytes = lib.rnntb200_joint_at_workspace_bytes(V, H, gemm)
+            ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
             bench("at_lse_kernel", lambda: _lib.check(lib.rnntb200_joint_at_logprobs(
                 p(enc), p(dec), p(w), p(b), gemm, p(lab), p(al), p(ll), B, T, U1, V, H, 0, p(lp2),
-                p(lse), stream)), 12 * cells + io)
+                p(lse), p(ws), ws_bytes, stream)), 12 * cells + io)
             bench("lattice_sweep_kernel", lambda: _lib.check(lib.rnntb200_lattice_sweep(
                 p(lp2), p(al), p(ll), B, T, U1, p(alpha), p(beta), p(costs), None, stream)), 24 * cells)
             bench("at_grad_kernel", lambda: _lib.check(lib.rnntb200_joint_at_bwd(
                 p(enc), p(dec), p(w), p(b), gemm, p(lab), p(al), p(ll), B, T, U1, V, H, 0, p(lp2), p(lse),
-                p(alpha), p(beta), p(gcosts), p(d_enc), p(d_dec), p(d_w), p(d_b), stream)),
+                p(alpha), p(beta), p(gcosts), p(d_enc), p(d_dec), p(d_w), p(d_b), p(ws), ws_bytes, stream)),
                 12 * cells + 2 * io)
             for k in ("at_lse_kernel", "at_grad_kernel"):
                 passes = 1 if k == "at_lse_kernel" else 3  # fwd | recompute + dgrad + wgrad

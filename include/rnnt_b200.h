@@ -22,10 +22,12 @@
  *   - lattice planes are [B, T, U1] row-major, 4 bytes per cell, U1 = max_label_len + 1:
  *       lp2   float2  (log p(blank|t,u), log p(y_{u+1}|t,u)), natural log
  *       lse   float   log-sum-exp of the cell's logits, natural log
- *       alpha, beta   rnntb200_q16_t: base-2 log in Q16 fixed point (int32), i.e.
- *                     ln(alpha) = q * ln(2) / 65536.  Fixed point keeps 1.5e-5 resolution at
- *                     any magnitude, so alpha + beta - log P(y|x) is formed exactly in integers
- *                     by the gradient kernels; beta[b,0,0] is log2 P(y|x) of utterance b.
+ *       alpha, beta   rnntb200_q16_t: a 32-bit wide-exponent float ("e16m16"), value =
+ *                     (1 + (q & 0xFFFF) / 65536) * 2^(q >> 16)  (arithmetic shift), i.e.
+ *                     ln(alpha) = ((q >> 16) + log2(1 + (q & 0xFFFF) / 65536)) * ln(2).
+ *                     2^-17 relative precision at any magnitude (|log2| < 32768), so the
+ *                     occupancy alpha * beta / P(y|x) is formed from exact integer exponents
+ *                     by the gradient kernels; beta[b,0,0] is P(y|x) of utterance b.
  *     entries outside an utterance's (T_b, U_b + 1) box are left untouched by
  *     forward calls and are written as exact zeros in gradient outputs;
  *   - return value: rnntb200_status_t, modelled on warp-transducer's
@@ -61,7 +63,7 @@ typedef enum {
 /* element type of logits / activations handed in by the caller */
 typedef enum { RNNTB200_F32 = 0, RNNTB200_F16 = 1, RNNTB200_BF16 = 2 } rnntb200_dtype_t;
 
-/* alpha / beta plane element: log2(value) * 65536, rounded (see conventions above) */
+/* alpha / beta plane element: e16m16 wide-exponent float (see conventions above) */
 typedef int32_t rnntb200_q16_t;
 
 /* joint function.  CONCAT_GELU is the reference's joint (transducer.py:64-69):
@@ -83,7 +85,7 @@ RNNTB200_API const char* rnntb200_status_string(int status);
 /* ------------------------------------------------------------------------------------------
  * Lattice sweeps (alpha and beta in ONE launch, one CTA per utterance and direction).
  *   lp2   [B,T,U1] float2 = (log p(blank | t,u), log p(y_{u+1} | t,u)), natural log
- *   alpha, beta [B,T,U1] Q16 out;  costs[B] = -ln beta(0,0) = -log P(y|x), fp32 natural log
+ *   alpha, beta [B,T,U1] e16m16 out;  costs[B] = -ln beta(0,0) = -log P(y|x), fp32 natural log
  *   ll_alpha[B] optional (may be NULL): ln(alpha(T-1,U) p_blank(T-1,U)), a cross-check of -costs.
  * Replaces warp-transducer compute_alphas/compute_betas and torchaudio's
  * ComputeAlphasBetasCosts.  Requires U1 <= 1024. */
@@ -138,12 +140,17 @@ RNNTB200_API int rnntb200_joint_cg_bwd(const float* penc, const float* pdec, con
  * dense H x V contraction per lattice cell.  enc [B,T,H], dec [B,U1,H], weight [V,H], bias [V].
  * fwd emits lp2 / lse only; bwd recomputes the logits tile, forms g and feeds it straight into
  * dgrad (g W (1 - z^2)) and wgrad (g^T z): d_enc [B,T,H], d_dec [B,U1,H], d_weight [V,H],
- * d_bias [V]; all four are fully overwritten. */
+ * d_bias [V]; all four are fully overwritten.  lp2 is the plane the forward wrote.
+ * `workspace` (rnntb200_joint_at_workspace_bytes, 16-byte aligned, may be NULL when that is 0)
+ * holds the bf16 copy of the weight the TMA streams in RNNTB200_GEMM_BF16 mode. */
+RNNTB200_API size_t rnntb200_joint_at_workspace_bytes(int V, int H, int gemm);
+
 RNNTB200_API int rnntb200_joint_at_fwd(const float* enc, const float* dec, const float* weight,
                           const float* bias, int gemm, const int32_t* labels,
                           const int32_t* act_lens, const int32_t* label_lens, int B, int T, int U1,
                           int V, int H, int blank, float* costs, void* lp2, float* lse,
-                          rnntb200_q16_t* alpha, rnntb200_q16_t* beta, void* stream);
+                          rnntb200_q16_t* alpha, rnntb200_q16_t* beta, void* workspace,
+                          size_t workspace_bytes, void* stream);
 
 RNNTB200_API int rnntb200_joint_at_bwd(const float* enc, const float* dec, const float* weight,
                           const float* bias, int gemm, const int32_t* labels,
@@ -151,7 +158,7 @@ RNNTB200_API int rnntb200_joint_at_bwd(const float* enc, const float* dec, const
                           int V, int H, int blank, const void* lp2, const float* lse,
                           const rnntb200_q16_t* alpha, const rnntb200_q16_t* beta,
                           const float* grad_costs, float* d_enc, float* d_dec, float* d_weight,
-                          float* d_bias, void* stream);
+                          float* d_bias, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Stage entry points: the per-cell front-ends alone (no sweep), so that each kernel can be
@@ -169,7 +176,8 @@ RNNTB200_API int rnntb200_joint_cg_logprobs(const float* penc, const float* pdec
 RNNTB200_API int rnntb200_joint_at_logprobs(const float* enc, const float* dec, const float* weight,
                                const float* bias, int gemm, const int32_t* labels,
                                const int32_t* act_lens, const int32_t* label_lens, int B, int T,
-                               int U1, int V, int H, int blank, void* lp2, float* lse, void* stream);
+                               int U1, int V, int H, int blank, void* lp2, float* lse, void* workspace,
+                               size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

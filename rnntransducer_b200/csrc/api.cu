@@ -110,11 +110,17 @@ RNNTB200_API int rnntb200_joint_cg_bwd(const float* penc, const float* pdec, con
                           workspace_bytes, (cudaStream_t)stream);
 }
 
+RNNTB200_API size_t rnntb200_joint_at_workspace_bytes(int V, int H, int gemm) {
+    if (V <= 0 || H <= 0 || bad_gemm(gemm)) return 0;
+    return at_workspace_bytes(V, H, gemm);
+}
+
 RNNTB200_API int rnntb200_joint_at_fwd(const float* enc, const float* dec, const float* weight,
                           const float* bias, int gemm, const int32_t* labels,
                           const int32_t* act_lens, const int32_t* label_lens, int B, int T, int U1,
                           int V, int H, int blank, float* costs, void* lp2, float* lse,
-                          rnntb200_q16_t* alpha, rnntb200_q16_t* beta, void* stream) {
+                          rnntb200_q16_t* alpha, rnntb200_q16_t* beta, void* workspace,
+                          size_t workspace_bytes, void* stream) {
     if (bad_shape(B, T, U1, V, blank) || H <= 0 || bad_gemm(gemm)) return RNNTB200_STATUS_INVALID_VALUE;
     if (B > 0 && (!enc || !dec || !weight || !bias || !act_lens || !label_lens || !costs || !lp2 ||
                   !lse || !alpha || !beta))
@@ -122,7 +128,7 @@ RNNTB200_API int rnntb200_joint_at_fwd(const float* enc, const float* dec, const
     if (B > 0 && U1 > 1 && !labels) return RNNTB200_STATUS_INVALID_VALUE;
     cudaStream_t s = (cudaStream_t)stream;
     int st = launch_at_lse(enc, dec, weight, bias, gemm, labels, act_lens, label_lens, B, T, U1, V, H,
-                           blank, (float2*)lp2, lse, s);
+                           blank, (float2*)lp2, lse, workspace, workspace_bytes, s);
     if (st != RNNTB200_STATUS_SUCCESS) return st;
     return launch_lattice_sweep((const float2*)lp2, act_lens, label_lens, B, T, U1, alpha, beta,
                                 costs, nullptr, s);
@@ -134,7 +140,7 @@ RNNTB200_API int rnntb200_joint_at_bwd(const float* enc, const float* dec, const
                           int V, int H, int blank, const void* lp2, const float* lse,
                           const rnntb200_q16_t* alpha, const rnntb200_q16_t* beta,
                           const float* grad_costs, float* d_enc, float* d_dec, float* d_weight,
-                          float* d_bias, void* stream) {
+                          float* d_bias, void* workspace, size_t workspace_bytes, void* stream) {
     if (bad_shape(B, T, U1, V, blank) || H <= 0 || bad_gemm(gemm)) return RNNTB200_STATUS_INVALID_VALUE;
     if (B > 0 && (!enc || !dec || !weight || !bias || !act_lens || !label_lens || !lp2 || !lse ||
                   !alpha || !beta || !grad_costs || !d_enc || !d_dec || !d_weight || !d_bias))
@@ -142,7 +148,7 @@ RNNTB200_API int rnntb200_joint_at_bwd(const float* enc, const float* dec, const
     if (B > 0 && U1 > 1 && !labels) return RNNTB200_STATUS_INVALID_VALUE;
     return launch_at_grad(enc, dec, weight, bias, gemm, labels, act_lens, label_lens, B, T, U1, V, H,
                           blank, (const float2*)lp2, lse, alpha, beta, grad_costs, d_enc, d_dec,
-                          d_weight, d_bias, (cudaStream_t)stream);
+                          d_weight, d_bias, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 RNNTB200_API int rnntb200_dense_logprobs(const void* logits, int dtype, const int32_t* labels,
@@ -168,13 +174,14 @@ RNNTB200_API int rnntb200_joint_cg_logprobs(const float* penc, const float* pdec
 RNNTB200_API int rnntb200_joint_at_logprobs(const float* enc, const float* dec, const float* weight,
                                const float* bias, int gemm, const int32_t* labels,
                                const int32_t* act_lens, const int32_t* label_lens, int B, int T,
-                               int U1, int V, int H, int blank, void* lp2, float* lse, void* stream) {
+                               int U1, int V, int H, int blank, void* lp2, float* lse, void* workspace,
+                               size_t workspace_bytes, void* stream) {
     if (bad_shape(B, T, U1, V, blank) || H <= 0 || bad_gemm(gemm)) return RNNTB200_STATUS_INVALID_VALUE;
     if (B > 0 && (!enc || !dec || !weight || !bias || !act_lens || !label_lens || !lp2 || !lse))
         return RNNTB200_STATUS_INVALID_VALUE;
     if (B > 0 && U1 > 1 && !labels) return RNNTB200_STATUS_INVALID_VALUE;
     return launch_at_lse(enc, dec, weight, bias, gemm, labels, act_lens, label_lens, B, T, U1, V, H,
-                         blank, (float2*)lp2, lse, (cudaStream_t)stream);
+                         blank, (float2*)lp2, lse, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 }  // extern "C"

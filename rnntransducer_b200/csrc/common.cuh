@@ -62,10 +62,14 @@ __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2hal
 template <>
 __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
-// alpha / beta planes hold Q16 fixed-point base-2 logs (see lattice.cu).  log2 of the lattice
-// occupancy ratio alpha * beta / P(y|x), formed exactly in integers before going to float.
-__device__ __forceinline__ float q16_log2_ratio(int aq, int bq, int llq) {
-    return (float)((long long)aq + (long long)bq - (long long)llq) * (1.0f / 65536.0f);
+// alpha / beta planes hold "e16m16" wide-exponent floats (lattice.cu): value = (1 + lo16 / 65536) *
+// 2^(hi16 as signed).  log2 of the occupancy ratio alpha * beta / P(y|x): exponents combine exactly
+// in integers, mantissas as one small float; pass bq = 0 for a factor of 1.
+__device__ __forceinline__ float e16m16_mant(int q) { return __int_as_float(0x3f800000 | ((q & 0xFFFF) << 7)); }
+__device__ __forceinline__ float e16m16_log2_ratio(int aq, int bq, int llq) {
+    const int e = (aq >> 16) + (bq >> 16) - (llq >> 16);
+    const float m = e16m16_mant(aq) * e16m16_mant(bq) * __frcp_rn(e16m16_mant(llq));
+    return (float)e + fast_lg2(m);
 }
 
 inline int status_from_cuda(cudaError_t e) {
@@ -103,11 +107,14 @@ size_t cg_grad_workspace_bytes(int B, int T, int U1, int V, int deterministic);
 
 int launch_at_lse(const float* enc, const float* dec, const float* weight, const float* bias, int gemm,
                   const int32_t* labels, const int32_t* act_lens, const int32_t* label_lens, int B,
-                  int T, int U1, int V, int H, int blank, float2* lp2, float* lse, cudaStream_t stream);
+                  int T, int U1, int V, int H, int blank, float2* lp2, float* lse, void* workspace,
+                  size_t workspace_bytes, cudaStream_t stream);
+size_t at_workspace_bytes(int V, int H, int gemm);
 int launch_at_grad(const float* enc, const float* dec, const float* weight, const float* bias, int gemm,
                    const int32_t* labels, const int32_t* act_lens, const int32_t* label_lens, int B,
                    int T, int U1, int V, int H, int blank, const float2* lp2, const float* lse,
                    const int32_t* alpha, const int32_t* beta, const float* grad_costs, float* d_enc,
-                   float* d_dec, float* d_weight, float* d_bias, cudaStream_t stream);
+                   float* d_dec, float* d_weight, float* d_bias, void* workspace, size_t workspace_bytes,
+                   cudaStream_t stream);
 
 }  // namespace rnntb200

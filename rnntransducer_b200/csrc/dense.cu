@@ -146,17 +146,17 @@ dense_grad_kernel(const T* __restrict__ logits, const int32_t* __restrict__ labe
         const int Tb = __ldg(act_lens + k.b), Ub = __ldg(label_lens + k.b);
         const int aq = alpha[c], llq = beta[(long long)k.b * T_ * U1];  // beta(0,0) = log2 P(y|x)
         const float z2 = lse[c] * kLog2e, gc = grad_costs[k.b];
-        const float c_all = q16_log2_ratio(aq, beta[c], llq) - z2;  // log2(occupancy / partition)
+        const float c_all = e16m16_log2_ratio(aq, beta[c], llq) - z2;  // log2(occupancy / partition)
         // corrections at the blank and label columns
         float corr_b = 0.f, corr_l = 0.f;
         int y = -1;
         const float lb2 = to_f32<T>(row[blank]) * kLog2e - z2;
-        if (k.t < Tb - 1) corr_b = fast_ex2(q16_log2_ratio(aq, beta[c + U1], llq) + lb2);
-        else if (k.u == Ub) corr_b = fast_ex2(q16_log2_ratio(aq, 0, llq) + lb2);
+        if (k.t < Tb - 1) corr_b = fast_ex2(e16m16_log2_ratio(aq, beta[c + U1], llq) + lb2);
+        else if (k.u == Ub) corr_b = fast_ex2(e16m16_log2_ratio(aq, 0, llq) + lb2);
         if (k.u < Ub) {
             y = __ldg(labels + (size_t)k.b * (U1 - 1) + k.u);
             const float ll2 = to_f32<T>(row[y]) * kLog2e - z2;
-            corr_l = fast_ex2(q16_log2_ratio(aq, beta[c + 1], llq) + ll2);
+            corr_l = fast_ex2(e16m16_log2_ratio(aq, beta[c + 1], llq) + ll2);
         }
         for (int v = lane; v < V; v += 32) {
             float gv = fast_ex2(fmaf(to_f32<T>(row[v]), kLog2e, c_all));

@@ -19,9 +19,10 @@ namespace rnntb200 {
 
 int launch_at_lse_tc(const float* enc, const float* dec, const float* weight, const float* bias,
                      const int32_t* labels, const int32_t* act_lens, const int32_t* label_lens, int B,
-                     int T, int U1, int V, int H, int blank, float2* lp2, float* lse,
-                     cudaStream_t stream);  // joint_at_tc.cu
+                     int T, int U1, int V, int H, int blank, float2* lp2, float* lse, void* workspace,
+                     size_t workspace_bytes, cudaStream_t stream);  // joint_at_tc.cu
 bool at_tc_supported(int V, int H);
+size_t at_tc_workspace_bytes(int V, int H);
 
 namespace {
 
@@ -202,12 +203,12 @@ at_grad_simt_kernel(const float* __restrict__ enc, const float* __restrict__ dec
             const size_t c = ((size_t)b * T + t) * U1 + u;
             const int aq = alpha[c], llq = beta[(size_t)b * T * U1];
             const float2 lp = lp2[c];
-            g.c_all = q16_log2_ratio(aq, beta[c], llq) - lse[c] * kLog2e;
-            if (t < Tb - 1) g.corr_b = fast_ex2(q16_log2_ratio(aq, beta[c + U1], llq) + lp.x * kLog2e);
-            else if (u == Ub) g.corr_b = fast_ex2(q16_log2_ratio(aq, 0, llq) + lp.x * kLog2e);
+            g.c_all = e16m16_log2_ratio(aq, beta[c], llq) - lse[c] * kLog2e;
+            if (t < Tb - 1) g.corr_b = fast_ex2(e16m16_log2_ratio(aq, beta[c + U1], llq) + lp.x * kLog2e);
+            else if (u == Ub) g.corr_b = fast_ex2(e16m16_log2_ratio(aq, 0, llq) + lp.x * kLog2e);
             if (u < Ub) {
                 g.y = __ldg(labels + (size_t)b * (U1 - 1) + u);
-                g.corr_l = fast_ex2(q16_log2_ratio(aq, beta[c + 1], llq) + lp.y * kLog2e);
+                g.corr_l = fast_ex2(e16m16_log2_ratio(aq, beta[c + 1], llq) + lp.y * kLog2e);
             }
         }
         gc_s[tid] = g;
@@ -326,14 +327,19 @@ int set_smem(K kernel, size_t smem) {
 
 }  // namespace
 
+size_t at_workspace_bytes(int V, int H, int gemm) {
+    return (gemm == RNNTB200_GEMM_BF16 && at_tc_supported(V, H)) ? at_tc_workspace_bytes(V, H) : 0;
+}
+
 int launch_at_lse(const float* enc, const float* dec, const float* weight, const float* bias, int gemm,
                   const int32_t* labels, const int32_t* act_lens, const int32_t* label_lens, int B,
-                  int T, int U1, int V, int H, int blank, float2* lp2, float* lse, cudaStream_t stream) {
+                  int T, int U1, int V, int H, int blank, float2* lp2, float* lse, void* workspace,
+                  size_t workspace_bytes, cudaStream_t stream) {
     if ((long long)B * T * U1 == 0) return RNNTB200_STATUS_SUCCESS;
     if (gemm == RNNTB200_GEMM_TF32X3) return RNNTB200_STATUS_INVALID_VALUE;  // reserved
     if (gemm == RNNTB200_GEMM_BF16 && at_tc_supported(V, H))
         return launch_at_lse_tc(enc, dec, weight, bias, labels, act_lens, label_lens, B, T, U1, V, H,
-                                blank, lp2, lse, stream);
+                                blank, lp2, lse, workspace, workspace_bytes, stream);
     const int Hs = (H + kKT - 1) / kKT * kKT + 1;  // odd stride; columns H..Hs-1 are zero
     const size_t smem = ((size_t)64 * Hs + kNT * kWs + 128) * sizeof(float);
     dim3 grid((U1 + 7) / 8, (T + 7) / 8, B);
@@ -354,7 +360,10 @@ int launch_at_grad(const float* enc, const float* dec, const float* weight, cons
                    const int32_t* labels, const int32_t* act_lens, const int32_t* label_lens, int B,
                    int T, int U1, int V, int H, int blank, const float2* lp2, const float* lse,
                    const int32_t* alpha, const int32_t* beta, const float* grad_costs, float* d_enc,
-                   float* d_dec, float* d_weight, float* d_bias, cudaStream_t stream) {
+                   float* d_dec, float* d_weight, float* d_bias, void* workspace, size_t workspace_bytes,
+                   cudaStream_t stream) {
+    (void)workspace;
+    (void)workspace_bytes;
     if (gemm == RNNTB200_GEMM_TF32X3) return RNNTB200_STATUS_INVALID_VALUE;  // reserved
     if (H > 512) return RNNTB200_STATUS_INVALID_VALUE;  // dz register tile (see kernel)
     // all four outputs are accumulated with fp32 atomics: clear them first (also the B == 0 case)

@@ -1,15 +1,440 @@
-// joint_at_tc.cu -- tcgen05 (5th-gen tensor core) forward of the ADD_TANH joint.  Placeholder:
-// reports "unsupported" so RNNTB200_GEMM_BF16 runs the bf16-emulating CUDA-core kernels.
+// joint_at_tc.cu -- tcgen05 forward of the ADD_TANH joint: logits = tanh(enc_t + dec_u) W^T + bias
+// on the 5th-gen tensor cores with the log-softmax fused into the accumulator read-out, so that
+// only (lp_blank, lp_label) and the log-sum-exp of each lattice cell ever reach HBM.
+//
+// One persistent CTA per SM walks tiles of 128 lattice cells (16 t x 8 u of one utterance):
+//
+//   warps 0-7   A producers: z = tanh(e_t + d_u) on the CUDA cores (MUFU.TANH), rounded to bf16 and
+//               written straight into the UMMA K-major core-matrix layout, one 64-wide K block per
+//               shared-memory slot (the A operand is computed, never loaded);
+//   warp  8     TMA producer: streams W (bf16 copy, [V,H]) as [N-chunk x 64] K blocks through a
+//               ring of shared-memory stages with cp.async.bulk.tensor (3-D view so that the
+//               box lands directly in core-matrix order; rows >= V are zero-filled by the TMA);
+//   warp  9     MMA issuer: one elected thread issues tcgen05.mma (M = 128 cells, N = chunk of the
+//               vocabulary, K = 16 per instruction), accumulating in TMEM; tcgen05.commit releases
+//               W stages / A slots and publishes the accumulator;
+//   warps 10-13 epilogue: each thread owns one lattice cell (one TMEM lane), reads its logits with
+//               tcgen05.ld, adds the bias and runs an online log-sum-exp across vocabulary chunks
+//               (two accumulator stages in TMEM, so chunk c+1 is multiplied while chunk c is
+//               reduced), picks the blank / label columns and writes 12 bytes per cell.
+//
+// Synchronisation is mbarrier-only (full/empty pairs per A slot, W stage and accumulator stage).
+// Supported shapes: H a multiple of 64, H <= 512; any V (chunks of <= 128 columns, so V = 1024 is
+// 8 chunks with the A tile resident in shared memory and computed once).
+#include <cuda.h>
+
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace rnntb200 {
 
-bool at_tc_supported(int, int) { return false; }
+namespace {
 
-int launch_at_lse_tc(const float*, const float*, const float*, const float*, const int32_t*,
-                     const int32_t*, const int32_t*, int, int, int, int, int, int, float2*, float*,
-                     cudaStream_t) {
-    return RNNTB200_STATUS_EXECUTION_FAILED;
+constexpr int kTT = 16, kUU = 8;       // tile = 16 frames x 8 label positions = 128 cells (MMA M)
+constexpr int kKB = 64;                // K elements per A slot / W stage
+constexpr int kProducerThreads = 256;  // warps 0-7
+constexpr int kTmaWarp = 8, kMmaWarp = 9;  // warps 10-13: epilogue
+constexpr int kThreads = 14 * 32;
+constexpr int kWStages = 2;
+constexpr int kAccStride = 128;        // TMEM columns per accumulator stage
+constexpr int kTmemCols = 256;
+constexpr int kASlotBytes = 128 * kKB * 2;  // 16 KiB
+constexpr int kMaxSlots = 8;                // H <= 512
+
+struct Smem {  // offsets into dynamic shared memory
+    int a, w, ed, bars, total;
+    int w_stage_bytes, ed_stride;
+};
+
+__host__ __device__ inline Smem smem_layout(int H, int NB) {
+    Smem s;
+    s.a = 0;
+    s.w = (H / kKB) * kASlotBytes;
+    s.w_stage_bytes = NB * kKB * 2;
+    s.ed = s.w + kWStages * s.w_stage_bytes;
+    s.ed_stride = H + 8;  // floats; +8 keeps rows on different banks
+    s.bars = s.ed + (kTT + kUU) * s.ed_stride * 4;
+    s.bars = (s.bars + 15) & ~15;
+    s.total = s.bars + 32 * 8 + 16;
+    return s;
+}
+
+// ---- PTX wrappers -----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Waits for the phase with the given parity.  A protocol bug would otherwise hang the GPU, so
+// the wait is bounded (~2 s of SM clocks) and traps instead: the launch then fails loudly.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    long long start = 0;
+    for (uint32_t spins = 0;; ++spins) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) return;
+        if ((spins & 1023) == 1023) {
+            const long long now = clock64();
+            if (start == 0) start = now;
+            else if (now - start > 4000000000LL) __trap();
+        }
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2,
+                                            uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::
+            "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// K-major, no-swizzle shared-memory matrix descriptor: core matrix = 8 rows x 16 bytes (128
+// contiguous bytes); SBO = byte distance between 8-row groups, LBO = between 16-byte K chunks.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ float tanh_fast(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__global__ void convert_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = __float2bfloat16_rn(src[i]);
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1)
+at_lse_tc_kernel(const __grid_constant__ CUtensorMap w_map, const float* __restrict__ enc,
+                 const float* __restrict__ dec, const float* __restrict__ bias,
+                 const int32_t* __restrict__ labels, const int32_t* __restrict__ act_lens,
+                 const int32_t* __restrict__ label_lens, int B, int T, int U1, int V, int H, int NB,
+                 int blank, float2* __restrict__ lp2, float* __restrict__ lse_out) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const Smem L = smem_layout(H, NB);
+    const int n_slots = H / kKB;
+    const int n_chunks = (V + NB - 1) / NB;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t a_base = sbase + L.a, w_base = sbase + L.w;
+    float* ed = reinterpret_cast<float*>(smem + L.ed);  // [16 enc rows | 8 dec rows][ed_stride]
+    const uint32_t bars = sbase + L.bars;
+    auto a_full = [&](int i) { return bars + 8 * i; };
+    auto a_empty = [&](int i) { return bars + 8 * (8 + i); };
+    auto w_full = [&](int i) { return bars + 8 * (16 + i); };
+    auto w_empty = [&](int i) { return bars + 8 * (18 + i); };
+    auto acc_full = [&](int i) { return bars + 8 * (20 + i); };
+    auto acc_empty = [&](int i) { return bars + 8 * (22 + i); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.bars + 32 * 8);
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kMaxSlots; ++i) { mbar_init(a_full(i), 8); mbar_init(a_empty(i), 1); }
+        for (int i = 0; i < kWStages; ++i) { mbar_init(w_full(i), 1); mbar_init(w_empty(i), 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), 4); }
+        fence_barrier_init();
+    }
+    if (warp == kMmaWarp) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "n"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int nT = (T + kTT - 1) / kTT, nU = (U1 + kUU - 1) / kUU;
+    const int n_tiles = B * nT * nU;
+
+    // tile -> (b, t0, u0) and whether any of its cells is inside the utterance's lattice
+    auto decode = [&](int tile, int& b, int& t0, int& u0) -> bool {
+        b = tile / (nT * nU);
+        const int r = tile - b * nT * nU;
+        t0 = (r / nU) * kTT;
+        u0 = (r % nU) * kUU;
+        return t0 < min(__ldg(act_lens + b), T) && u0 <= min(__ldg(label_lens + b), U1 - 1);
+    };
+
+    if (warp < 8) {
+        // ===== A producers =====
+        const int p = threadIdx.x;
+        const int r = p & 127, kc0 = p >> 7;  // cell row of the tile, first 8-wide K chunk
+        const int tt = r / kUU, uu = r % kUU;
+        uint32_t n = 0;  // tiles processed by this CTA so far
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            int b, t0, u0;
+            if (!decode(tile, b, t0, u0)) continue;
+            // stage the tile's 16 encoder rows and 8 predictor rows (fp32)
+            asm volatile("bar.sync 1, 256;" ::: "memory");  // previous tile's readers are done
+            const int H4 = H / 4;
+            for (int i = p; i < (kTT + kUU) * H4; i += kProducerThreads) {
+                const int row = i / H4, c4 = i - row * H4;
+                const float* src = row < kTT ? enc + ((size_t)b * T + min(t0 + row, T - 1)) * H
+                                             : dec + ((size_t)b * U1 + min(u0 + row - kTT, U1 - 1)) * H;
+                *reinterpret_cast<float4*>(ed + row * L.ed_stride + 4 * c4) =
+                    __ldg(reinterpret_cast<const float4*>(src) + c4);
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const float* erow = ed + tt * L.ed_stride;
+            const float* drow = ed + (kTT + uu) * L.ed_stride;
+            for (int kb = 0; kb < n_slots; ++kb) {
+                mbar_wait(a_empty(kb), (n & 1) ^ 1);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int kc = kc0 + 2 * i;
+                    const int k = kb * kKB + kc * 8;
+                    const float4 e0 = *reinterpret_cast<const float4*>(erow + k);
+                    const float4 e1 = *reinterpret_cast<const float4*>(erow + k + 4);
+                    const float4 d0 = *reinterpret_cast<const float4*>(drow + k);
+                    const float4 d1 = *reinterpret_cast<const float4*>(drow + k + 4);
+                    uint4 out;
+                    out.x = pack_bf16(tanh_fast(e0.x + d0.x), tanh_fast(e0.y + d0.y));
+                    out.y = pack_bf16(tanh_fast(e0.z + d0.z), tanh_fast(e0.w + d0.w));
+                    out.z = pack_bf16(tanh_fast(e1.x + d1.x), tanh_fast(e1.y + d1.y));
+                    out.w = pack_bf16(tanh_fast(e1.z + d1.z), tanh_fast(e1.w + d1.w));
+                    // core-matrix layout: K chunk kc at kc * 2048, cell row r at r * 16
+                    *reinterpret_cast<uint4*>(smem + L.a + kb * kASlotBytes + kc * 2048 + r * 16) = out;
+                }
+                fence_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(a_full(kb));
+            }
+            ++n;
+        }
+    } else if (warp == kTmaWarp) {
+        // ===== TMA producer for W =====
+        if (lane == 0) {
+            uint32_t wi = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                int b, t0, u0;
+                if (!decode(tile, b, t0, u0)) continue;
+                for (int c = 0; c < n_chunks; ++c)
+                    for (int kb = 0; kb < n_slots; ++kb, ++wi) {
+                        const int st = wi % kWStages;
+                        mbar_wait(w_empty(st), ((wi / kWStages) & 1) ^ 1);
+                        mbar_arrive_expect_tx(w_full(st), (uint32_t)L.w_stage_bytes);
+                        tma_load_3d(w_base + st * L.w_stage_bytes, &w_map, 0, c * NB, kb * (kKB / 8), w_full(st));
+                    }
+            }
+        }
+    } else if (warp == kMmaWarp) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            // kind::f16, A/B = bf16 K-major, D = fp32, M = 128, N = NB
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NB >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t b_lbo = NB * 16;
+            uint32_t n = 0, wi = 0, ci = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                int b, t0, u0;
+                if (!decode(tile, b, t0, u0)) continue;
+                for (int c = 0; c < n_chunks; ++c, ++ci) {
+                    const int as = ci & 1;
+                    mbar_wait(acc_empty(as), ((ci >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    for (int kb = 0; kb < n_slots; ++kb, ++wi) {
+                        const int st = wi % kWStages;
+                        if (c == 0) mbar_wait(a_full(kb), n & 1);
+                        mbar_wait(w_full(st), (wi / kWStages) & 1);
+                        tc_fence_after();
+#pragma unroll
+                        for (int j = 0; j < kKB / 16; ++j) {
+                            const uint64_t ad = umma_desc(a_base + kb * kASlotBytes + j * 2 * 2048, 2048, 128);
+                            const uint64_t bd = umma_desc(w_base + st * L.w_stage_bytes + j * 2 * b_lbo, b_lbo, 128);
+                            umma_bf16(tmem_base + as * kAccStride, ad, bd, idesc, (kb | j) != 0);
+                        }
+                        umma_commit(w_empty(st));
+                        if (c == n_chunks - 1) umma_commit(a_empty(kb));
+                    }
+                    umma_commit(acc_full(as));
+                }
+                ++n;
+            }
+        }
+    } else {
+        // ===== epilogue: one lattice cell per thread =====
+        const int q = warp & 3;               // TMEM lane quarter this warp may read
+        const int r = q * 32 + lane;          // cell row of the tile
+        const int tt = r / kUU, uu = r % kUU;
+        uint32_t ci = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            int b, t0, u0;
+            if (!decode(tile, b, t0, u0)) continue;
+            const int Tb = min(__ldg(act_lens + b), T), Ub = min(__ldg(label_lens + b), U1 - 1);
+            const int t = t0 + tt, u = u0 + uu;
+            const bool valid = t < Tb && u <= Ub;
+            const int y = (valid && u < Ub) ? __ldg(labels + (size_t)b * (U1 - 1) + u) : -1;
+            float m = -INFINITY, s = 0.f, xb = 0.f, xl = 0.f;
+            for (int c = 0; c < n_chunks; ++c, ++ci) {
+                const int as = ci & 1;
+                mbar_wait(acc_full(as), (ci >> 1) & 1);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + as * kAccStride + ((uint32_t)(q * 32) << 16);
+                float v[16];
+                float cmax = -INFINITY;
+                for (int pc = 0; pc < NB / 16; ++pc) {
+                    tmem_ld16(taddr + pc * 16, v);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int col = c * NB + pc * 16 + i;
+                        if (col < V) {
+                            const float x = fmaf(v[i], kLog2e, __ldg(bias + col) * kLog2e);
+                            cmax = fmaxf(cmax, x);
+                            if (col == blank) xb = x;
+                            if (col == y) xl = x;
+                        }
+                    }
+                }
+                const float m_new = fmaxf(m, cmax);
+                s *= fast_ex2(m - m_new);
+                for (int pc = 0; pc < NB / 16; ++pc) {
+                    tmem_ld16(taddr + pc * 16, v);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int col = c * NB + pc * 16 + i;
+                        if (col < V) s += fast_ex2(fmaf(v[i], kLog2e, __ldg(bias + col) * kLog2e) - m_new);
+                    }
+                }
+                m = m_new;
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_empty(as));
+            }
+            if (valid) {
+                const float lse2 = m + fast_lg2(s);
+                const size_t cidx = ((size_t)b * T + t) * U1 + u;
+                const float lb = fmaxf((xb - lse2) * kLn2, kNegInf);
+                const float ll = u < Ub ? fmaxf((xl - lse2) * kLn2, kNegInf) : 0.f;
+                lp2[cidx] = make_float2(lb, ll);
+                lse_out[cidx] = lse2 * kLn2;
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kMmaWarp) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+inline int chunk_cols(int V) { return std::min(((V + 15) / 16) * 16, 128); }
+
+}  // namespace
+
+bool at_tc_supported(int V, int H) { return V >= 1 && H >= kKB && H % kKB == 0 && H <= kKB * kMaxSlots; }
+
+size_t at_tc_workspace_bytes(int V, int H) { return ((size_t)V * H * sizeof(__nv_bfloat16) + 255) & ~(size_t)255; }
+
+int launch_at_lse_tc(const float* enc, const float* dec, const float* weight, const float* bias,
+                     const int32_t* labels, const int32_t* act_lens, const int32_t* label_lens, int B,
+                     int T, int U1, int V, int H, int blank, float2* lp2, float* lse, void* workspace,
+                     size_t workspace_bytes, cudaStream_t stream) {
+    if (!at_tc_supported(V, H)) return RNNTB200_STATUS_INVALID_VALUE;
+    if (!workspace || workspace_bytes < at_tc_workspace_bytes(V, H) || ((uintptr_t)workspace & 15))
+        return RNNTB200_STATUS_INVALID_VALUE;
+    EncodeTiledFn encode = encode_tiled_fn();
+    if (!encode) return RNNTB200_STATUS_EXECUTION_FAILED;
+
+    __nv_bfloat16* wb = static_cast<__nv_bfloat16*>(workspace);
+    const size_t nw = (size_t)V * H;
+    convert_bf16_kernel<<<(unsigned)std::min<size_t>((nw + 255) / 256, 1184), 256, 0, stream>>>(weight, wb, nw);
+
+    // 3-D view of W[V][H] as [H/8][V][8]: a box {8, NB, 8} lands in shared memory as
+    // [k-chunk][row][8 elements] = UMMA K-major core matrices (SBO = 128 B, LBO = NB * 16 B)
+    const int NB = chunk_cols(V);
+    CUtensorMap map;
+    const cuuint64_t gdim[3] = {8, (cuuint64_t)V, (cuuint64_t)(H / 8)};
+    const cuuint64_t gstride[2] = {(cuuint64_t)H * 2, 16};
+    const cuuint32_t box[3] = {8, (cuuint32_t)NB, (cuuint32_t)(kKB / 8)};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    if (encode(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, wb, gdim, gstride, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return RNNTB200_STATUS_INVALID_VALUE;
+
+    const Smem L = smem_layout(H, NB);
+    cudaError_t e = cudaFuncSetAttribute(at_lse_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
+    if (e != cudaSuccess) return status_from_cuda(e);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int n_tiles = B * ((T + kTT - 1) / kTT) * ((U1 + kUU - 1) / kUU);
+    const int grid = std::min(n_tiles, sms);
+    at_lse_tc_kernel<<<grid, kThreads, L.total, stream>>>(map, enc, dec, bias, labels, act_lens, label_lens, B,
+                                                         T, U1, V, H, NB, blank, lp2, lse);
+    return launch_status();
 }
 
 }  // namespace rnntb200

@@ -99,7 +99,7 @@ cg_grad_kernel(const float* __restrict__ penc, const float* __restrict__ pdec,
     const int t0 = tile * kGT;
     const int Tb = min(__ldg(act_lens + b), T), Ub = min(__ldg(label_lens + b), U1 - 1);
     const float gc = grad_costs[b];
-    const int llq = beta[(size_t)b * T * U1];  // beta(0,0) = log2 P(y|x), Q16
+    const int llq = beta[(size_t)b * T * U1];  // beta(0,0) = log2 P(y|x), e16m16
     const int n_tiles = gridDim.x;
     // deterministic mode: slab [b][tile][U1][V]
     float* slab = partial ? partial + ((size_t)b * n_tiles + tile) * U1 * V : nullptr;
@@ -138,16 +138,16 @@ cg_grad_kernel(const float* __restrict__ penc, const float* __restrict__ pdec,
                     const size_t c = ((size_t)b * T + t) * U1 + u;
                     const int aq = alpha[c];
                     const float z2 = lse[c] * kLog2e;
-                    s.c_all = q16_log2_ratio(aq, beta[c], llq) - z2;
+                    s.c_all = e16m16_log2_ratio(aq, beta[c], llq) - z2;
                     const float* per = penc + ((size_t)b * T + t) * V;
                     const float* pdr = pdec + ((size_t)b * U1 + u) * V;
                     const float lb2 = (per[blank] + pdr[blank]) * kLog2e - z2;
-                    if (t < Tb - 1) s.corr_b = fast_ex2(q16_log2_ratio(aq, beta[c + U1], llq) + lb2);
-                    else if (u == Ub) s.corr_b = fast_ex2(q16_log2_ratio(aq, 0, llq) + lb2);
+                    if (t < Tb - 1) s.corr_b = fast_ex2(e16m16_log2_ratio(aq, beta[c + U1], llq) + lb2);
+                    else if (u == Ub) s.corr_b = fast_ex2(e16m16_log2_ratio(aq, 0, llq) + lb2);
                     if (u < Ub) {
                         const int y = __ldg(labels + (size_t)b * (U1 - 1) + u);
                         const float ll2 = (per[y] + pdr[y]) * kLog2e - z2;
-                        s.corr_l = fast_ex2(q16_log2_ratio(aq, beta[c + 1], llq) + ll2);
+                        s.corr_l = fast_ex2(e16m16_log2_ratio(aq, beta[c + 1], llq) + ll2);
                     }
                 }
                 sc[r][uu] = s;

@@ -19,10 +19,11 @@
 // underflow for any lattice size, ~1e-7 relative error per step (the log-domain form costs two
 // MUFUs per step on the chain and loses ulp(|alpha|) ~ 1e-4 per step once |alpha| reaches 10^3).
 //
-// Storage.  alpha / beta planes are written as Q16 fixed-point base-2 logs (int32, value =
-// log2(alpha) * 65536): 4 bytes per cell like fp32 but with 1.5e-5 resolution over +-32767, so the
-// occupancy alpha + beta - log P(y|x) the gradient needs is formed exactly in integers instead of
-// cancelling three fp32 numbers of magnitude 10^3.  beta[b,0,0] is log2 P(y|x) in the same format.
+// Storage.  alpha / beta planes are written in a 32-bit wide-exponent float ("e16m16", see
+// common.cuh): signed 16-bit binary exponent in the high half, 16 mantissa bits in the low half.
+// 4 bytes per cell like fp32, 2^-17 relative precision at ANY magnitude (|log2| < 32768), so the
+// occupancy alpha * beta / P(y|x) the gradient needs is formed from exact integer exponents
+// instead of cancelling three fp32 logs of magnitude 10^3.  beta[b,0,0] is P(y|x) in that format.
 //
 // Loads.  The (lp_blank, lp_label) pair of a cell is one 8-byte cp.async into a per-thread slot
 // of a shared-memory ring, issued kDepth-1 diagonals ahead (the loads do not depend on the
@@ -33,48 +34,50 @@ namespace rnntb200 {
 
 namespace {
 
-constexpr int kDepth = 16;      // cp.async ring depth (diagonals in flight per thread)
-constexpr int kLag = 8;         // diagonals warp w trails warp w-1
-constexpr int kEdgeRing = 32;   // >= 2*kLag + 1 slots for warp-boundary values
-constexpr int kZeroExp = -(1 << 30);  // exponent of the (mantissa, exponent) encoding of 0
+constexpr int kDepth = 16;        // cp.async ring depth (diagonals in flight per thread) = unroll
+constexpr int kRingStride = 17;   // float2 slots per thread (+1 pad: conflict-free 8-byte accesses)
+constexpr int kLag = 8;           // diagonals warp w trails warp w-1
+constexpr int kEdgeRing = 32;     // >= 2*kLag + 1 slots for warp-boundary values
+constexpr int kZeroExp = -(1 << 29);  // (1, kZeroExp) stands for 0: it never wins an addition
 
-struct ME {  // value = m * 2^e, m in [1,2) after normalize(), or m == 0
+struct ME {  // value = m * 2^e; m in [1,2) after normalize(), in [0.7, 5.7) before
     float m;
     int e;
 };
 
-__device__ __forceinline__ ME me_zero() { return ME{0.f, kZeroExp}; }
-
-// log-probability (natural log, <= 0) -> (mantissa in [1,2), exponent)
+// log-probability (natural log, <= 0) -> (mantissa in [0.707, 1.414], exponent): round-to-nearest
+// split with the 1.5 * 2^23 trick (no F2I / FRND on the path), one MUFU.EX2
 __device__ __forceinline__ ME me_from_log(float lp) {
-    float x = fmaxf(lp * kLog2e, -16384.f);
-    const float fl = floorf(x);
-    return ME{fast_ex2(x - fl), (int)fl};
+    const float x = fmaxf(lp * kLog2e, -16000.f);
+    const float t = x + 12582912.f;
+    return ME{fast_ex2(x - (t - 12582912.f)), __float_as_int(t) - 0x4B400000};
 }
 
 __device__ __forceinline__ ME me_mul(ME a, ME b) { return ME{a.m * b.m, a.e + b.e}; }
 
-// a + b for mantissas that are 0 or in [1,4); result mantissa in [1,8) (or 0), not normalised
+// a + b: the term with the smaller exponent is scaled by 2^-(exponent gap) (0 once the gap >= 127)
 __device__ __forceinline__ ME me_add(ME a, ME b) {
     const int dd = b.e - a.e;
     const bool b_big = dd > 0;
     const int k = min(abs(dd), 127);
-    const float s = __int_as_float((127 - k) << 23);  // 2^-k, and +0.0 when k == 127
+    const float s = __int_as_float((127 - k) << 23);
     const float big = b_big ? b.m : a.m, small = b_big ? a.m : b.m;
     return ME{fmaf(small, s, big), max(a.e, b.e)};
 }
 
 __device__ __forceinline__ ME me_normalize(ME a) {
     const int bits = __float_as_int(a.m);
-    const bool z = a.m == 0.f;
-    return ME{z ? 0.f : __int_as_float((bits & 0x007fffff) | 0x3f800000),
-              z ? kZeroExp : a.e + (bits >> 23) - 127};
+    return ME{__int_as_float((bits & 0x007fffff) | 0x3f800000), a.e + (bits >> 23) - 127};
 }
 
-// Q16 fixed-point log2 of a normalised value
-__device__ __forceinline__ int me_to_q16(ME a) {
-    const int e = max(min(a.e, 32766), -32767);
-    return e * 65536 + __float2int_rn(fast_lg2(a.m) * 65536.f);
+__device__ __forceinline__ int me_pack(ME a) {  // a normalised -> e16m16, mantissa rounded to nearest
+    const int rb = __float_as_int(a.m) + 0x40;
+    const int e = max(min(a.e + (rb >> 23) - 127, 32767), -32767);
+    return (e << 16) | ((rb >> 7) & 0xFFFF);
+}
+
+__device__ __forceinline__ double me_ln(ME a) {
+    return ((double)a.e + (double)log2f(a.m)) * 0.6931471805599453;
 }
 
 __device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gmem_src) {
@@ -87,6 +90,106 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// DIR 0: alpha (u = j, rows walked upwards); DIR 1: beta (u = U_b - j, rows walked downwards)
+template <int DIR, bool kMultiWarp>
+__device__ __forceinline__ void sweep(const float2* __restrict__ lp2, int Tb, int Ub, int T, int U1, int b,
+                                      int32_t* __restrict__ out, float* __restrict__ costs,
+                                      float* __restrict__ ll_alpha, float2* ring, int2 (*edge)[32]) {
+    const int j = threadIdx.x;  // position along the sweep
+    const int lane = j & 31, warp = j >> 5;
+    const int U1b = Ub + 1;
+    const bool lane_on = j < U1b;
+    const int u = DIR == 0 ? j : Ub - j;
+    const int lag = kMultiWarp ? warp * kLag : 0;
+    const int n_warps_on = (U1b + 31) >> 5;
+    // every warp runs the same number of steps (uniform barriers), rounded up to the unroll
+    const int S = (Tb + Ub + (kMultiWarp ? (n_warps_on - 1) * kLag : 0) + kDepth - 1) / kDepth * kDepth;
+
+    // this thread's cell at progress tau: row t = tau (alpha) or T_b-1-tau (beta)
+    const long long stride = DIR == 0 ? U1 : -U1;
+    const size_t first = (size_t)b * T * U1 + (size_t)(DIR == 0 ? 0 : Tb - 1) * U1 + u;
+    int tau = -lag - j;                                           // progress at step 0
+    const float2* pf = lp2 + first + (long long)tau * stride;      // cell consumed at the step being prefetched
+    int32_t* dst = out + first + (long long)tau * stride;          // cell produced at the current step
+    float2* myring = ring + (size_t)j * kRingStride;
+    const bool thread0 = j == 0;
+
+    // prologue: cells of steps 0 .. kDepth-2
+#pragma unroll
+    for (int k = 0; k < kDepth - 1; ++k) {
+        if (lane_on && (unsigned)(tau + k) < (unsigned)Tb) cp_async_8(myring + k, pf);
+        cp_async_commit();
+        pf += stride;
+    }
+    int tau_pf = tau + kDepth - 1;
+    int es = (-lag - 1) & (kEdgeRing - 1);  // edge slot of diagonal d-1
+
+    ME own{1.f, kZeroExp};    // alpha: alpha(t-1,u) * P_blank(t-1,u);   beta: beta(t+1,u)
+    ME share{1.f, kZeroExp};  // alpha: alpha(t,u)   * P_label(t,u);     beta: beta(t,u)
+
+#pragma unroll 1
+    for (int s0 = 0; s0 < S; s0 += kDepth) {
+#pragma unroll
+        for (int k = 0; k < kDepth; ++k) {
+            if (kMultiWarp && (k % kLag) == 0) __syncthreads();
+            // hand-off from the u-1 neighbour (its value on diagonal d-1)
+            ME in;
+            in.m = __shfl_up_sync(0xffffffffu, share.m, 1);
+            in.e = __shfl_up_sync(0xffffffffu, share.e, 1);
+            if (lane == 0) {
+                if (kMultiWarp && warp > 0) {
+                    const int2 v = edge[es][warp - 1];
+                    in.m = __int_as_float(v.x);
+                    in.e = v.y;
+                } else {
+                    in = ME{1.f, kZeroExp};
+                }
+            }
+            const bool on = lane_on && (unsigned)tau < (unsigned)Tb;
+            cp_async_wait<kDepth - 2>();
+            const float2 lp = myring[k];
+            // refill the slot consumed one step ago with the cell of step s + kDepth - 1
+            if (lane_on && (unsigned)tau_pf < (unsigned)Tb) cp_async_8(myring + (k + kDepth - 1) % kDepth, pf);
+            cp_async_commit();
+
+            const ME pb = me_from_log(lp.x), pl = me_from_log(lp.y);
+            if (tau == 0) {  // first row of this column: nothing arrives from t-1 (alpha) / t+1 (beta)
+                own = ME{1.f, (DIR == 1 && thread0) ? 0 : kZeroExp};
+                if (DIR == 0 && thread0) in = ME{1.f, 0};  // alpha(0,0) = 1
+            }
+            ME val;
+            if (DIR == 0) {
+                val = me_normalize(me_add(own, in));
+                own = me_mul(val, pb);
+                share = me_mul(val, pl);
+            } else {
+                val = me_normalize(me_add(me_mul(own, pb), me_mul(in, pl)));
+                own = val;
+                share = val;
+            }
+            if (on) {
+                *dst = me_pack(val);
+                if (j == Ub && tau == Tb - 1) {
+                    if (DIR == 0) {  // alpha(T-1,U) * P_blank(T-1,U)
+                        if (ll_alpha) ll_alpha[b] = (float)me_ln(me_normalize(own));
+                    } else {         // beta(0,0) = P(y|x)
+                        costs[b] = (float)(-me_ln(val));
+                    }
+                }
+            }
+            if (kMultiWarp) {
+                es = (es + 1) & (kEdgeRing - 1);  // now the slot of diagonal d
+                if (lane == 31) edge[es][warp] = make_int2(__float_as_int(share.m), share.e);
+            }
+            ++tau;
+            ++tau_pf;
+            pf += stride;
+            dst += stride;
+        }
+    }
+    cp_async_wait<0>();
+}
+
 template <bool kMultiWarp>
 __global__ void __launch_bounds__(1024, 1)
 lattice_sweep_kernel(const float2* __restrict__ lp2, const int32_t* __restrict__ act_lens,
@@ -94,105 +197,15 @@ lattice_sweep_kernel(const float2* __restrict__ lp2, const int32_t* __restrict__
                      int32_t* __restrict__ alpha, int32_t* __restrict__ beta,
                      float* __restrict__ costs, float* __restrict__ ll_alpha) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2* ring = reinterpret_cast<float2*>(smem_raw);  // [kDepth][blockDim.x]
-    __shared__ float edge_m[kEdgeRing][32];
-    __shared__ int edge_e[kEdgeRing][32];
-
+    float2* ring = reinterpret_cast<float2*>(smem_raw);  // [blockDim.x][kRingStride]
+    __shared__ int2 edge[kEdgeRing][32];
     const int b = blockIdx.x;
-    const int dir = blockIdx.y;  // 0: alpha (forward), 1: beta (backward)
-    const int j = threadIdx.x;   // position along the sweep: u = j (alpha) or U_b - j (beta)
-    const int lane = j & 31, warp = j >> 5;
-    const int nthreads = blockDim.x;
-
-    int Tb = act_lens[b], Ub = label_lens[b];
-    Tb = min(max(Tb, 1), T);
-    Ub = min(max(Ub, 0), U1 - 1);
-    const int U1b = Ub + 1;
-    const int D = Tb + Ub;  // anti-diagonals of this utterance
-    const bool lane_on = j < U1b;
-    const int u = dir == 0 ? j : Ub - j;
-    const size_t base = (size_t)b * T * U1;
-    const float2* src = lp2 + base;
-    int32_t* dst = (dir == 0 ? alpha : beta) + base;
-    const int lag = kMultiWarp ? warp * kLag : 0;
-    const int n_warps_on = (U1b + 31) >> 5;
-    // every warp runs the same number of steps (uniform barriers), rounded to the barrier period
-    int S = D + (kMultiWarp ? (n_warps_on - 1) * kLag : 0);
-    if (kMultiWarp) S = (S + kLag - 1) / kLag * kLag;
-
-    // cell index at local progress tau (tau = d - j): row t = tau (alpha) or T_b-1-tau (beta)
-    auto cell = [&](int tau) -> int { return (dir == 0 ? tau : Tb - 1 - tau) * U1 + u; };
-    auto prefetch = [&](int s) {  // cell this thread consumes at local step s
-        const int tau = s - lag - j;
-        if (lane_on && tau >= 0 && tau < Tb) cp_async_8(&ring[(s % kDepth) * nthreads + j], src + cell(tau));
-        cp_async_commit();
-    };
-
-#pragma unroll 1
-    for (int s = 0; s < kDepth - 1; ++s) prefetch(s);
-
-    ME own = me_zero();    // alpha: alpha(t-1,u) * P_blank(t-1,u);   beta: beta(t+1,u)
-    ME share = me_zero();  // alpha: alpha(t,u)   * P_label(t,u);     beta: beta(t,u)
-
-#pragma unroll 1
-    for (int s = 0; s < S; ++s) {
-        if (kMultiWarp && (s % kLag) == 0) __syncthreads();
-        const int d = s - lag;
-        const int tau = d - j;
-        const bool on = lane_on && tau >= 0 && tau < Tb;
-
-        // hand-off from the u-1 neighbour (its value on diagonal d-1)
-        ME in;
-        in.m = __shfl_up_sync(0xffffffffu, share.m, 1);
-        in.e = __shfl_up_sync(0xffffffffu, share.e, 1);
-        if (lane == 0) {
-            if (kMultiWarp && warp > 0) {
-                const int slot = (d - 1) & (kEdgeRing - 1);
-                in.m = edge_m[slot][warp - 1];
-                in.e = edge_e[slot][warp - 1];
-            } else {
-                in = me_zero();
-            }
-        }
-
-        cp_async_wait<kDepth - 2>();
-        const float2 lp = on ? ring[(s % kDepth) * nthreads + j] : make_float2(0.f, 0.f);
-        prefetch(s + kDepth - 1);  // refills the slot consumed one step ago
-
-        const ME pb = me_from_log(lp.x), pl = me_from_log(lp.y);
-        ME val;
-        if (dir == 0) {
-            val = me_normalize(me_add(own, in));
-            if (tau == 0 && j == 0) val = ME{1.f, 0};
-            own = me_mul(val, pb);
-            share = me_mul(val, pl);
-        } else {
-            val = me_normalize(me_add(me_mul(own, pb), me_mul(in, pl)));
-            if (tau == 0 && j == 0) val = pb;
-            own = val;
-            share = val;
-        }
-        if (!on) {
-            own = me_zero();
-            share = me_zero();
-        } else {
-            dst[cell(tau)] = me_to_q16(val);
-            if (j == Ub && tau == Tb - 1) {
-                if (dir == 0) {  // alpha(T-1,U) * P_blank(T-1,U)
-                    const ME f = me_normalize(own);
-                    if (ll_alpha) ll_alpha[b] = (float)(((double)f.e + (double)fast_lg2(f.m)) * 0.6931471805599453);
-                } else {         // beta(0,0) = P(y|x)
-                    costs[b] = (float)(-((double)val.e + (double)fast_lg2(val.m)) * 0.6931471805599453);
-                }
-            }
-        }
-        if (kMultiWarp && lane == 31) {
-            const int slot = d & (kEdgeRing - 1);
-            edge_m[slot][warp] = share.m;
-            edge_e[slot][warp] = share.e;
-        }
-    }
-    cp_async_wait<0>();
+    const int Tb = min(max(act_lens[b], 1), T);
+    const int Ub = min(max(label_lens[b], 0), U1 - 1);
+    if (blockIdx.y == 0)
+        sweep<0, kMultiWarp>(lp2, Tb, Ub, T, U1, b, alpha, costs, ll_alpha, ring, edge);
+    else
+        sweep<1, kMultiWarp>(lp2, Tb, Ub, T, U1, b, beta, costs, ll_alpha, ring, edge);
 }
 
 }  // namespace
@@ -203,7 +216,7 @@ int launch_lattice_sweep(const float2* lp2, const int32_t* act_lens, const int32
     if (B == 0) return RNNTB200_STATUS_SUCCESS;
     if (U1 > 1024) return RNNTB200_STATUS_INVALID_VALUE;
     const int threads = ((U1 + 31) / 32) * 32;
-    const size_t smem = (size_t)kDepth * threads * sizeof(float2);  // <= 128 KiB at U1 = 1024
+    const size_t smem = (size_t)kRingStride * threads * sizeof(float2);  // <= 136 KiB at U1 = 1024
     dim3 grid(B, 2);
     if (threads <= 32) {
         lattice_sweep_kernel<false><<<grid, threads, smem, stream>>>(lp2, act_lens, label_lens, T, U1,

@@ -39,11 +39,13 @@ class _AddTanhRNNT(torch.autograd.Function):
         lse = torch.empty(B, T, U1, **f32)
         alpha, beta = (torch.empty(B, T, U1, device=enc.device, dtype=torch.int32) for _ in range(2))
         lib = _lib.load()
+        ws_bytes = lib.rnntb200_joint_at_workspace_bytes(V, H, gemm)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=enc.device) if ws_bytes else None
         with torch.cuda.device(enc.device):
             _lib.check(lib.rnntb200_joint_at_fwd(
                 _ptr(enc), _ptr(dec), _ptr(weight), _ptr(bias), gemm, _ptr(labels), _ptr(act_lens),
                 _ptr(label_lens), B, T, U1, V, H, blank, _ptr(costs), _ptr(lp2), _ptr(lse),
-                _ptr(alpha), _ptr(beta), _stream()), "rnntb200_joint_at_fwd")
+                _ptr(alpha), _ptr(beta), _ptr(ws), ws_bytes, _stream()), "rnntb200_joint_at_fwd")
         ctx.save_for_backward(enc, dec, weight, bias, labels, act_lens, label_lens, lp2, lse, alpha,
                               beta)
         ctx.blank, ctx.gemm = blank, gemm
@@ -60,12 +62,14 @@ class _AddTanhRNNT(torch.autograd.Function):
         d_enc, d_dec = torch.empty_like(enc), torch.empty_like(dec)
         d_w, d_b = torch.empty_like(weight), torch.empty_like(bias)
         lib = _lib.load()
+        ws_bytes = lib.rnntb200_joint_at_workspace_bytes(V, H, ctx.gemm)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=enc.device) if ws_bytes else None
         with torch.cuda.device(enc.device):
             _lib.check(lib.rnntb200_joint_at_bwd(
                 _ptr(enc), _ptr(dec), _ptr(weight), _ptr(bias), ctx.gemm, _ptr(labels),
                 _ptr(act_lens), _ptr(label_lens), B, T, U1, V, H, ctx.blank, _ptr(lp2), _ptr(lse),
                 _ptr(alpha), _ptr(beta), _ptr(grad_costs), _ptr(d_enc), _ptr(d_dec), _ptr(d_w),
-                _ptr(d_b), _stream()), "rnntb200_joint_at_bwd")
+                _ptr(d_b), _ptr(ws), ws_bytes, _stream()), "rnntb200_joint_at_bwd")
         return d_enc, d_dec, d_w, d_b, None, None, None, None, None
 
 

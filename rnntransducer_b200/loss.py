@@ -78,7 +78,7 @@ class _DenseRNNT(torch.autograd.Function):
         costs = torch.empty(B, **f32)
         lp2 = torch.empty(B, T, U1, 2, **f32)
         lse = torch.empty(B, T, U1, **f32)
-        alpha, beta = (torch.empty(B, T, U1, device=dev, dtype=torch.int32) for _ in range(2))  # Q16
+        alpha, beta = (torch.empty(B, T, U1, device=dev, dtype=torch.int32) for _ in range(2))  # e16m16
         lib = _lib.load()
         with torch.cuda.device(dev):
             _lib.check(lib.rnntb200_loss_dense_fwd(

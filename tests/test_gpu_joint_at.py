@@ -50,7 +50,7 @@ def test_add_tanh_matches_torchaudio_joiner_golden(cuda_lib, name, gemm):
 
 @pytest.mark.parametrize("gemm", ["fp32", "bf16"])
 @pytest.mark.parametrize("shape", [(3, 33, 9, 73, 64), (2, 21, 18, 200, 96), (4, 9, 3, 5, 40),
-                                   (2, 50, 12, 73, 512)])
+                                   (2, 50, 12, 73, 512), (2, 20, 10, 300, 128), (3, 70, 20, 73, 256)])
 def test_add_tanh_matches_cpu_restatement(cuda_lib, oracle_lib, shape, gemm):
     B, T, U, V, H = shape
     d = synthetic.make_batch(B, T, U, V, H, mode="add_tanh", ragged=True, seed=55 + V)

@@ -165,7 +165,7 @@ def test_lattice_sweep_abi_alpha_beta(cuda_lib, oracle_lib):
     lp2 = torch.stack([lp[..., 0], lp_label], -1).contiguous().cuda()
     al, ll = dev(d["act_lens"]), dev(d["label_lens"])
     f32 = dict(device="cuda", dtype=torch.float32)
-    alpha, beta = (torch.zeros(B, T, U1, device="cuda", dtype=torch.int32) for _ in range(2))  # Q16
+    alpha, beta = (torch.zeros(B, T, U1, device="cuda", dtype=torch.int32) for _ in range(2))  # e16m16
     costs, ll_alpha = torch.zeros(B, **f32), torch.zeros(B, **f32)
     st = cuda_lib.rnntb200_lattice_sweep(lp2.data_ptr(), al.data_ptr(), ll.data_ptr(), B, T, U1,
                                          alpha.data_ptr(), beta.data_ptr(), costs.data_ptr(),
@@ -174,8 +174,10 @@ def test_lattice_sweep_abi_alpha_beta(cuda_lib, oracle_lib):
     torch.cuda.synchronize()
     np.testing.assert_allclose(costs.cpu().numpy(), ref["costs"], rtol=LOSS_RTOL)
     np.testing.assert_allclose(-ll_alpha.cpu().numpy(), ref["costs"], rtol=LOSS_RTOL)
-    # planes are Q16 fixed-point base-2 logs (include/rnnt_b200.h): ln(x) = q * ln2 / 65536
-    to_ln = lambda q: q.cpu().numpy().astype(np.float64) * (np.log(2.0) / 65536.0)
+    # planes are e16m16 wide-exponent floats (include/rnnt_b200.h)
+    def to_ln(q):
+        q = q.cpu().numpy().astype(np.int64)
+        return ((q >> 16) + np.log2(1.0 + (q & 0xFFFF) / 65536.0)) * np.log(2.0)
     ref64 = oracle_lib.rnnt_loss_cpu(d["logits"].numpy(), d["labels"].numpy(), d["act_lens"].numpy(),
                                      d["label_lens"].numpy(), 0, want_alpha_beta=True, dtype=np.float64)
     for b in range(B):
