@@ -34,7 +34,8 @@ namespace rnntb200 {
 
 namespace {
 
-constexpr int kDepth = 16;        // cp.async ring depth (diagonals in flight per thread) = unroll
+constexpr int kDepth = 16;        // cp.async ring depth (diagonals in flight per thread)
+constexpr int kUnroll = 8;        // steps per loop body = half a ring = kLag
 constexpr int kRingStride = 17;   // float2 slots per thread (+1 pad: conflict-free 8-byte accesses)
 constexpr int kLag = 8;           // diagonals warp w trails warp w-1
 constexpr int kEdgeRing = 32;     // >= 2*kLag + 1 slots for warp-boundary values
@@ -90,7 +91,10 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-// DIR 0: alpha (u = j, rows walked upwards); DIR 1: beta (u = U_b - j, rows walked downwards)
+// DIR 0: alpha (u = j, rows walked upwards); DIR 1: beta (u = U_b - j, rows walked downwards).
+// The loop is software-pipelined: the (lp_blank, lp_label) pair of step s+1 is read from the ring
+// and split into (mantissa, exponent) form during step s, so the only work between receiving the
+// neighbour's value and handing the new value on is add -> normalise -> multiply.
 template <int DIR, bool kMultiWarp>
 __device__ __forceinline__ void sweep(const float2* __restrict__ lp2, int Tb, int Ub, int T, int U1, int b,
                                       int32_t* __restrict__ out, float* __restrict__ costs,
@@ -103,21 +107,23 @@ __device__ __forceinline__ void sweep(const float2* __restrict__ lp2, int Tb, in
     const int lag = kMultiWarp ? warp * kLag : 0;
     const int n_warps_on = (U1b + 31) >> 5;
     // every warp runs the same number of steps (uniform barriers), rounded up to the unroll
-    const int S = (Tb + Ub + (kMultiWarp ? (n_warps_on - 1) * kLag : 0) + kDepth - 1) / kDepth * kDepth;
+    const int S = (Tb + Ub + (kMultiWarp ? (n_warps_on - 1) * kLag : 0) + kUnroll - 1) / kUnroll * kUnroll;
 
     // this thread's cell at progress tau: row t = tau (alpha) or T_b-1-tau (beta)
     const long long stride = DIR == 0 ? U1 : -U1;
     const size_t first = (size_t)b * T * U1 + (size_t)(DIR == 0 ? 0 : Tb - 1) * U1 + u;
     int tau = -lag - j;                                           // progress at step 0
-    const float2* pf = lp2 + first + (long long)tau * stride;      // cell consumed at the step being prefetched
+    const float2* pf = lp2 + first + (long long)tau * stride;      // cell of the step being prefetched
     int32_t* dst = out + first + (long long)tau * stride;          // cell produced at the current step
-    float2* myring = ring + (size_t)j * kRingStride;
+    float2* cur = ring + (size_t)j * kRingStride;                  // ring half of steps s0 .. s0+7
+    float2* oth = cur + kUnroll;                                   // ring half of the next 8 steps
     const bool thread0 = j == 0;
+    const bool from_edge = kMultiWarp && lane == 0 && warp > 0;
 
-    // prologue: cells of steps 0 .. kDepth-2
+    // prologue: cells of steps 0 .. kDepth-2 (slot of step s = s mod 16: cur[0..7], oth[0..6])
 #pragma unroll
     for (int k = 0; k < kDepth - 1; ++k) {
-        if (lane_on && (unsigned)(tau + k) < (unsigned)Tb) cp_async_8(myring + k, pf);
+        if (lane_on && (unsigned)(tau + k) < (unsigned)Tb) cp_async_8(k < kUnroll ? cur + k : oth + (k - kUnroll), pf);
         cp_async_commit();
         pf += stride;
     }
@@ -126,37 +132,33 @@ __device__ __forceinline__ void sweep(const float2* __restrict__ lp2, int Tb, in
 
     ME own{1.f, kZeroExp};    // alpha: alpha(t-1,u) * P_blank(t-1,u);   beta: beta(t+1,u)
     ME share{1.f, kZeroExp};  // alpha: alpha(t,u)   * P_label(t,u);     beta: beta(t,u)
+    ME last{1.f, kZeroExp};   // value at the terminal cell (alpha(T-1,U) P_blank / beta(0,0))
+
+    cp_async_wait<kDepth - 2>();
+    ME pb = me_from_log(cur[0].x), pl = me_from_log(cur[0].y);  // factors of step 0
 
 #pragma unroll 1
-    for (int s0 = 0; s0 < S; s0 += kDepth) {
+    for (int s0 = 0; s0 < S; s0 += kUnroll) {
+        if (kMultiWarp) __syncthreads();  // kLag == kUnroll: one barrier per 8 diagonals
 #pragma unroll
-        for (int k = 0; k < kDepth; ++k) {
-            if (kMultiWarp && (k % kLag) == 0) __syncthreads();
+        for (int k = 0; k < kUnroll; ++k) {
             // hand-off from the u-1 neighbour (its value on diagonal d-1)
             ME in;
             in.m = __shfl_up_sync(0xffffffffu, share.m, 1);
             in.e = __shfl_up_sync(0xffffffffu, share.e, 1);
-            if (lane == 0) {
-                if (kMultiWarp && warp > 0) {
-                    const int2 v = edge[es][warp - 1];
-                    in.m = __int_as_float(v.x);
-                    in.e = v.y;
-                } else {
-                    in = ME{1.f, kZeroExp};
-                }
-            }
-            const bool on = lane_on && (unsigned)tau < (unsigned)Tb;
-            cp_async_wait<kDepth - 2>();
-            const float2 lp = myring[k];
-            // refill the slot consumed one step ago with the cell of step s + kDepth - 1
-            if (lane_on && (unsigned)tau_pf < (unsigned)Tb) cp_async_8(myring + (k + kDepth - 1) % kDepth, pf);
-            cp_async_commit();
+            const int2 ev = kMultiWarp ? edge[es][(warp + 31) & 31] : make_int2(0, 0);
 
-            const ME pb = me_from_log(lp.x), pl = me_from_log(lp.y);
-            if (tau == 0) {  // first row of this column: nothing arrives from t-1 (alpha) / t+1 (beta)
-                own = ME{1.f, (DIR == 1 && thread0) ? 0 : kZeroExp};
-                if (DIR == 0 && thread0) in = ME{1.f, 0};  // alpha(0,0) = 1
-            }
+            // off the dependent chain: refill the ring, fetch and split the factors of step s+1
+            if (lane_on && (unsigned)tau_pf < (unsigned)Tb) cp_async_8(k == 0 ? oth + kUnroll - 1 : cur + k - 1, pf);
+            cp_async_commit();
+            cp_async_wait<kDepth - 2>();
+            const float2 lpn = k + 1 < kUnroll ? cur[k + 1] : oth[0];
+            const ME pbn = me_from_log(lpn.x), pln = me_from_log(lpn.y);
+
+            if (lane == 0) in = from_edge ? ME{__int_as_float(ev.x), ev.y} : ME{1.f, kZeroExp};
+            const bool first_row = tau == 0;  // nothing arrives from t-1 (alpha) / t+1 (beta)
+            if (first_row) own = ME{1.f, (DIR == 1 && thread0) ? 0 : kZeroExp};
+            if (DIR == 0 && first_row && thread0) in = ME{1.f, 0};  // alpha(0,0) = 1
             ME val;
             if (DIR == 0) {
                 val = me_normalize(me_add(own, in));
@@ -167,27 +169,32 @@ __device__ __forceinline__ void sweep(const float2* __restrict__ lp2, int Tb, in
                 own = val;
                 share = val;
             }
-            if (on) {
-                *dst = me_pack(val);
-                if (j == Ub && tau == Tb - 1) {
-                    if (DIR == 0) {  // alpha(T-1,U) * P_blank(T-1,U)
-                        if (ll_alpha) ll_alpha[b] = (float)me_ln(me_normalize(own));
-                    } else {         // beta(0,0) = P(y|x)
-                        costs[b] = (float)(-me_ln(val));
-                    }
-                }
-            }
+            const bool on = lane_on && (unsigned)tau < (unsigned)Tb;
+            if (on) *dst = me_pack(val);
+            if (on && j == Ub && tau == Tb - 1) last = DIR == 0 ? own : val;
             if (kMultiWarp) {
                 es = (es + 1) & (kEdgeRing - 1);  // now the slot of diagonal d
                 if (lane == 31) edge[es][warp] = make_int2(__float_as_int(share.m), share.e);
             }
+            pb = pbn;
+            pl = pln;
             ++tau;
             ++tau_pf;
             pf += stride;
             dst += stride;
         }
+        float2* tmp = cur;
+        cur = oth;
+        oth = tmp;
     }
     cp_async_wait<0>();
+    if (lane_on && j == Ub) {
+        if (DIR == 0) {
+            if (ll_alpha) ll_alpha[b] = (float)me_ln(me_normalize(last));
+        } else {
+            costs[b] = (float)(-me_ln(last));
+        }
+    }
 }
 
 template <bool kMultiWarp>
@@ -222,11 +229,10 @@ int launch_lattice_sweep(const float2* lp2, const int32_t* act_lens, const int32
         lattice_sweep_kernel<false><<<grid, threads, smem, stream>>>(lp2, act_lens, label_lens, T, U1,
                                                                       alpha, beta, costs, ll_alpha);
     } else {
-        if (smem > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(lattice_sweep_kernel<true>,
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return status_from_cuda(e);
-        }
+        // static (edge ring, 8 KiB) + dynamic may exceed the 48 KiB default: always opt in
+        cudaError_t e = cudaFuncSetAttribute(lattice_sweep_kernel<true>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return status_from_cuda(e);
         lattice_sweep_kernel<true><<<grid, threads, smem, stream>>>(lp2, act_lens, label_lens, T, U1,
                                                                      alpha, beta, costs, ll_alpha);
     }

@@ -18,6 +18,6 @@ python bench.py --steps 3 --warmup 3 --no-cpu-baseline "$@" > $OUT/${TAG}_plain.
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/${TAG}_launches.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline "$@" > $OUT/${TAG}_ncu_launches.log 2>&1
 python bench.py --steps 3 --warmup 3 --no-cpu-baseline "$@" > $OUT/${TAG}_plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:$KREGEX -s 6 -c 2 -f -o $OUT/${TAG}_prof \
+ncu --set full --clock-control none --import-source on -k regex:$KREGEX -s 9 -c 6 -f -o $OUT/${TAG}_prof \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline "$@" > $OUT/${TAG}_ncu_full.log 2>&1
 ls -la $OUT | tail -5
