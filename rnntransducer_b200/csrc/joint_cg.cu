@@ -13,6 +13,17 @@
 
 namespace rnntb200 {
 
+// joint_cg_mm.cu: the factorised (exp(a+b) = exp(a) exp(b)) kernels used for V <= 128
+bool cg_mm_supported(int V);
+int cg_mm_tile_rows();
+int launch_cg_lse_mm(const float* penc, const float* pdec, const int32_t* labels, const int32_t* act_lens,
+                     const int32_t* label_lens, int B, int T, int U1, int V, int blank, float2* lp2,
+                     float* lse, cudaStream_t stream);
+int launch_cg_grad_mm(const float* penc, const float* pdec, const int32_t* labels, const int32_t* act_lens,
+                      const int32_t* label_lens, int B, int T, int U1, int V, int blank, const float* lse,
+                      const int32_t* alpha, const int32_t* beta, const float* grad_costs, float* d_penc,
+                      float* d_pdec, float* partial, cudaStream_t stream);
+
 namespace {
 
 // ---------------------------------------------------------------------------------------------
@@ -206,6 +217,8 @@ int launch_cg_lse(const float* penc, const float* pdec, const int32_t* labels, c
                   const int32_t* label_lens, int B, int T, int U1, int V, int blank, float2* lp2,
                   float* lse, cudaStream_t stream) {
     if ((long long)B * T * U1 == 0) return RNNTB200_STATUS_SUCCESS;
+    if (cg_mm_supported(V))
+        return launch_cg_lse_mm(penc, pdec, labels, act_lens, label_lens, B, T, U1, V, blank, lp2, lse, stream);
     const int Vs = V | 1;  // odd row stride: lanes reading different rows hit different banks
     const size_t smem = (size_t)(kTT + kUU) * Vs * sizeof(float);
     if (smem > 227 * 1024) return RNNTB200_STATUS_INVALID_VALUE;
@@ -221,7 +234,8 @@ int launch_cg_lse(const float* penc, const float* pdec, const int32_t* labels, c
 
 size_t cg_grad_workspace_bytes(int B, int T, int U1, int V, int deterministic) {
     if (!deterministic) return 0;
-    const size_t n_tiles = (T + kGT - 1) / kGT;
+    const int rows = cg_mm_supported(V) ? cg_mm_tile_rows() : kGT;
+    const size_t n_tiles = (T + rows - 1) / rows;
     return (size_t)B * n_tiles * U1 * V * sizeof(float);
 }
 
@@ -231,7 +245,9 @@ int launch_cg_grad(const float* penc, const float* pdec, const int32_t* labels, 
                    float* d_penc, float* d_pdec, int deterministic, void* workspace,
                    size_t workspace_bytes, cudaStream_t stream) {
     if ((long long)B * T * U1 == 0) return RNNTB200_STATUS_SUCCESS;
-    const int n_tiles = (T + kGT - 1) / kGT;
+    const bool mm = cg_mm_supported(V);
+    const int rows = mm ? cg_mm_tile_rows() : kGT;
+    const int n_tiles = (T + rows - 1) / rows;
     float* partial = nullptr;
     if (deterministic) {
         if (!workspace || workspace_bytes < cg_grad_workspace_bytes(B, T, U1, V, 1))
@@ -241,12 +257,18 @@ int launch_cg_grad(const float* penc, const float* pdec, const int32_t* labels, 
         cudaError_t e = cudaMemsetAsync(d_pdec, 0, (size_t)B * U1 * V * sizeof(float), stream);
         if (e != cudaSuccess) return RNNTB200_STATUS_MEMOPS_FAILED;
     }
-    const int threads = min(256, ((V + 31) / 32) * 32);
-    dim3 grid(n_tiles, B);
-    cg_grad_kernel<<<grid, threads, 0, stream>>>(penc, pdec, labels, act_lens, label_lens, T, U1, V,
-                                                 blank, lse, alpha, beta, grad_costs, d_penc,
-                                                 d_pdec, partial);
-    int st = launch_status();
+    int st;
+    if (mm) {
+        st = launch_cg_grad_mm(penc, pdec, labels, act_lens, label_lens, B, T, U1, V, blank, lse, alpha, beta,
+                               grad_costs, d_penc, d_pdec, partial, stream);
+    } else {
+        const int threads = min(256, ((V + 31) / 32) * 32);
+        dim3 grid(n_tiles, B);
+        cg_grad_kernel<<<grid, threads, 0, stream>>>(penc, pdec, labels, act_lens, label_lens, T, U1, V,
+                                                     blank, lse, alpha, beta, grad_costs, d_penc,
+                                                     d_pdec, partial);
+        st = launch_status();
+    }
     if (st != RNNTB200_STATUS_SUCCESS || !deterministic) return st;
     const size_t uv = (size_t)U1 * V;
     dim3 rgrid((unsigned)((uv + 255) / 256), B);

@@ -95,6 +95,21 @@ def test_fused_matches_cpu_restatement(cuda_lib, oracle_lib, shape):
             np.testing.assert_allclose(r[k], ref[k], atol=GRAD_ATOL + own, err_msg=k)
 
 
+@pytest.mark.parametrize("scale", [8.0, 40.0, 150.0])
+def test_fused_extreme_logit_ranges(cuda_lib, oracle_lib, scale):
+    """exp(P_enc + P_dec) is evaluated as exp(P_enc) * exp(P_dec) (joint_cg_mm.cu).  With logit ranges
+    of tens to hundreds of nats in BOTH projections and peaks that do not line up, the factorised
+    partition underflows and cells must take the exact path; results still match the oracle."""
+    d = synthetic.make_batch(3, 21, 7, 11, 16, ragged=True, seed=321)
+    d["weight"] = d["weight"] * scale
+    ref64 = ref_step(d, dtype=torch.float64)
+    for det in (False, True):
+        r = fused_step({k: v.cuda() for k, v in d.items()}, deterministic=det)
+        np.testing.assert_allclose(r["costs"], ref64["costs"], rtol=2e-5)
+        for k in ("d_enc", "d_dec", "d_weight", "d_bias"):
+            np.testing.assert_allclose(r[k], ref64[k], atol=param_atol(ref64[k], 1e-4 * scale), err_msg=k)
+
+
 def test_deterministic_mode_is_bit_reproducible(cuda_lib):
     d = synthetic.make_batch(4, 64, 17, 73, 32, ragged=True, seed=5, device="cuda")
     a = fused_step(d, deterministic=True)
