@@ -31,24 +31,44 @@ constexpr float kTinyLog2 = -66.f;  // log2 of the partition threshold below whi
 constexpr int kFT = 32;    // frames per CTA
 constexpr int kFUC = 64;   // label positions per staged chunk
 
-__device__ __forceinline__ void stage_rows_exp(float* dst, float* rowmax, const float* __restrict__ src,
-                                               int n_rows, int n_valid, int V, int Vs) {
-    // one warp per row: row max (base 2), then A = 2^(x - max); rows >= n_valid become zeros
+// Stage n_rows rows of src ([.., V] row-major, contiguous) as E = 2^(x log2e - rowmax): a bulk
+// coalesced copy with every load in flight at once, then (after a barrier) one warp per row takes
+// the row maximum and exponentiates in place.  Rows >= n_valid become zeros.  Optionally records
+// the normalised base-2 log at column `col` of every row (the blank column), which would underflow
+// if it were recovered from E.  Contains two block barriers.
+__device__ __forceinline__ void stage_rows_exp(float* dst, float* rowmax, float* log_at_col, int col,
+                                               const float* __restrict__ src, int n_rows, int n_valid,
+                                               int V, int Vs, float* log_at_cols = nullptr,
+                                               const int* cols = nullptr) {
+    const int n = n_valid * V;
+    for (int i = threadIdx.x; i < n_rows * V; i += blockDim.x) {
+        const int r = i / V, v = i - r * V;
+        dst[r * Vs + v] = i < n ? __ldg(src + i) * kLog2e : 0.f;
+    }
+    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
     for (int r = warp; r < n_rows; r += n_warps) {
         float* d = dst + r * Vs;
-        if (r >= n_valid) {
-            for (int v = lane; v < V; v += 32) d[v] = 0.f;
-            if (lane == 0) rowmax[r] = 0.f;
+        if (r >= n_valid) {  // already zeros
+            if (lane == 0) {
+                rowmax[r] = 0.f;
+                if (log_at_col) log_at_col[r] = 0.f;
+                if (log_at_cols) log_at_cols[r] = 0.f;
+            }
             continue;
         }
-        const float* s = src + (size_t)r * V;
         float m = -INFINITY;
-        for (int v = lane; v < V; v += 32) m = fmaxf(m, __ldg(s + v));
-        m = warp_max(m) * kLog2e;
-        for (int v = lane; v < V; v += 32) d[v] = fast_ex2(fmaf(__ldg(s + v), kLog2e, -m));
-        if (lane == 0) rowmax[r] = m;
+        for (int v = lane; v < V; v += 32) m = fmaxf(m, d[v]);
+        m = warp_max(m);
+        if (lane == 0) {
+            rowmax[r] = m;
+            if (log_at_col) log_at_col[r] = d[col] - m;
+            if (log_at_cols) log_at_cols[r] = cols[r] >= 0 ? d[cols[r]] - m : 0.f;  // per-row column
+        }
+        __syncwarp();
+        for (int v = lane; v < V; v += 32) d[v] = fast_ex2(d[v] - m);
     }
+    __syncthreads();
 }
 
 __global__ void __launch_bounds__(128)
@@ -61,17 +81,18 @@ cg_lse_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec,
     float* Bs = As + kFT * Vs;      // [kFUC][Vs]
     float* mA = Bs + kFUC * Vs;     // [kFT]   row maxima, base 2
     float* mB = mA + kFT;           // [kFUC]
+    float* lAb = mB + kFUC;         // [kFT]   log2 A[t][blank]
+    float* lBb = lAb + kFT;         // [kFUC]  log2 B[u][blank]
     const int b = blockIdx.y, t0 = blockIdx.x * kFT;
     const int Tb = min(__ldg(act_lens + b), T), Ub = min(__ldg(label_lens + b), U1 - 1);
     if (t0 >= Tb) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ty = lane >> 3, tx = lane & 7;
 
-    stage_rows_exp(As, mA, penc + ((size_t)b * T + t0) * V, kFT, min(kFT, Tb - t0), V, Vs);
+    stage_rows_exp(As, mA, lAb, blank, penc + ((size_t)b * T + t0) * V, kFT, min(kFT, Tb - t0), V, Vs);
     for (int u0 = 0; u0 <= Ub; u0 += kFUC) {
-        __syncthreads();
-        stage_rows_exp(Bs, mB, pdec + ((size_t)b * U1 + u0) * V, kFUC, min(kFUC, Ub + 1 - u0), V, Vs);
-        __syncthreads();
+        if (u0 > 0) __syncthreads();  // every warp is done with the previous chunk
+        stage_rows_exp(Bs, mB, lBb, blank, pdec + ((size_t)b * U1 + u0) * V, kFUC, min(kFUC, Ub + 1 - u0), V, Vs);
         for (int item = warp; item < (kFT / 16) * (kFUC / 16); item += 4) {
             const int rt = (item / (kFUC / 16)) * 16 + 4 * ty;  // first of this thread's 4 frames
             const int ru = (item % (kFUC / 16)) * 16 + 2 * tx;  // first of its 2 label positions
@@ -97,27 +118,24 @@ cg_lse_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec,
                 for (int k = 0; k < 2; ++k) {
                     const int t = t0 + rt + i, u = u0 + ru + k;
                     if (t >= Tb || u > Ub) continue;
-                    const float* ar = a + i * Vs;
-                    const float* br = bb + k * Vs;
                     const float mm = mA[rt + i] + mB[ru + k];
+                    const float* pe = penc + ((size_t)b * T + t) * V;
+                    const float* pd = pdec + ((size_t)b * U1 + u) * V;
                     float lgs = fast_lg2(s[i][k]);
                     const int y = u < Ub ? __ldg(labels + (size_t)b * (U1 - 1) + u) : blank;
                     float lb2, ll2;
                     if (lgs < kTinyLog2) {
                         // exact path: the row peaks do not line up, redo this cell in the log domain
-                        const float* pe = penc + ((size_t)b * T + t) * V;
-                        const float* pd = pdec + ((size_t)b * U1 + u) * V;
                         float mx = -INFINITY;
                         for (int v = 0; v < V; ++v) mx = fmaxf(mx, (pe[v] + pd[v]) * kLog2e);
                         float se = 0.f;
                         for (int v = 0; v < V; ++v) se += fast_ex2((pe[v] + pd[v]) * kLog2e - mx);
                         lgs = mx + fast_lg2(se) - mm;
-                        lb2 = (pe[blank] + pd[blank]) * kLog2e - mm - lgs;
-                        ll2 = (pe[y] + pd[y]) * kLog2e - mm - lgs;
-                    } else {
-                        lb2 = fast_lg2(ar[blank] * br[blank]) - lgs;
-                        ll2 = fast_lg2(ar[y] * br[y]) - lgs;
                     }
+                    // blank / label log-probs straight in the log domain (A * B would underflow
+                    // below 2^-126 although such steps are representable -- and may be on the path)
+                    lb2 = lAb[rt + i] + lBb[ru + k] - lgs;
+                    ll2 = (__ldg(pe + y) + __ldg(pd + y)) * kLog2e - mm - lgs;
                     const size_t c = ((size_t)b * T + t) * U1 + u;
                     lp2[c] = make_float2(fmaxf(lb2 * kLn2, kNegInf), u < Ub ? fmaxf(ll2 * kLn2, kNegInf) : 0.f);
                     lse_out[c] = (mm + lgs) * kLn2;
@@ -129,9 +147,14 @@ cg_lse_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec,
 // =================================================================================================
 // backward: CTA = (utterance, 32 frames), 128 threads as 8 (ty) x 16 (tx); thread tile for
 // E = C B: frames 4ty..4ty+3 x columns tx + 16c; for D = C^T A: positions ty + 8i x the same columns.
+// The blank / label corrections ride along as rank-1 style terms with a fixed summation order, so
+// the only order-dependent arithmetic is the cross-tile accumulation of d_pdec (fp32 atomics, or
+// per-tile slabs + a fixed-order reduction in deterministic mode) and the cold exact path.
 constexpr int kGT2 = 32;   // frames per CTA
 constexpr int kGUC2 = 48;  // label positions per chunk (6 per thread row group)
 constexpr int kCs = kGUC2 + 1;
+constexpr int kCellsPerThread = kGT2 * kGUC2 / 128;  // 12
+constexpr int kBatch = 4;  // cells whose global loads are in flight together
 
 template <int NC>
 __global__ void __launch_bounds__(128)
@@ -145,12 +168,18 @@ cg_grad_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec
     extern __shared__ float smem[];
     float* As = smem;                  // [32][Vs]  A = 2^(P_enc - max)
     float* Bs = As + kGT2 * Vs;        // [48][Vs]  B chunk
-    float* Oe = Bs + kGUC2 * Vs;       // [32][Vs]  corrections of d_penc (negative), all chunks
-    float* Cs = Oe + kGT2 * Vs;        // [32][49]  C chunk
-    float* mA = Cs + kGT2 * kCs;       // [32]
+    float* Xs = Bs + kGUC2 * Vs;       // [32][Vs]  exact-path additions to d_penc (cold)
+    float* Cs = Xs + kGT2 * Vs;        // [32][49]  C chunk
+    float* CBs = Cs + kGT2 * kCs;      // [32][49]  blank corrections
+    float* CLs = CBs + kGT2 * kCs;     // [32][49]  label corrections
+    float* mA = CLs + kGT2 * kCs;      // [32] row maxima (base 2)
     float* mB = mA + kGT2;             // [48]
-    float* ub = mB + kGUC2;            // [48] sum_t corr_blank
+    float* lAb = mB + kGUC2;           // [32] log2 A[t][blank]
+    float* lBb = lAb + kGT2;           // [48] log2 B[u][blank]
+    float* ub = lBb + kGUC2;           // [48] sum_t corr_blank
     float* ul = ub + kGUC2;            // [48] sum_t corr_label
+    float* rb = ul + kGUC2;            // [32] sum_u corr_blank (all chunks)
+    float* lBy = rb + kGT2;            // [48] log2 B[u][y_u]
     __shared__ int ys[kGUC2];
     __shared__ int n_exact;
 
@@ -173,74 +202,106 @@ cg_grad_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec
     const int llq = beta[(size_t)b * T * U1];  // beta(0,0) = P(y|x), e16m16
     const int rows_t = min(kGT2, Tb - t0);
 
-    stage_rows_exp(As, mA, penc + ((size_t)b * T + t0) * V, kGT2, rows_t, V, Vs);
-    for (int i = tid; i < kGT2 * Vs; i += 128) Oe[i] = 0.f;
+    for (int i = tid; i < kGT2 * Vs; i += 128) Xs[i] = 0.f;
+    if (tid < kGT2) rb[tid] = 0.f;
     if (tid == 0) n_exact = 0;
+    stage_rows_exp(As, mA, lAb, blank, penc + ((size_t)b * T + t0) * V, kGT2, rows_t, V, Vs);
 
-    float E[4][NC];
+    float E[4][NC], EL[4][NC];  // (C B)[t][v] and the label correction sum_{u: y_u = v} cl[t][u]
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int c = 0; c < NC; ++c) E[i][c] = 0.f;
+        for (int c = 0; c < NC; ++c) E[i][c] = EL[i][c] = 0.f;
 
     for (int u0 = 0; u0 < U1; u0 += kGUC2) {
         if (!slab && u0 > Ub) break;  // nothing left to add (slabs must be written in full)
         const int rows_u = max(0, min(kGUC2, Ub + 1 - u0));
-        __syncthreads();  // previous chunk fully consumed
-        stage_rows_exp(Bs, mB, pdec + ((size_t)b * U1 + u0) * V, kGUC2, rows_u, V, Vs);
+        if (u0 > 0) __syncthreads();  // previous chunk fully consumed
         if (tid < kGUC2) {
             const int u = u0 + tid;
             ys[tid] = u < Ub ? __ldg(labels + (size_t)b * (U1 - 1) + u) : -1;
-            ub[tid] = 0.f;
-            ul[tid] = 0.f;
         }
-        __syncthreads();
-        // per-cell scalars of the (32 x 48) block: C and the two corrections
-        for (int i = tid; i < kGT2 * kGUC2; i += 128) {
-            const int r = i / kGUC2, uu = i - r * kGUC2;
-            const int t = t0 + r, u = u0 + uu;
-            float cval = 0.f;
-            if (t < Tb && u <= Ub) {
-                const size_t c = ((size_t)b * T + t) * U1 + u;
-                const int aq = alpha[c];
-                const float shift = mA[r] + mB[uu] - lse[c] * kLog2e;  // -log2 S(t,u)
-                const float* ar = As + r * Vs;
-                const float* br = Bs + uu * Vs;
-                const int y = ys[uu];
-                const bool exact = shift > -kTinyLog2;
-                float pb, pl = 0.f;  // p(blank), p(label) of the cell
-                if (!exact) {
-                    cval = gc * fast_ex2(e16m16_log2_ratio(aq, beta[c], llq) + shift);
-                    pb = ar[blank] * br[blank] * fast_ex2(shift);
-                    if (y >= 0) pl = ar[y] * br[y] * fast_ex2(shift);
-                } else {
-                    atomicAdd(&n_exact, 1);
-                    const float* pe = penc + ((size_t)b * T + t) * V;
-                    const float* pd = pdec + ((size_t)b * U1 + u) * V;
-                    const float z2 = lse[c] * kLog2e;
-                    pb = fast_ex2((pe[blank] + pd[blank]) * kLog2e - z2);
-                    if (y >= 0) pl = fast_ex2((pe[y] + pd[y]) * kLog2e - z2);
-                }
-                float cb = 0.f, cl = 0.f;
-                if (t < Tb - 1) cb = gc * pb * fast_ex2(e16m16_log2_ratio(aq, beta[c + U1], llq));
-                else if (u == Ub) cb = gc * pb * fast_ex2(e16m16_log2_ratio(aq, 0, llq));
-                if (y >= 0) cl = gc * pl * fast_ex2(e16m16_log2_ratio(aq, beta[c + 1], llq));
-                if (cb != 0.f) { atomicAdd(Oe + r * Vs + blank, -cb); atomicAdd(ub + uu, cb); }
-                if (cl != 0.f) { atomicAdd(Oe + r * Vs + y, -cl); atomicAdd(ul + uu, cl); }
-            }
-            Cs[r * kCs + uu] = cval;
-        }
-        __syncthreads();
-        // E += C B   (K = label positions of the chunk)
-        for (int uu = 0; uu < rows_u; ++uu) {
-            float bv[NC];
+        __syncthreads();  // ys visible to the staging warps
+        stage_rows_exp(Bs, mB, lBb, blank, pdec + ((size_t)b * U1 + u0) * V, kGUC2, rows_u, V, Vs, lBy, ys);
+
+        // per-cell scalars of the (32 x 48) block: C and the two corrections.  The global loads of
+        // kBatch cells are issued together before any of them is used.
+#pragma unroll 1
+        for (int q0 = 0; q0 < kCellsPerThread; q0 += kBatch) {
+            int aq[kBatch], bq[kBatch], bdn[kBatch], brt[kBatch];
+            float z2[kBatch], pey[kBatch];
 #pragma unroll
-            for (int c = 0; c < NC; ++c) bv[c] = Bs[uu * Vs + tx + 16 * c];
+            for (int q = 0; q < kBatch; ++q) {
+                const int i = tid + 128 * (q0 + q), r = i / kGUC2, uu = i - r * kGUC2;
+                const int t = t0 + r, u = u0 + uu;
+                aq[q] = bq[q] = bdn[q] = brt[q] = 0;
+                z2[q] = pey[q] = 0.f;
+                if (t < Tb && u <= Ub) {
+                    const size_t c = ((size_t)b * T + t) * U1 + u;
+                    aq[q] = alpha[c];
+                    bq[q] = beta[c];
+                    if (t < Tb - 1) bdn[q] = beta[c + U1];
+                    if (u < Ub) {
+                        brt[q] = beta[c + 1];
+                        pey[q] = __ldg(penc + ((size_t)b * T + t) * V + ys[uu]);
+                    }
+                    z2[q] = lse[c] * kLog2e;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < kBatch; ++q) {
+                const int i = tid + 128 * (q0 + q), r = i / kGUC2, uu = i - r * kGUC2;
+                const int t = t0 + r, u = u0 + uu;
+                float cval = 0.f, cb = 0.f, cl = 0.f;
+                if (t < Tb && u <= Ub) {
+                    const float mm = mA[r] + mB[uu];
+                    const float shift = mm - z2[q];  // -log2 S(t,u)
+                    if (shift > -kTinyLog2) atomicAdd(&n_exact, 1);  // C = 0: handled by the exact path
+                    else cval = gc * fast_ex2(e16m16_log2_ratio(aq[q], bq[q], llq) + shift);
+                    // log-domain p(blank), p(label): representable far below 2^-126
+                    const float lb2 = lAb[r] + lBb[uu] + shift;
+                    if (t < Tb - 1) cb = gc * fast_ex2(e16m16_log2_ratio(aq[q], bdn[q], llq) + lb2);
+                    else if (u == Ub) cb = gc * fast_ex2(e16m16_log2_ratio(aq[q], 0, llq) + lb2);
+                    if (u < Ub) {
+                        const float ll2 = pey[q] * kLog2e - mA[r] + lBy[uu] + shift;
+                        cl = gc * fast_ex2(e16m16_log2_ratio(aq[q], brt[q], llq) + ll2);
+                    }
+                }
+                Cs[r * kCs + uu] = cval;
+                CBs[r * kCs + uu] = cb;
+                CLs[r * kCs + uu] = cl;
+            }
+        }
+        __syncthreads();
+        // fixed-order row / column sums of the corrections
+        if (tid < kGT2) {
+            float sb = 0.f;
+            for (int uu = 0; uu < kGUC2; ++uu) sb += CBs[tid * kCs + uu];
+            rb[tid] += sb;
+        } else if (tid >= 64 && tid < 64 + kGUC2) {
+            const int uu = tid - 64;
+            float sb = 0.f, sl = 0.f;
+            for (int r = 0; r < kGT2; ++r) { sb += CBs[r * kCs + uu]; sl += CLs[r * kCs + uu]; }
+            ub[uu] = sb;
+            ul[uu] = sl;
+        }
+        // E += C B, EL += CL Y   (K = label positions of the chunk; Y[u][v] = [v == y_u])
+        for (int uu = 0; uu < rows_u; ++uu) {
+            float bv[NC], yv[NC];
+            const int y = ys[uu];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                bv[c] = Bs[uu * Vs + tx + 16 * c];
+                yv[c] = (tx + 16 * c == y) ? 1.f : 0.f;
+            }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const float cv = Cs[(4 * ty + i) * kCs + uu];
+                const float cv = Cs[(4 * ty + i) * kCs + uu], cl = CLs[(4 * ty + i) * kCs + uu];
 #pragma unroll
-                for (int c = 0; c < NC; ++c) E[i][c] = fmaf(cv, bv[c], E[i][c]);
+                for (int c = 0; c < NC; ++c) {
+                    E[i][c] = fmaf(cv, bv[c], E[i][c]);
+                    EL[i][c] = fmaf(cl, yv[c], EL[i][c]);
+                }
             }
         }
         // D = C^T A   (K = frames of the tile), then d_pdec partial = B .* D - corrections
@@ -260,6 +321,7 @@ cg_grad_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec
                 for (int c = 0; c < NC; ++c) D[i][c] = fmaf(cv, av[c], D[i][c]);
             }
         }
+        __syncthreads();  // ub / ul are complete
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
             const int uu = ty + 8 * i, u = u0 + uu;
@@ -286,14 +348,14 @@ cg_grad_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec
                 const int t = t0 + r, u = u0 + uu;
                 if (t >= Tb || u > Ub) continue;
                 const size_t c = ((size_t)b * T + t) * U1 + u;
-                const float z2 = lse[c] * kLog2e;
-                if (!(mA[r] + mB[uu] - z2 > -kTinyLog2)) continue;
-                const float occ = e16m16_log2_ratio(alpha[c], beta[c], llq) - z2;
+                const float zz = lse[c] * kLog2e;
+                if (!(mA[r] + mB[uu] - zz > -kTinyLog2)) continue;
+                const float occ = e16m16_log2_ratio(alpha[c], beta[c], llq) - zz;
                 const float* pe = penc + ((size_t)b * T + t) * V;
                 const float* pd = pdec + ((size_t)b * U1 + u) * V;
                 for (int v = 0; v < V; ++v) {
                     const float g = gc * fast_ex2((pe[v] + pd[v]) * kLog2e + occ);
-                    atomicAdd(Oe + r * Vs + v, g);
+                    atomicAdd(Xs + r * Vs + v, g);
                     if (slab) atomicAdd(slab + (size_t)u * V + v, g);
                     else atomicAdd(d_pdec + ((size_t)b * U1 + u) * V + v, g);
                 }
@@ -301,7 +363,7 @@ cg_grad_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec
         }
     }
     __syncthreads();
-    // d_penc = A .* E + corrections (blank / label columns, exact-path cells); padded rows are zero
+    // d_penc = A .* E - blank correction (+ exact-path cells); padded rows come out as zeros
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int r = 4 * ty + i;
@@ -309,7 +371,9 @@ cg_grad_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
             const int v = tx + 16 * c;
-            if (v < V) d_penc[((size_t)b * T + t0 + r) * V + v] = fmaf(As[r * Vs + v], E[i][c], Oe[r * Vs + v]);
+            if (v >= V) continue;
+            const float g = fmaf(As[r * Vs + v], E[i][c], -EL[i][c]);
+            d_penc[((size_t)b * T + t0 + r) * V + v] = g + Xs[r * Vs + v] - (v == blank ? rb[r] : 0.f);
         }
     }
 }
@@ -320,7 +384,7 @@ int launch_grad_mm(const float* penc, const float* pdec, const int32_t* labels, 
                    const int32_t* alpha, const int32_t* beta, const float* grad_costs, float* d_penc,
                    float* d_pdec, float* partial, cudaStream_t stream) {
     const int Vs = V | 1;
-    const size_t smem = ((size_t)(2 * kGT2 + kGUC2) * Vs + kGT2 * kCs + kGT2 + 3 * kGUC2) * sizeof(float);
+    const size_t smem = ((size_t)(2 * kGT2 + kGUC2) * Vs + 3 * kGT2 * kCs + 3 * kGT2 + 5 * kGUC2) * sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(cg_grad_mm_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return status_from_cuda(e);
     dim3 grid((T + kGT2 - 1) / kGT2, B);
@@ -338,7 +402,7 @@ int launch_cg_lse_mm(const float* penc, const float* pdec, const int32_t* labels
                      const int32_t* label_lens, int B, int T, int U1, int V, int blank, float2* lp2,
                      float* lse, cudaStream_t stream) {
     const int Vs = V | 1;
-    const size_t smem = ((size_t)(kFT + kFUC) * Vs + kFT + kFUC) * sizeof(float);
+    const size_t smem = ((size_t)(kFT + kFUC) * Vs + 2 * (kFT + kFUC)) * sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(cg_lse_mm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return status_from_cuda(e);
     dim3 grid((T + kFT - 1) / kFT, B);

@@ -95,14 +95,18 @@ __device__ __forceinline__ void cp_async_wait() {
 // The loop is software-pipelined: the (lp_blank, lp_label) pair of step s+1 is read from the ring
 // and split into (mantissa, exponent) form during step s, so the only work between receiving the
 // neighbour's value and handing the new value on is add -> normalise -> multiply.
+// There is no special-casing of the lattice borders inside the loop: the ring starts zeroed
+// (log-prob 0 = factor 1) and every absent term is the "zero" (1, kZeroExp), which loses every
+// addition, so a thread that has not reached its first cell yet just carries zeros along.
 template <int DIR, bool kMultiWarp>
 __device__ __forceinline__ void sweep(const float2* __restrict__ lp2, int Tb, int Ub, int T, int U1, int b,
                                       int32_t* __restrict__ out, float* __restrict__ costs,
-                                      float* __restrict__ ll_alpha, float2* ring, int2 (*edge)[32]) {
+                                      float* __restrict__ ll_alpha, float2* ring, int2 (*edge)[33]) {
     const int j = threadIdx.x;  // position along the sweep
     const int lane = j & 31, warp = j >> 5;
     const int U1b = Ub + 1;
     const bool lane_on = j < U1b;
+    const unsigned Tb_eff = lane_on ? Tb : 0;  // (unsigned)tau < Tb_eff  <=>  this thread has a cell
     const int u = DIR == 0 ? j : Ub - j;
     const int lag = kMultiWarp ? warp * kLag : 0;
     const int n_warps_on = (U1b + 31) >> 5;
@@ -110,29 +114,36 @@ __device__ __forceinline__ void sweep(const float2* __restrict__ lp2, int Tb, in
     const int S = (Tb + Ub + (kMultiWarp ? (n_warps_on - 1) * kLag : 0) + kUnroll - 1) / kUnroll * kUnroll;
 
     // this thread's cell at progress tau: row t = tau (alpha) or T_b-1-tau (beta)
-    const long long stride = DIR == 0 ? U1 : -U1;
+    const int stride = DIR == 0 ? U1 : -U1;
     const size_t first = (size_t)b * T * U1 + (size_t)(DIR == 0 ? 0 : Tb - 1) * U1 + u;
-    int tau = -lag - j;                                           // progress at step 0
-    const float2* pf = lp2 + first + (long long)tau * stride;      // cell of the step being prefetched
-    int32_t* dst = out + first + (long long)tau * stride;          // cell produced at the current step
-    float2* cur = ring + (size_t)j * kRingStride;                  // ring half of steps s0 .. s0+7
-    float2* oth = cur + kUnroll;                                   // ring half of the next 8 steps
-    const bool thread0 = j == 0;
-    const bool from_edge = kMultiWarp && lane == 0 && warp > 0;
+    int tau = -lag - j;                 // progress at step 0
+    int off = tau * stride;             // cell offset (elements) of the current step from `first`
+    const float2* src = lp2 + first;    // + off : cell consumed at the current step
+    const float2* src_pf = src + (long long)(kDepth - 1) * stride;  // + off : cell being prefetched
+    int32_t* dst = out + first;
+    float2* cur = ring + (size_t)j * kRingStride;  // ring half of steps s0 .. s0+7
+    float2* oth = cur + kUnroll;                   // ring half of the next 8 steps
+    const int edge_col = (kMultiWarp && warp > 0) ? warp - 1 : 32;  // column 32 always holds zero
+
+    // zero ring (factor 1 for steps without a cell), "zero" edge values
+#pragma unroll
+    for (int k = 0; k < kDepth; ++k) cur[k] = make_float2(0.f, 0.f);
+    if (kMultiWarp)
+        for (int i = j; i < kEdgeRing * 33; i += blockDim.x) edge[i / 33][i % 33] = make_int2(0x3f800000, kZeroExp);
 
     // prologue: cells of steps 0 .. kDepth-2 (slot of step s = s mod 16: cur[0..7], oth[0..6])
 #pragma unroll
     for (int k = 0; k < kDepth - 1; ++k) {
-        if (lane_on && (unsigned)(tau + k) < (unsigned)Tb) cp_async_8(k < kUnroll ? cur + k : oth + (k - kUnroll), pf);
+        if ((unsigned)(tau + k) < Tb_eff) cp_async_8(k < kUnroll ? cur + k : oth + (k - kUnroll), src + (off + k * stride));
         cp_async_commit();
-        pf += stride;
     }
-    int tau_pf = tau + kDepth - 1;
     int es = (-lag - 1) & (kEdgeRing - 1);  // edge slot of diagonal d-1
 
-    ME own{1.f, kZeroExp};    // alpha: alpha(t-1,u) * P_blank(t-1,u);   beta: beta(t+1,u)
-    ME share{1.f, kZeroExp};  // alpha: alpha(t,u)   * P_label(t,u);     beta: beta(t,u)
-    ME last{1.f, kZeroExp};   // value at the terminal cell (alpha(T-1,U) P_blank / beta(0,0))
+    // alpha: own = alpha(t-1,u) P_blank(t-1,u), share = alpha(t,u) P_label(t,u); the first cell gets
+    // alpha(0,0) = 1 as own.  beta: own = share = beta(t+1,u) / beta(t,u+1); the first cell gets 1 so
+    // that beta(T-1,U) = 1 * P_blank.
+    ME own{1.f, j == 0 ? 0 : kZeroExp};
+    ME share{1.f, kZeroExp};
 
     cp_async_wait<kDepth - 2>();
     ME pb = me_from_log(cur[0].x), pl = me_from_log(cur[0].y);  // factors of step 0
@@ -146,19 +157,16 @@ __device__ __forceinline__ void sweep(const float2* __restrict__ lp2, int Tb, in
             ME in;
             in.m = __shfl_up_sync(0xffffffffu, share.m, 1);
             in.e = __shfl_up_sync(0xffffffffu, share.e, 1);
-            const int2 ev = kMultiWarp ? edge[es][(warp + 31) & 31] : make_int2(0, 0);
+            const int2 ev = kMultiWarp ? edge[es][edge_col] : make_int2(0x3f800000, kZeroExp);
 
             // off the dependent chain: refill the ring, fetch and split the factors of step s+1
-            if (lane_on && (unsigned)tau_pf < (unsigned)Tb) cp_async_8(k == 0 ? oth + kUnroll - 1 : cur + k - 1, pf);
+            if ((unsigned)(tau + kDepth - 1) < Tb_eff) cp_async_8(k == 0 ? oth + kUnroll - 1 : cur + k - 1, src_pf + off);
             cp_async_commit();
             cp_async_wait<kDepth - 2>();
             const float2 lpn = k + 1 < kUnroll ? cur[k + 1] : oth[0];
             const ME pbn = me_from_log(lpn.x), pln = me_from_log(lpn.y);
 
-            if (lane == 0) in = from_edge ? ME{__int_as_float(ev.x), ev.y} : ME{1.f, kZeroExp};
-            const bool first_row = tau == 0;  // nothing arrives from t-1 (alpha) / t+1 (beta)
-            if (first_row) own = ME{1.f, (DIR == 1 && thread0) ? 0 : kZeroExp};
-            if (DIR == 0 && first_row && thread0) in = ME{1.f, 0};  // alpha(0,0) = 1
+            if (lane == 0) in = ME{__int_as_float(ev.x), ev.y};
             ME val;
             if (DIR == 0) {
                 val = me_normalize(me_add(own, in));
@@ -169,9 +177,16 @@ __device__ __forceinline__ void sweep(const float2* __restrict__ lp2, int Tb, in
                 own = val;
                 share = val;
             }
-            const bool on = lane_on && (unsigned)tau < (unsigned)Tb;
-            if (on) *dst = me_pack(val);
-            if (on && j == Ub && tau == Tb - 1) last = DIR == 0 ? own : val;
+            if ((unsigned)tau < Tb_eff) {
+                dst[off] = me_pack(val);
+                if (__builtin_expect(j == Ub && tau == Tb - 1, 0)) {  // terminal cell, once per sweep
+                    if (DIR == 0) {
+                        if (ll_alpha) ll_alpha[b] = (float)me_ln(me_normalize(own));  // alpha(T-1,U) P_blank
+                    } else {
+                        costs[b] = (float)(-me_ln(val));  // beta(0,0) = P(y|x)
+                    }
+                }
+            }
             if (kMultiWarp) {
                 es = (es + 1) & (kEdgeRing - 1);  // now the slot of diagonal d
                 if (lane == 31) edge[es][warp] = make_int2(__float_as_int(share.m), share.e);
@@ -179,22 +194,13 @@ __device__ __forceinline__ void sweep(const float2* __restrict__ lp2, int Tb, in
             pb = pbn;
             pl = pln;
             ++tau;
-            ++tau_pf;
-            pf += stride;
-            dst += stride;
+            off += stride;
         }
         float2* tmp = cur;
         cur = oth;
         oth = tmp;
     }
     cp_async_wait<0>();
-    if (lane_on && j == Ub) {
-        if (DIR == 0) {
-            if (ll_alpha) ll_alpha[b] = (float)me_ln(me_normalize(last));
-        } else {
-            costs[b] = (float)(-me_ln(last));
-        }
-    }
 }
 
 template <bool kMultiWarp>
@@ -205,7 +211,7 @@ lattice_sweep_kernel(const float2* __restrict__ lp2, const int32_t* __restrict__
                      float* __restrict__ costs, float* __restrict__ ll_alpha) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* ring = reinterpret_cast<float2*>(smem_raw);  // [blockDim.x][kRingStride]
-    __shared__ int2 edge[kEdgeRing][32];
+    __shared__ int2 edge[kEdgeRing][33];
     const int b = blockIdx.x;
     const int Tb = min(max(act_lens[b], 1), T);
     const int Ub = min(max(label_lens[b], 0), U1 - 1);

@@ -46,4 +46,6 @@ def test_argument_validation_needs_no_gpu(cuda_lib):
                                             None, None, None, None) == 2  # bad dtype
     assert cuda_lib.rnntb200_lattice_sweep(None, None, None, 1, 0, 3, None, None, None, None, None) == 2
     assert cuda_lib.rnntb200_joint_cg_bwd_workspace_bytes(2, 16, 5, 7, 0) == 0
-    assert cuda_lib.rnntb200_joint_cg_bwd_workspace_bytes(2, 16, 5, 7, 1) == 2 * 2 * 5 * 7 * 4
+    # deterministic mode: one [U1, V] slab per (utterance, 32-frame tile) for V <= 128, 8-frame tile above
+    assert cuda_lib.rnntb200_joint_cg_bwd_workspace_bytes(2, 16, 5, 7, 1) == 2 * 1 * 5 * 7 * 4
+    assert cuda_lib.rnntb200_joint_cg_bwd_workspace_bytes(2, 16, 5, 200, 1) == 2 * 2 * 5 * 200 * 4

@@ -80,7 +80,7 @@ def test_add_tanh_properties_cfg2_slice(cuda_lib):
         ref = t[k].grad.cpu().numpy()
         np.testing.assert_allclose(fused["d_" + k], ref, err_msg=k,
                                    atol=param_atol(ref) if k in ("weight", "bias") else 1e-4)
-    assert abs(float(fused["d_bias"].sum())) < 1e-4
+    assert abs(float(fused["d_bias"].sum())) < param_atol(fused["d_bias"])
     assert np.all(fused["d_enc"][1, 333:] == 0)
 
 

@@ -134,7 +134,7 @@ def test_full_size_cfg2_fused_vs_dense_path(cuda_lib):
         np.testing.assert_allclose(fused["d_" + k], ref, err_msg=k,
                                    atol=param_atol(ref) if k in ("weight", "bias") else GRAD_ATOL)
     # sum_v g = 0 per cell  =>  the bias gradient sums to zero
-    assert abs(float(fused["d_bias"].sum())) < 1e-4
+    assert abs(float(fused["d_bias"].sum())) < param_atol(fused["d_bias"])
     # frames past an utterance's length receive exactly zero gradient
     al = d["act_lens"].cpu().numpy()
     for b in range(c["B"]):
