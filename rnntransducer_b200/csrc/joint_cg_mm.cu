@@ -31,42 +31,48 @@ constexpr float kTinyLog2 = -66.f;  // log2 of the partition threshold below whi
 constexpr int kFT = 32;    // frames per CTA
 constexpr int kFUC = 64;   // label positions per staged chunk
 
-// Stage n_rows rows of src ([.., V] row-major, contiguous) as E = 2^(x log2e - rowmax): a bulk
-// coalesced copy with every load in flight at once, then (after a barrier) one warp per row takes
-// the row maximum and exponentiates in place.  Rows >= n_valid become zeros.  Optionally records
-// the normalised base-2 log at column `col` of every row (the blank column), which would underflow
-// if it were recovered from E.  Contains two block barriers.
+__device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gmem_src) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(gmem_src) : "memory");
+}
+
+// Stage n_rows rows of src ([.., V] row-major) as E = 2^((x - rowmax) log2e).  The raw rows go to
+// shared memory with cp.async (fire-and-forget: every load of the tile is in flight at once, no
+// register dependency), then one warp per row takes the row maximum and exponentiates in place.
+// Rows >= n_valid become zeros.  Optionally records the normalised base-2 log at column `col` of
+// every row (the blank column) and at a per-row column cols[r] (the row's label): those can
+// underflow in E although they are representable -- and may lie on the best path.
+// Contains two block barriers.
 __device__ __forceinline__ void stage_rows_exp(float* dst, float* rowmax, float* log_at_col, int col,
                                                const float* __restrict__ src, int n_rows, int n_valid,
                                                int V, int Vs, float* log_at_cols = nullptr,
                                                const int* cols = nullptr) {
-    const int n = n_valid * V;
-    for (int i = threadIdx.x; i < n_rows * V; i += blockDim.x) {
-        const int r = i / V, v = i - r * V;
-        dst[r * Vs + v] = i < n ? __ldg(src + i) * kLog2e : 0.f;
-    }
-    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-    for (int r = warp; r < n_rows; r += n_warps) {
-        float* d = dst + r * Vs;
-        if (r >= n_valid) {  // already zeros
-            if (lane == 0) {
-                rowmax[r] = 0.f;
-                if (log_at_col) log_at_col[r] = 0.f;
-                if (log_at_cols) log_at_cols[r] = 0.f;
-            }
-            continue;
+    for (int r = warp; r < n_valid; r += n_warps)
+        for (int v = lane; v < V; v += 32) cp_async_4(dst + r * Vs + v, src + (size_t)r * V + v);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    for (int r = n_valid + warp; r < n_rows; r += n_warps) {
+        for (int v = lane; v < V; v += 32) dst[r * Vs + v] = 0.f;
+        if (lane == 0) {
+            rowmax[r] = 0.f;
+            if (log_at_col) log_at_col[r] = 0.f;
+            if (log_at_cols) log_at_cols[r] = 0.f;
         }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    for (int r = warp; r < n_valid; r += n_warps) {
+        float* d = dst + r * Vs;
         float m = -INFINITY;
         for (int v = lane; v < V; v += 32) m = fmaxf(m, d[v]);
         m = warp_max(m);
         if (lane == 0) {
-            rowmax[r] = m;
-            if (log_at_col) log_at_col[r] = d[col] - m;
-            if (log_at_cols) log_at_cols[r] = cols[r] >= 0 ? d[cols[r]] - m : 0.f;  // per-row column
+            rowmax[r] = m * kLog2e;
+            if (log_at_col) log_at_col[r] = (d[col] - m) * kLog2e;
+            if (log_at_cols) log_at_cols[r] = cols[r] >= 0 ? (d[cols[r]] - m) * kLog2e : 0.f;
         }
         __syncwarp();
-        for (int v = lane; v < V; v += 32) d[v] = fast_ex2(d[v] - m);
+        for (int v = lane; v < V; v += 32) d[v] = fast_ex2((d[v] - m) * kLog2e);
     }
     __syncthreads();
 }
@@ -83,6 +89,8 @@ cg_lse_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec,
     float* mB = mA + kFT;           // [kFUC]
     float* lAb = mB + kFUC;         // [kFT]   log2 A[t][blank]
     float* lBb = lAb + kFT;         // [kFUC]  log2 B[u][blank]
+    float* lBy = lBb + kFUC;        // [kFUC]  log2 B[u][y_u]
+    __shared__ int ys[kFUC];
     const int b = blockIdx.y, t0 = blockIdx.x * kFT;
     const int Tb = min(__ldg(act_lens + b), T), Ub = min(__ldg(label_lens + b), U1 - 1);
     if (t0 >= Tb) return;
@@ -92,7 +100,13 @@ cg_lse_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec,
     stage_rows_exp(As, mA, lAb, blank, penc + ((size_t)b * T + t0) * V, kFT, min(kFT, Tb - t0), V, Vs);
     for (int u0 = 0; u0 <= Ub; u0 += kFUC) {
         if (u0 > 0) __syncthreads();  // every warp is done with the previous chunk
-        stage_rows_exp(Bs, mB, lBb, blank, pdec + ((size_t)b * U1 + u0) * V, kFUC, min(kFUC, Ub + 1 - u0), V, Vs);
+        if (threadIdx.x < kFUC) {
+            const int u = u0 + threadIdx.x;
+            ys[threadIdx.x] = u < Ub ? __ldg(labels + (size_t)b * (U1 - 1) + u) : -1;
+        }
+        __syncthreads();
+        stage_rows_exp(Bs, mB, lBb, blank, pdec + ((size_t)b * U1 + u0) * V, kFUC, min(kFUC, Ub + 1 - u0), V, Vs,
+                       lBy, ys);
         for (int item = warp; item < (kFT / 16) * (kFUC / 16); item += 4) {
             const int rt = (item / (kFUC / 16)) * 16 + 4 * ty;  // first of this thread's 4 frames
             const int ru = (item % (kFUC / 16)) * 16 + 2 * tx;  // first of its 2 label positions
@@ -122,7 +136,7 @@ cg_lse_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec,
                     const float* pe = penc + ((size_t)b * T + t) * V;
                     const float* pd = pdec + ((size_t)b * U1 + u) * V;
                     float lgs = fast_lg2(s[i][k]);
-                    const int y = u < Ub ? __ldg(labels + (size_t)b * (U1 - 1) + u) : blank;
+                    const int y = u < Ub ? ys[ru + k] : blank;
                     float lb2, ll2;
                     if (lgs < kTinyLog2) {
                         // exact path: the row peaks do not line up, redo this cell in the log domain
@@ -135,7 +149,9 @@ cg_lse_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec,
                     // blank / label log-probs straight in the log domain (A * B would underflow
                     // below 2^-126 although such steps are representable -- and may be on the path)
                     lb2 = lAb[rt + i] + lBb[ru + k] - lgs;
-                    ll2 = (__ldg(pe + y) + __ldg(pd + y)) * kLog2e - mm - lgs;
+                    const float ay = a[i * Vs + y];  // A[t][y]: its log unless it underflowed
+                    const float lay = ay > 1e-30f ? fast_lg2(ay) : __ldg(pe + y) * kLog2e - mA[rt + i];
+                    ll2 = lay + lBy[ru + k] - lgs;
                     const size_t c = ((size_t)b * T + t) * U1 + u;
                     lp2[c] = make_float2(fmaxf(lb2 * kLn2, kNegInf), u < Ub ? fmaxf(ll2 * kLn2, kNegInf) : 0.f);
                     lse_out[c] = (mm + lgs) * kLn2;
@@ -243,7 +259,9 @@ cg_grad_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec
                     if (t < Tb - 1) bdn[q] = beta[c + U1];
                     if (u < Ub) {
                         brt[q] = beta[c + 1];
-                        pey[q] = __ldg(penc + ((size_t)b * T + t) * V + ys[uu]);
+                        const float ay = As[r * Vs + ys[uu]];  // log2 A[t][y_u]; gather if it underflowed
+                        pey[q] = ay > 1e-30f ? fast_lg2(ay)
+                                             : __ldg(penc + ((size_t)b * T + t) * V + ys[uu]) * kLog2e - mA[r];
                     }
                     z2[q] = lse[c] * kLog2e;
                 }
@@ -263,7 +281,7 @@ cg_grad_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec
                     if (t < Tb - 1) cb = gc * fast_ex2(e16m16_log2_ratio(aq[q], bdn[q], llq) + lb2);
                     else if (u == Ub) cb = gc * fast_ex2(e16m16_log2_ratio(aq[q], 0, llq) + lb2);
                     if (u < Ub) {
-                        const float ll2 = pey[q] * kLog2e - mA[r] + lBy[uu] + shift;
+                        const float ll2 = pey[q] + lBy[uu] + shift;
                         cl = gc * fast_ex2(e16m16_log2_ratio(aq[q], brt[q], llq) + ll2);
                     }
                 }
@@ -402,7 +420,7 @@ int launch_cg_lse_mm(const float* penc, const float* pdec, const int32_t* labels
                      const int32_t* label_lens, int B, int T, int U1, int V, int blank, float2* lp2,
                      float* lse, cudaStream_t stream) {
     const int Vs = V | 1;
-    const size_t smem = ((size_t)(kFT + kFUC) * Vs + 2 * (kFT + kFUC)) * sizeof(float);
+    const size_t smem = ((size_t)(kFT + kFUC) * Vs + 2 * kFT + 3 * kFUC) * sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(cg_lse_mm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return status_from_cuda(e);
     dim3 grid((T + kFT - 1) / kFT, B);

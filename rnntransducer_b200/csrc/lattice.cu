@@ -144,6 +144,8 @@ __device__ __forceinline__ void sweep(const float2* __restrict__ lp2, int Tb, in
     // that beta(T-1,U) = 1 * P_blank.
     ME own{1.f, j == 0 ? 0 : kZeroExp};
     ME share{1.f, kZeroExp};
+    ME last{1.f, kZeroExp};                               // alpha(T-1,U) P_blank(T-1,U) / beta(0,0)
+    const int t_last = (lane_on && j == Ub) ? Tb - 1 : -1;  // progress at which this thread is there
 
     cp_async_wait<kDepth - 2>();
     ME pb = me_from_log(cur[0].x), pl = me_from_log(cur[0].y);  // factors of step 0
@@ -177,16 +179,9 @@ __device__ __forceinline__ void sweep(const float2* __restrict__ lp2, int Tb, in
                 own = val;
                 share = val;
             }
-            if ((unsigned)tau < Tb_eff) {
-                dst[off] = me_pack(val);
-                if (__builtin_expect(j == Ub && tau == Tb - 1, 0)) {  // terminal cell, once per sweep
-                    if (DIR == 0) {
-                        if (ll_alpha) ll_alpha[b] = (float)me_ln(me_normalize(own));  // alpha(T-1,U) P_blank
-                    } else {
-                        costs[b] = (float)(-me_ln(val));  // beta(0,0) = P(y|x)
-                    }
-                }
-            }
+            const int packed = me_pack(val);
+            if ((unsigned)tau < Tb_eff) dst[off] = packed;
+            if (tau == t_last) last = DIR == 0 ? own : val;  // terminal cell (t_last = -1 elsewhere)
             if (kMultiWarp) {
                 es = (es + 1) & (kEdgeRing - 1);  // now the slot of diagonal d
                 if (lane == 31) edge[es][warp] = make_int2(__float_as_int(share.m), share.e);
@@ -201,6 +196,13 @@ __device__ __forceinline__ void sweep(const float2* __restrict__ lp2, int Tb, in
         oth = tmp;
     }
     cp_async_wait<0>();
+    if (t_last >= 0) {
+        if (DIR == 0) {
+            if (ll_alpha) ll_alpha[b] = (float)me_ln(me_normalize(last));
+        } else {
+            costs[b] = (float)(-me_ln(last));
+        }
+    }
 }
 
 template <bool kMultiWarp>
