@@ -23,6 +23,12 @@ int launch_at_lse_tc(const float* enc, const float* dec, const float* weight, co
                      size_t workspace_bytes, cudaStream_t stream);  // joint_at_tc.cu
 bool at_tc_supported(int V, int H);
 size_t at_tc_workspace_bytes(int V, int H);
+bool at_tc_bwd_supported(int V, int H);  // joint_at_tc_bwd.cu
+int launch_at_grad_tc(const float* enc, const float* dec, const float* weight, const float* bias,
+                      const int32_t* labels, const int32_t* act_lens, const int32_t* label_lens, int B, int T,
+                      int U1, int V, int H, int blank, const float2* lp2, const float* lse, const int32_t* alpha,
+                      const int32_t* beta, const float* grad_costs, float* d_enc, float* d_dec, float* d_weight,
+                      float* d_bias, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
 namespace {
 
@@ -362,10 +368,9 @@ int launch_at_grad(const float* enc, const float* dec, const float* weight, cons
                    const int32_t* alpha, const int32_t* beta, const float* grad_costs, float* d_enc,
                    float* d_dec, float* d_weight, float* d_bias, void* workspace, size_t workspace_bytes,
                    cudaStream_t stream) {
-    (void)workspace;
-    (void)workspace_bytes;
     if (gemm == RNNTB200_GEMM_TF32X3) return RNNTB200_STATUS_INVALID_VALUE;  // reserved
-    if (H > 512) return RNNTB200_STATUS_INVALID_VALUE;  // dz register tile (see kernel)
+    const bool tc = gemm == RNNTB200_GEMM_BF16 && at_tc_bwd_supported(V, H);
+    if (!tc && H > 512) return RNNTB200_STATUS_INVALID_VALUE;  // dz register tile (see kernel)
     // all four outputs are accumulated with fp32 atomics: clear them first (also the B == 0 case)
     if (cudaMemsetAsync(d_enc, 0, (size_t)B * T * H * sizeof(float), stream) != cudaSuccess ||
         cudaMemsetAsync(d_dec, 0, (size_t)B * U1 * H * sizeof(float), stream) != cudaSuccess ||
@@ -373,6 +378,10 @@ int launch_at_grad(const float* enc, const float* dec, const float* weight, cons
         cudaMemsetAsync(d_bias, 0, (size_t)V * sizeof(float), stream) != cudaSuccess)
         return RNNTB200_STATUS_MEMOPS_FAILED;
     if ((long long)B * T * U1 == 0) return RNNTB200_STATUS_SUCCESS;
+    if (tc)
+        return launch_at_grad_tc(enc, dec, weight, bias, labels, act_lens, label_lens, B, T, U1, V, H, blank, lp2,
+                                 lse, alpha, beta, grad_costs, d_enc, d_dec, d_weight, d_bias, workspace,
+                                 workspace_bytes, stream);
     const int Hs = (H + kKT - 1) / kKT * kKT + 1;
     const size_t smem = ((size_t)32 * Hs + kNT * kWs + 32 * (kNT + 1)) * sizeof(float);
     dim3 grid((U1 + 7) / 8, (T + 3) / 4, B);

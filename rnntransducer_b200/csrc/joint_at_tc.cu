@@ -21,13 +21,13 @@
 // Synchronisation is mbarrier-only (full/empty pairs per A slot, W stage and accumulator stage).
 // Supported shapes: H a multiple of 64, H <= 512; any V (chunks of <= 128 columns, so V = 1024 is
 // 8 chunks with the A tile resident in shared memory and computed once).
-#include <cuda.h>
-
 #include <algorithm>
 
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace rnntb200 {
+
+using namespace tc;
 
 namespace {
 
@@ -58,97 +58,6 @@ __host__ __device__ inline Smem smem_layout(int H, int NB) {
     s.bars = (s.bars + 15) & ~15;
     s.total = s.bars + 32 * 8 + 16;
     return s;
-}
-
-// ---- PTX wrappers -----------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-// Waits for the phase with the given parity.  A protocol bug would otherwise hang the GPU, so
-// the wait is bounded (~2 s of SM clocks) and traps instead: the launch then fails loudly.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done = 0;
-    long long start = 0;
-    for (uint32_t spins = 0;; ++spins) {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t"
-            "}\n"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (done) return;
-        if ((spins & 1023) == 1023) {
-            const long long now = clock64();
-            if (start == 0) start = now;
-            else if (now - start > 4000000000LL) __trap();
-        }
-    }
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2,
-                                            uint32_t bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::
-            "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-// K-major, no-swizzle shared-memory matrix descriptor: core matrix = 8 rows x 16 bytes (128
-// contiguous bytes); SBO = byte distance between 8-row groups, LBO = between 16-byte K chunks.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
-           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
-}
-
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-__device__ __forceinline__ float tanh_fast(float x) {
-    float y;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-    return *reinterpret_cast<uint32_t*>(&v);
 }
 
 __global__ void convert_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
@@ -276,7 +185,7 @@ at_lse_tc_kernel(const __grid_constant__ CUtensorMap w_map, const float* __restr
         // ===== MMA issuer =====
         if (lane == 0) {
             // kind::f16, A/B = bf16 K-major, D = fp32, M = 128, N = NB
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NB >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t idesc = umma_idesc_bf16(NB, false, false);
             const uint32_t b_lbo = NB * 16;
             uint32_t n = 0, wi = 0, ci = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -397,32 +306,38 @@ bool at_tc_supported(int V, int H) { return V >= 1 && H >= kKB && H % kKB == 0 &
 
 size_t at_tc_workspace_bytes(int V, int H) { return ((size_t)V * H * sizeof(__nv_bfloat16) + 255) & ~(size_t)255; }
 
+// bf16 copy of W into the workspace + the TMA descriptor of its 3-D view [H/8][V][8]: a box
+// {8, NB, 8} lands in shared memory as [8-element column group][row][8 elements], i.e. UMMA core
+// matrices that can be read K-major (K = H) or MN-major (K = V).
+int at_tc_prepare_weight(const float* weight, int V, int H, int NB, void* workspace, size_t workspace_bytes,
+                         CUtensorMap* map, cudaStream_t stream) {
+    if (!workspace || workspace_bytes < at_tc_workspace_bytes(V, H) || ((uintptr_t)workspace & 15))
+        return RNNTB200_STATUS_INVALID_VALUE;
+    EncodeTiledFn encode = encode_tiled_fn();
+    if (!encode) return RNNTB200_STATUS_EXECUTION_FAILED;
+    __nv_bfloat16* wb = static_cast<__nv_bfloat16*>(workspace);
+    const size_t nw = (size_t)V * H;
+    convert_bf16_kernel<<<(unsigned)std::min<size_t>((nw + 255) / 256, 1184), 256, 0, stream>>>(weight, wb, nw);
+    const cuuint64_t gdim[3] = {8, (cuuint64_t)V, (cuuint64_t)(H / 8)};
+    const cuuint64_t gstride[2] = {(cuuint64_t)H * 2, 16};
+    const cuuint32_t box[3] = {8, (cuuint32_t)NB, (cuuint32_t)(kKB / 8)};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    if (encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, wb, gdim, gstride, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return RNNTB200_STATUS_INVALID_VALUE;
+    return launch_status();
+}
+
 int launch_at_lse_tc(const float* enc, const float* dec, const float* weight, const float* bias,
                      const int32_t* labels, const int32_t* act_lens, const int32_t* label_lens, int B,
                      int T, int U1, int V, int H, int blank, float2* lp2, float* lse, void* workspace,
                      size_t workspace_bytes, cudaStream_t stream) {
     if (!at_tc_supported(V, H)) return RNNTB200_STATUS_INVALID_VALUE;
-    if (!workspace || workspace_bytes < at_tc_workspace_bytes(V, H) || ((uintptr_t)workspace & 15))
-        return RNNTB200_STATUS_INVALID_VALUE;
-    EncodeTiledFn encode = encode_tiled_fn();
-    if (!encode) return RNNTB200_STATUS_EXECUTION_FAILED;
-
-    __nv_bfloat16* wb = static_cast<__nv_bfloat16*>(workspace);
-    const size_t nw = (size_t)V * H;
-    convert_bf16_kernel<<<(unsigned)std::min<size_t>((nw + 255) / 256, 1184), 256, 0, stream>>>(weight, wb, nw);
-
-    // 3-D view of W[V][H] as [H/8][V][8]: a box {8, NB, 8} lands in shared memory as
-    // [k-chunk][row][8 elements] = UMMA K-major core matrices (SBO = 128 B, LBO = NB * 16 B)
     const int NB = chunk_cols(V);
     CUtensorMap map;
-    const cuuint64_t gdim[3] = {8, (cuuint64_t)V, (cuuint64_t)(H / 8)};
-    const cuuint64_t gstride[2] = {(cuuint64_t)H * 2, 16};
-    const cuuint32_t box[3] = {8, (cuuint32_t)NB, (cuuint32_t)(kKB / 8)};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    if (encode(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, wb, gdim, gstride, box, estr,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-        return RNNTB200_STATUS_INVALID_VALUE;
+    int st = at_tc_prepare_weight(weight, V, H, NB, workspace, workspace_bytes, &map, stream);
+    if (st != RNNTB200_STATUS_SUCCESS) return st;
 
     const Smem L = smem_layout(H, NB);
     cudaError_t e = cudaFuncSetAttribute(at_lse_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
