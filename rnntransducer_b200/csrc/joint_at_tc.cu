@@ -36,15 +36,15 @@ constexpr int kKB = 64;                // K elements per A slot / W stage
 constexpr int kProducerThreads = 256;  // warps 0-7
 constexpr int kTmaWarp = 8, kMmaWarp = 9;  // warps 10-13: epilogue
 constexpr int kThreads = 14 * 32;
-constexpr int kWStages = 2;
+constexpr int kMaxWStages = 8;  // W K-blocks in flight (TMA latency ~1 us: a 2-deep ring starves the MMA)
 constexpr int kAccStride = 128;        // TMEM columns per accumulator stage
 constexpr int kTmemCols = 256;
 constexpr int kASlotBytes = 128 * kKB * 2;  // 16 KiB
 constexpr int kMaxSlots = 8;                // H <= 512
 
 struct Smem {  // offsets into dynamic shared memory
-    int a, w, ed, bars, total;
-    int w_stage_bytes, ed_stride;
+    int a, w, dd, bars, total;
+    int w_stage_bytes, dd_stride, w_stages;
 };
 
 __host__ __device__ inline Smem smem_layout(int H, int NB) {
@@ -52,11 +52,13 @@ __host__ __device__ inline Smem smem_layout(int H, int NB) {
     s.a = 0;
     s.w = (H / kKB) * kASlotBytes;
     s.w_stage_bytes = NB * kKB * 2;
-    s.ed = s.w + kWStages * s.w_stage_bytes;
-    s.ed_stride = H + 8;  // floats; +8 keeps rows on different banks
-    s.bars = s.ed + (kTT + kUU) * s.ed_stride * 4;
-    s.bars = (s.bars + 15) & ~15;
-    s.total = s.bars + 32 * 8 + 16;
+    s.dd_stride = H + 8;  // floats; +8 keeps the 8 predictor rows on different banks
+    const int fixed = s.w + kUU * s.dd_stride * 4 + 40 * 8 + 32;
+    s.w_stages = (227 * 1024 - fixed) / s.w_stage_bytes;
+    s.w_stages = s.w_stages > kMaxWStages ? kMaxWStages : s.w_stages;
+    s.dd = s.w + s.w_stages * s.w_stage_bytes;
+    s.bars = (s.dd + kUU * s.dd_stride * 4 + 15) & ~15;
+    s.total = s.bars + 40 * 8 + 16;
     return s;
 }
 
@@ -80,19 +82,20 @@ at_lse_tc_kernel(const __grid_constant__ CUtensorMap w_map, const float* __restr
 
     const uint32_t sbase = smem_u32(smem);
     const uint32_t a_base = sbase + L.a, w_base = sbase + L.w;
-    float* ed = reinterpret_cast<float*>(smem + L.ed);  // [16 enc rows | 8 dec rows][ed_stride]
+    float* dd = reinterpret_cast<float*>(smem + L.dd);  // [8 predictor rows][dd_stride]
+    const int kWStages = L.w_stages;
     const uint32_t bars = sbase + L.bars;
     auto a_full = [&](int i) { return bars + 8 * i; };
     auto a_empty = [&](int i) { return bars + 8 * (8 + i); };
     auto w_full = [&](int i) { return bars + 8 * (16 + i); };
-    auto w_empty = [&](int i) { return bars + 8 * (18 + i); };
-    auto acc_full = [&](int i) { return bars + 8 * (20 + i); };
-    auto acc_empty = [&](int i) { return bars + 8 * (22 + i); };
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.bars + 32 * 8);
+    auto w_empty = [&](int i) { return bars + 8 * (24 + i); };
+    auto acc_full = [&](int i) { return bars + 8 * (32 + i); };
+    auto acc_empty = [&](int i) { return bars + 8 * (34 + i); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.bars + 40 * 8);
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kMaxSlots; ++i) { mbar_init(a_full(i), 8); mbar_init(a_empty(i), 1); }
-        for (int i = 0; i < kWStages; ++i) { mbar_init(w_full(i), 1); mbar_init(w_empty(i), 1); }
+        for (int i = 0; i < kMaxWStages; ++i) { mbar_init(w_full(i), 1); mbar_init(w_empty(i), 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), 4); }
         fence_barrier_init();
     }
@@ -128,27 +131,39 @@ at_lse_tc_kernel(const __grid_constant__ CUtensorMap w_map, const float* __restr
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             int b, t0, u0;
             if (!decode(tile, b, t0, u0)) continue;
-            // stage the tile's 16 encoder rows and 8 predictor rows (fp32)
+            // stage the tile's 8 predictor rows (each is reused by all 16 frames); the encoder rows
+            // are read straight from global memory: every element is needed by exactly one warp
             asm volatile("bar.sync 1, 256;" ::: "memory");  // previous tile's readers are done
             const int H4 = H / 4;
-            for (int i = p; i < (kTT + kUU) * H4; i += kProducerThreads) {
+            for (int i = p; i < kUU * H4; i += kProducerThreads) {
                 const int row = i / H4, c4 = i - row * H4;
-                const float* src = row < kTT ? enc + ((size_t)b * T + min(t0 + row, T - 1)) * H
-                                             : dec + ((size_t)b * U1 + min(u0 + row - kTT, U1 - 1)) * H;
-                *reinterpret_cast<float4*>(ed + row * L.ed_stride + 4 * c4) =
+                const float* src = dec + ((size_t)b * U1 + min(u0 + row, U1 - 1)) * H;
+                *reinterpret_cast<float4*>(dd + row * L.dd_stride + 4 * c4) =
                     __ldg(reinterpret_cast<const float4*>(src) + c4);
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");
-            const float* erow = ed + tt * L.ed_stride;
-            const float* drow = ed + (kTT + uu) * L.ed_stride;
+            const float4* erow = reinterpret_cast<const float4*>(enc + ((size_t)b * T + min(t0 + tt, T - 1)) * H);
+            const float* drow = dd + uu * L.dd_stride;
+            float4 ecur[8], enxt[8];  // this thread's 4 x 8 encoder values of a K block, double-buffered
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                ecur[2 * i] = __ldg(erow + (kc0 + 2 * i) * 2);
+                ecur[2 * i + 1] = __ldg(erow + (kc0 + 2 * i) * 2 + 1);
+            }
             for (int kb = 0; kb < n_slots; ++kb) {
+                if (kb + 1 < n_slots) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        enxt[2 * i] = __ldg(erow + ((kb + 1) * kKB / 4) + (kc0 + 2 * i) * 2);
+                        enxt[2 * i + 1] = __ldg(erow + ((kb + 1) * kKB / 4) + (kc0 + 2 * i) * 2 + 1);
+                    }
+                }
                 mbar_wait(a_empty(kb), (n & 1) ^ 1);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int kc = kc0 + 2 * i;
                     const int k = kb * kKB + kc * 8;
-                    const float4 e0 = *reinterpret_cast<const float4*>(erow + k);
-                    const float4 e1 = *reinterpret_cast<const float4*>(erow + k + 4);
+                    const float4 e0 = ecur[2 * i], e1 = ecur[2 * i + 1];
                     const float4 d0 = *reinterpret_cast<const float4*>(drow + k);
                     const float4 d1 = *reinterpret_cast<const float4*>(drow + k + 4);
                     uint4 out;
@@ -159,6 +174,8 @@ at_lse_tc_kernel(const __grid_constant__ CUtensorMap w_map, const float* __restr
                     // core-matrix layout: K chunk kc at kc * 2048, cell row r at r * 16
                     *reinterpret_cast<uint4*>(smem + L.a + kb * kASlotBytes + kc * 2048 + r * 16) = out;
                 }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) ecur[i] = enxt[i];
                 fence_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
                 __syncwarp();
                 if (lane == 0) mbar_arrive(a_full(kb));

@@ -38,7 +38,7 @@ constexpr int kKB = 64;
 constexpr int kProducerThreads = 256;
 constexpr int kTmaWarp = 8, kMmaWarp = 9;
 constexpr int kThreads = 14 * 32;
-constexpr int kWStages = 2;
+constexpr int kMaxWStages = 8;
 constexpr int kASlotBytes = 128 * kKB * 2;  // one 64-wide K block of z: 16 KiB
 constexpr int kGroupBytes = 2048;           // 128 rows x 16 B: one 8-element column group of z / G
 constexpr int kRBytes = 16 * 512;           // selector matrix R: [32 rows][128 cells] bf16, K-major
@@ -46,8 +46,8 @@ constexpr int kColDW = 0, kColS = 320, kColDZ = 400, kColRed = 320, kColDB = 464
 constexpr int kTmemCols = 512;
 
 struct SmemB {
-    int z, g, w, r, ed, bars, total;
-    int w_stage_bytes, ed_stride;
+    int z, g, w, r, dd, bars, total;
+    int w_stage_bytes, dd_stride, w_stages;
 };
 
 __host__ __device__ inline SmemB smem_layout_b(int H, int NB) {
@@ -56,11 +56,14 @@ __host__ __device__ inline SmemB smem_layout_b(int H, int NB) {
     s.g = (H / kKB) * kASlotBytes;
     s.w = s.g + (NB / 8) * kGroupBytes;  // W stages directly after G (see the db product)
     s.w_stage_bytes = NB * kKB * 2;
-    s.r = s.w + kWStages * s.w_stage_bytes;
-    s.ed = s.r + kRBytes;
-    s.ed_stride = H + 8;
-    s.bars = (s.ed + (kTT + kUU) * s.ed_stride * 4 + 15) & ~15;
-    s.total = s.bars + 32 * 8 + 16;
+    s.dd_stride = H + 8;
+    const int fixed = s.w + kRBytes + kUU * s.dd_stride * 4 + 40 * 8 + 32;
+    s.w_stages = (227 * 1024 - fixed) / s.w_stage_bytes;
+    s.w_stages = s.w_stages > kMaxWStages ? kMaxWStages : s.w_stages;
+    s.r = s.w + s.w_stages * s.w_stage_bytes;
+    s.dd = s.r + kRBytes;
+    s.bars = (s.dd + kUU * s.dd_stride * 4 + 15) & ~15;
+    s.total = s.bars + 40 * 8 + 16;
     return s;
 }
 
@@ -93,21 +96,22 @@ at_grad_tc_kernel(const __grid_constant__ CUtensorMap w_map, const float* __rest
 
     const uint32_t sbase = smem_u32(smem);
     const uint32_t z_base = sbase + L.z, g_base = sbase + L.g, w_base = sbase + L.w, r_base = sbase + L.r;
-    float* ed = reinterpret_cast<float*>(smem + L.ed);
+    float* dd = reinterpret_cast<float*>(smem + L.dd);  // [8 predictor rows][dd_stride]
+    const int kWStages = L.w_stages;
     const uint32_t bars = sbase + L.bars;
     auto z_full = [&](int i) { return bars + 8 * i; };
     const uint32_t z_empty = bars + 8 * 8;
     auto w_full = [&](int i) { return bars + 8 * (9 + i); };
-    auto w_empty = [&](int i) { return bars + 8 * (11 + i); };
-    const uint32_t s_full = bars + 8 * 13, g_full = bars + 8 * 14, dz_full = bars + 8 * 15,
-                   dz_empty = bars + 8 * 16, p_full = bars + 8 * 17, r_full = bars + 8 * 18,
-                   r_empty = bars + 8 * 19, done = bars + 8 * 20;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.bars + 32 * 8);
+    auto w_empty = [&](int i) { return bars + 8 * (17 + i); };
+    const uint32_t s_full = bars + 8 * 25, g_full = bars + 8 * 26, dz_full = bars + 8 * 27,
+                   dz_empty = bars + 8 * 28, p_full = bars + 8 * 29, r_full = bars + 8 * 30,
+                   r_empty = bars + 8 * 31, done = bars + 8 * 32;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.bars + 40 * 8);
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 8; ++i) mbar_init(z_full(i), 8);
         mbar_init(z_empty, 1);
-        for (int i = 0; i < kWStages; ++i) { mbar_init(w_full(i), 1); mbar_init(w_empty(i), 1); }
+        for (int i = 0; i < kMaxWStages; ++i) { mbar_init(w_full(i), 1); mbar_init(w_empty(i), 1); }
         mbar_init(s_full, 1);
         mbar_init(g_full, 4);
         mbar_init(dz_full, 1);
@@ -158,25 +162,39 @@ at_grad_tc_kernel(const __grid_constant__ CUtensorMap w_map, const float* __rest
             int b, t0, u0;
             if (!decode(tile, b, t0, u0)) continue;
             mbar_wait(z_empty, (n & 1) ^ 1);  // every reader of the previous tile's z / dP is done
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            // stage the tile's 8 predictor rows (each is reused by all 16 frames); the encoder rows
+            // are read straight from global memory: every element is needed by exactly one warp
+            asm volatile("bar.sync 1, 256;" ::: "memory");  // previous tile's readers are done
             const int H4 = H / 4;
-            for (int i = p; i < (kTT + kUU) * H4; i += kProducerThreads) {
+            for (int i = p; i < kUU * H4; i += kProducerThreads) {
                 const int row = i / H4, c4 = i - row * H4;
-                const float* src = row < kTT ? enc + ((size_t)b * T + min(t0 + row, T - 1)) * H
-                                             : dec + ((size_t)b * U1 + min(u0 + row - kTT, U1 - 1)) * H;
-                *reinterpret_cast<float4*>(ed + row * L.ed_stride + 4 * c4) =
+                const float* src = dec + ((size_t)b * U1 + min(u0 + row, U1 - 1)) * H;
+                *reinterpret_cast<float4*>(dd + row * L.dd_stride + 4 * c4) =
                     __ldg(reinterpret_cast<const float4*>(src) + c4);
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");
-            const float* erow = ed + tt * L.ed_stride;
-            const float* drow = ed + (kTT + uu) * L.ed_stride;
+            const float4* erow = reinterpret_cast<const float4*>(enc + ((size_t)b * T + min(t0 + tt, T - 1)) * H);
+            const float* drow = dd + uu * L.dd_stride;
+            float4 ecur[8], enxt[8];  // this thread's 4 x 8 encoder values of a K block, double-buffered
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                ecur[2 * i] = __ldg(erow + (kc0 + 2 * i) * 2);
+                ecur[2 * i + 1] = __ldg(erow + (kc0 + 2 * i) * 2 + 1);
+            }
             for (int kb = 0; kb < n_slots; ++kb) {
+                if (kb + 1 < n_slots) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        enxt[2 * i] = __ldg(erow + ((kb + 1) * kKB / 4) + (kc0 + 2 * i) * 2);
+                        enxt[2 * i + 1] = __ldg(erow + ((kb + 1) * kKB / 4) + (kc0 + 2 * i) * 2 + 1);
+                    }
+                }
+                
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int kc = kc0 + 2 * i;
                     const int k = kb * kKB + kc * 8;
-                    const float4 e0 = *reinterpret_cast<const float4*>(erow + k);
-                    const float4 e1 = *reinterpret_cast<const float4*>(erow + k + 4);
+                    const float4 e0 = ecur[2 * i], e1 = ecur[2 * i + 1];
                     const float4 d0 = *reinterpret_cast<const float4*>(drow + k);
                     const float4 d1 = *reinterpret_cast<const float4*>(drow + k + 4);
                     uint4 out;
@@ -186,7 +204,9 @@ at_grad_tc_kernel(const __grid_constant__ CUtensorMap w_map, const float* __rest
                     out.w = pack_bf16(tanh_fast(e1.z + d1.z), tanh_fast(e1.w + d1.w));
                     *reinterpret_cast<uint4*>(smem + L.z + kb * kASlotBytes + kc * kGroupBytes + r * 16) = out;
                 }
-                fence_async_smem();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) ecur[i] = enxt[i];
+                fence_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
                 __syncwarp();
                 if (lane == 0) mbar_arrive(z_full(kb));
             }
