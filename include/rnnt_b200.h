@@ -121,6 +121,19 @@ RNNTB200_API int rnntb200_loss_dense_bwd(const void* logits, int dtype, const in
  *      both fully written (zeros outside the valid box).  `deterministic` != 0 selects the
  *      two-pass reduction through `workspace` (rnntb200_joint_cg_bwd_workspace_bytes) instead of
  *      fp32 atomics for d_pdec. */
+/* The two projections themselves, on the tensor cores at fp32 accuracy (bf16 hi/lo split, three
+ * tcgen05 MMAs per product, fp32 accumulation):
+ *   penc[r,:] = gelu_tanh(enc[r,:]) weight[:, :He]^T + bias,   pdec[r,:] = gelu_tanh(dec[r,:]) weight[:, He:]^T
+ * enc [rows_enc, He], dec [rows_dec, Hd], weight [V, He+Hd] (the reference's fc.weight), bias [V].
+ * rnntb200_joint_cg_project_workspace_bytes returns 0 when the shape is not supported (V > 80 or
+ * He/Hd not multiples of 64): the caller then uses a library GEMM for this step. */
+RNNTB200_API size_t rnntb200_joint_cg_project_workspace_bytes(int V, int He, int Hd);
+
+RNNTB200_API int rnntb200_joint_cg_project(const float* enc, const float* dec, const float* weight,
+                              const float* bias, int rows_enc, int rows_dec, int He, int Hd, int V,
+                              float* penc, float* pdec, void* workspace, size_t workspace_bytes,
+                              void* stream);
+
 RNNTB200_API int rnntb200_joint_cg_fwd(const float* penc, const float* pdec, const int32_t* labels,
                           const int32_t* act_lens, const int32_t* label_lens, int B, int T, int U1,
                           int V, int blank, float* costs, void* lp2, float* lse,

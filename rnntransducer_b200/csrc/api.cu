@@ -73,6 +73,22 @@ RNNTB200_API int rnntb200_loss_dense_bwd(const void* logits, int dtype, const in
                              alpha, beta, grad_costs, grad_logits, (cudaStream_t)stream);
 }
 
+RNNTB200_API size_t rnntb200_joint_cg_project_workspace_bytes(int V, int He, int Hd) {
+    return proj_tc_supported(V, He, Hd) ? proj_tc_workspace_bytes(V, He, Hd) : 0;
+}
+
+RNNTB200_API int rnntb200_joint_cg_project(const float* enc, const float* dec, const float* weight,
+                              const float* bias, int rows_enc, int rows_dec, int He, int Hd, int V,
+                              float* penc, float* pdec, void* workspace, size_t workspace_bytes,
+                              void* stream) {
+    if (rows_enc < 0 || rows_dec < 0 || V <= 0 || He <= 0 || Hd <= 0) return RNNTB200_STATUS_INVALID_VALUE;
+    if (!proj_tc_supported(V, He, Hd)) return RNNTB200_STATUS_INVALID_VALUE;
+    if ((rows_enc > 0 && (!enc || !penc)) || (rows_dec > 0 && (!dec || !pdec)) || !weight || !bias)
+        return RNNTB200_STATUS_INVALID_VALUE;
+    return launch_proj_tc(enc, dec, weight, bias, rows_enc, rows_dec, He, Hd, V, penc, pdec, workspace,
+                          workspace_bytes, (cudaStream_t)stream);
+}
+
 RNNTB200_API int rnntb200_joint_cg_fwd(const float* penc, const float* pdec, const int32_t* labels,
                           const int32_t* act_lens, const int32_t* label_lens, int B, int T, int U1,
                           int V, int blank, float* costs, void* lp2, float* lse,

@@ -110,6 +110,12 @@ int launch_at_lse(const float* enc, const float* dec, const float* weight, const
                   int T, int U1, int V, int H, int blank, float2* lp2, float* lse, void* workspace,
                   size_t workspace_bytes, cudaStream_t stream);
 size_t at_workspace_bytes(int V, int H, int gemm);
+
+bool proj_tc_supported(int V, int He, int Hd);
+size_t proj_tc_workspace_bytes(int V, int He, int Hd);
+int launch_proj_tc(const float* enc, const float* dec, const float* weight, const float* bias, int rows_enc,
+                   int rows_dec, int He, int Hd, int V, float* penc, float* pdec, void* workspace,
+                   size_t workspace_bytes, cudaStream_t stream);
 int launch_at_grad(const float* enc, const float* dec, const float* weight, const float* bias, int gemm,
                    const int32_t* labels, const int32_t* act_lens, const int32_t* label_lens, int B,
                    int T, int U1, int V, int H, int blank, const float2* lp2, const float* lse,

@@ -52,7 +52,7 @@ __host__ __device__ inline Smem smem_layout(int H, int NB) {
     s.a = 0;
     s.w = (H / kKB) * kASlotBytes;
     s.w_stage_bytes = NB * kKB * 2;
-    s.dd_stride = H + 8;  // floats; +8 keeps the 8 predictor rows on different banks
+    s.dd_stride = H + 4;  // floats; +4: the 8 predictor rows start 4 banks apart, float4 reads conflict-free
     const int fixed = s.w + kUU * s.dd_stride * 4 + 40 * 8 + 32;
     s.w_stages = (227 * 1024 - fixed) / s.w_stage_bytes;
     s.w_stages = s.w_stages > kMaxWStages ? kMaxWStages : s.w_stages;
@@ -250,32 +250,26 @@ at_lse_tc_kernel(const __grid_constant__ CUtensorMap w_map, const float* __restr
                 mbar_wait(acc_full(as), (ci >> 1) & 1);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + as * kAccStride + ((uint32_t)(q * 32) << 16);
-                float v[16];
-                float cmax = -INFINITY;
+                // one pass over the chunk: online log-sum-exp with one rescale per 16 columns
                 for (int pc = 0; pc < NB / 16; ++pc) {
+                    float v[16];
                     tmem_ld16(taddr + pc * 16, v);
+                    float pmax = -INFINITY;
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         const int col = c * NB + pc * 16 + i;
-                        if (col < V) {
-                            const float x = fmaf(v[i], kLog2e, __ldg(bias + col) * kLog2e);
-                            cmax = fmaxf(cmax, x);
-                            if (col == blank) xb = x;
-                            if (col == y) xl = x;
-                        }
+                        v[i] = col < V ? fmaf(v[i], kLog2e, __ldg(bias + col) * kLog2e) : -INFINITY;
+                        pmax = fmaxf(pmax, v[i]);
+                        if (col == blank) xb = v[i];
+                        if (col == y) xl = v[i];
                     }
-                }
-                const float m_new = fmaxf(m, cmax);
-                s *= fast_ex2(m - m_new);
-                for (int pc = 0; pc < NB / 16; ++pc) {
-                    tmem_ld16(taddr + pc * 16, v);
+                    const float m_new = fmaxf(m, pmax);  // finite: the first piece always has col < V
+                    float ps = 0.f;
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int col = c * NB + pc * 16 + i;
-                        if (col < V) s += fast_ex2(fmaf(v[i], kLog2e, __ldg(bias + col) * kLog2e) - m_new);
-                    }
+                    for (int i = 0; i < 16; ++i) ps += fast_ex2(v[i] - m_new);
+                    s = fmaf(s, fast_ex2(m - m_new), ps);
+                    m = m_new;
                 }
-                m = m_new;
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(acc_empty(as));

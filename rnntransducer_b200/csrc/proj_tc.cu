@@ -1,0 +1,290 @@
+// proj_tc.cu -- the two small projections of the reference-exact joint on the tensor cores:
+//     P_enc = gelu_tanh(enc) W[:, :He]^T + bias   [B*T,  V]
+//     P_dec = gelu_tanh(dec) W[:, He:]^T          [B*U1, V]
+// (networks/transducer.py:64-69 in factorised form), at fp32 accuracy: every
+// operand is split into two bf16 numbers (x = hi + lo, |lo| <= 2^-9 |x|) and three tcgen05 MMAs
+// accumulate hi*hi + hi*lo + lo*hi in fp32 TMEM; the dropped lo*lo term is 2^-18 relative.
+// One launch covers both projections: a tile is 128 consecutive rows of enc or of dec.
+//
+//   warps 0-7   A producers: x -> gelu_tanh(x) (= x * sigmoid(2y), one EX2 + one RCP) -> (hi, lo)
+//               bf16 pair, written in UMMA K-major core-matrix layout, one 64-wide K block per stage
+//   warp  8     TMA: the matching K blocks of W_hi and W_lo (bf16 copies made by a prologue kernel)
+//   warp  9     MMA issuer: 3 x 4 tcgen05.mma per K block
+//   warps 10-13 epilogue: TMEM -> registers -> + bias -> global (one output row per thread)
+#include <algorithm>
+
+#include "tc_common.cuh"
+
+namespace rnntb200 {
+
+using namespace tc;
+
+namespace {
+
+constexpr int kKB = 64;
+constexpr int kThreads = 14 * 32;
+constexpr int kStages = 4;
+constexpr int kAHalf = 128 * kKB * 2;  // 16 KiB: one K block of A_hi (A_lo follows)
+constexpr int kTmemCols = 128;
+
+struct Problem {  // one projection
+    const float* x;     // [rows, K]
+    const float* bias;  // [V] or null
+    float* out;         // [rows, V]
+    int rows, K, tiles;
+};
+
+struct SmemP {
+    int a, w, bars, total, w_half;
+};
+__host__ __device__ inline SmemP smem_layout_p(int NB) {
+    SmemP s;
+    s.a = 0;
+    s.w = kStages * 2 * kAHalf;
+    s.w_half = NB * kKB * 2;
+    s.bars = s.w + kStages * 2 * s.w_half;
+    s.total = s.bars + 24 * 8 + 16;
+    return s;
+}
+
+__device__ __forceinline__ float gelu_tanh(float x) {
+    // 0.5 x (1 + tanh(y)) = x * sigmoid(2y),  y = sqrt(2/pi) (x + 0.044715 x^3)
+    const float y2 = 1.5957691216057308f * fmaf(0.044715f * x * x, x, x);  // 2y
+    return x * __frcp_rn(1.f + fast_ex2(-y2 * kLog2e));
+}
+
+__device__ __forceinline__ void split_store(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+    const __nv_bfloat162 h = __halves2bfloat162(ah, bh);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(a - __bfloat162float(ah), b - __bfloat162float(bh));
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// W[:, col0 : col0 + K] (row stride ldw) -> bf16 hi and lo copies, [V, K] dense
+__global__ void split_weight_kernel(const float* __restrict__ w, int ldw, int col0, int V, int K,
+                                    __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < V * K; i += gridDim.x * blockDim.x) {
+        const int v = i / K, k = i - v * K;
+        const float x = w[(size_t)v * ldw + col0 + k];
+        const __nv_bfloat16 h = __float2bfloat16_rn(x);
+        hi[i] = h;
+        lo[i] = __float2bfloat16_rn(x - __bfloat162float(h));
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+proj_tc_kernel(const __grid_constant__ CUtensorMap w0_hi, const __grid_constant__ CUtensorMap w0_lo,
+               const __grid_constant__ CUtensorMap w1_hi, const __grid_constant__ CUtensorMap w1_lo,
+               Problem p0, Problem p1, int V, int NB) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const SmemP L = smem_layout_p(NB);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool second = (int)blockIdx.x >= p0.tiles;
+    const Problem P = second ? p1 : p0;
+    const int row0 = (second ? blockIdx.x - p0.tiles : blockIdx.x) * 128;
+    const int n_kb = P.K / kKB;
+
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t a_base = sbase + L.a, w_base = sbase + L.w, bars = sbase + L.bars;
+    auto a_full = [&](int i) { return bars + 8 * i; };
+    auto a_empty = [&](int i) { return bars + 8 * (4 + i); };
+    auto w_full = [&](int i) { return bars + 8 * (8 + i); };
+    auto w_empty = [&](int i) { return bars + 8 * (12 + i); };
+    const uint32_t acc_full = bars + 8 * 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.bars + 24 * 8);
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kStages; ++i) {
+            mbar_init(a_full(i), 8);
+            mbar_init(a_empty(i), 1);
+            mbar_init(w_full(i), 1);
+            mbar_init(w_empty(i), 1);
+        }
+        mbar_init(acc_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 9) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "n"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp < 8) {
+        // ===== A producers: thread = (row r, K chunks kc0, kc0+2, kc0+4, kc0+6 of each block) =====
+        const int r = threadIdx.x & 127, kc0 = threadIdx.x >> 7;
+        const int row = min(row0 + r, P.rows - 1);  // rows past the end are computed but never stored
+        const float4* xrow = reinterpret_cast<const float4*>(P.x + (size_t)row * P.K);
+        float4 cur[8], nxt[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            cur[2 * i] = __ldg(xrow + (kc0 + 2 * i) * 2);
+            cur[2 * i + 1] = __ldg(xrow + (kc0 + 2 * i) * 2 + 1);
+        }
+        for (int kb = 0; kb < n_kb; ++kb) {
+            if (kb + 1 < n_kb) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    nxt[2 * i] = __ldg(xrow + (kb + 1) * (kKB / 4) + (kc0 + 2 * i) * 2);
+                    nxt[2 * i + 1] = __ldg(xrow + (kb + 1) * (kKB / 4) + (kc0 + 2 * i) * 2 + 1);
+                }
+            }
+            const int st = kb % kStages;
+            mbar_wait(a_empty(st), ((kb / kStages) & 1) ^ 1);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int kc = kc0 + 2 * i;
+                const float4 x0 = cur[2 * i], x1 = cur[2 * i + 1];
+                uint4 hi, lo;
+                split_store(gelu_tanh(x0.x), gelu_tanh(x0.y), hi.x, lo.x);
+                split_store(gelu_tanh(x0.z), gelu_tanh(x0.w), hi.y, lo.y);
+                split_store(gelu_tanh(x1.x), gelu_tanh(x1.y), hi.z, lo.z);
+                split_store(gelu_tanh(x1.z), gelu_tanh(x1.w), hi.w, lo.w);
+                unsigned char* dst = smem + L.a + st * 2 * kAHalf + kc * 2048 + r * 16;
+                *reinterpret_cast<uint4*>(dst) = hi;
+                *reinterpret_cast<uint4*>(dst + kAHalf) = lo;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_full(st));
+        }
+    } else if (warp == 8) {
+        if (lane == 0) {
+            const CUtensorMap* mh = second ? &w1_hi : &w0_hi;
+            const CUtensorMap* ml = second ? &w1_lo : &w0_lo;
+            for (int kb = 0; kb < n_kb; ++kb) {
+                const int st = kb % kStages;
+                mbar_wait(w_empty(st), ((kb / kStages) & 1) ^ 1);
+                mbar_arrive_expect_tx(w_full(st), 2u * (uint32_t)L.w_half);
+                tma_load_3d(w_base + st * 2 * L.w_half, mh, 0, 0, kb * (kKB / 8), w_full(st));
+                tma_load_3d(w_base + st * 2 * L.w_half + L.w_half, ml, 0, 0, kb * (kKB / 8), w_full(st));
+            }
+        }
+    } else if (warp == 9) {
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(NB, false, false);
+            const uint32_t b_lbo = NB * 16;
+            for (int kb = 0; kb < n_kb; ++kb) {
+                const int st = kb % kStages;
+                mbar_wait(a_full(st), (kb / kStages) & 1);
+                mbar_wait(w_full(st), (kb / kStages) & 1);
+                tc_fence_after();
+                const uint32_t ah = a_base + st * 2 * kAHalf, al = ah + kAHalf;
+                const uint32_t wh = w_base + st * 2 * L.w_half, wl = wh + L.w_half;
+#pragma unroll
+                for (int j = 0; j < kKB / 16; ++j) {
+                    const uint64_t dah = umma_desc(ah + j * 2 * 2048, 2048, 128), dal = umma_desc(al + j * 2 * 2048, 2048, 128);
+                    const uint64_t dwh = umma_desc(wh + j * 2 * b_lbo, b_lbo, 128), dwl = umma_desc(wl + j * 2 * b_lbo, b_lbo, 128);
+                    umma_bf16(tmem, dal, dwh, idesc, (kb | j) != 0);  // small terms first
+                    umma_bf16(tmem, dah, dwl, idesc, 1);
+                    umma_bf16(tmem, dah, dwh, idesc, 1);
+                }
+                umma_commit(a_empty(st));
+                umma_commit(w_empty(st));
+            }
+            umma_commit(acc_full);
+        }
+    } else {
+        // ===== epilogue: one output row per thread =====
+        const int q = warp & 3, r = q * 32 + lane;
+        const int row = row0 + r;
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+        for (int pc = 0; pc < NB / 16; ++pc) {
+            float v[16];
+            tmem_ld16(tmem + pc * 16 + ((uint32_t)(q * 32) << 16), v);
+            if (row < P.rows) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int col = pc * 16 + i;
+                    if (col < V) P.out[(size_t)row * V + col] = v[i] + (P.bias ? __ldg(P.bias + col) : 0.f);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols) : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// TMA view [K/8][V][8] of a dense bf16 [V, K] matrix, box {8, NB, 8}: lands as UMMA core matrices
+bool make_w_map(CUtensorMap* map, void* w, int V, int K, int NB) {
+    EncodeTiledFn encode = encode_fn();
+    if (!encode) return false;
+    const cuuint64_t gdim[3] = {8, (cuuint64_t)V, (cuuint64_t)(K / 8)};
+    const cuuint64_t gstride[2] = {(cuuint64_t)K * 2, 16};
+    const cuuint32_t box[3] = {8, (cuuint32_t)NB, (cuuint32_t)(kKB / 8)};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, w, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+}  // namespace
+
+bool proj_tc_supported(int V, int He, int Hd) {
+    return V >= 1 && V <= 80 && He >= kKB && Hd >= kKB && He % kKB == 0 && Hd % kKB == 0;
+}
+
+size_t proj_tc_workspace_bytes(int V, int He, int Hd) {
+    return 2 * align256((size_t)V * He * 2) + 2 * align256((size_t)V * Hd * 2);
+}
+
+int launch_proj_tc(const float* enc, const float* dec, const float* weight, const float* bias, int rows_enc,
+                   int rows_dec, int He, int Hd, int V, float* penc, float* pdec, void* workspace,
+                   size_t workspace_bytes, cudaStream_t stream) {
+    if (!proj_tc_supported(V, He, Hd)) return RNNTB200_STATUS_INVALID_VALUE;
+    if (!workspace || workspace_bytes < proj_tc_workspace_bytes(V, He, Hd) || ((uintptr_t)workspace & 15))
+        return RNNTB200_STATUS_INVALID_VALUE;
+    if (rows_enc + rows_dec == 0) return RNNTB200_STATUS_SUCCESS;
+    const int NB = ((V + 15) / 16) * 16;
+    unsigned char* ws = static_cast<unsigned char*>(workspace);
+    __nv_bfloat16* e_hi = reinterpret_cast<__nv_bfloat16*>(ws);
+    __nv_bfloat16* e_lo = reinterpret_cast<__nv_bfloat16*>(ws + align256((size_t)V * He * 2));
+    __nv_bfloat16* d_hi = reinterpret_cast<__nv_bfloat16*>(ws + 2 * align256((size_t)V * He * 2));
+    __nv_bfloat16* d_lo = reinterpret_cast<__nv_bfloat16*>(ws + 2 * align256((size_t)V * He * 2) + align256((size_t)V * Hd * 2));
+    const int ldw = He + Hd;
+    split_weight_kernel<<<std::min((V * He + 255) / 256, 592), 256, 0, stream>>>(weight, ldw, 0, V, He, e_hi, e_lo);
+    split_weight_kernel<<<std::min((V * Hd + 255) / 256, 592), 256, 0, stream>>>(weight, ldw, He, V, Hd, d_hi, d_lo);
+    CUtensorMap m0h, m0l, m1h, m1l;
+    if (!make_w_map(&m0h, e_hi, V, He, NB) || !make_w_map(&m0l, e_lo, V, He, NB) ||
+        !make_w_map(&m1h, d_hi, V, Hd, NB) || !make_w_map(&m1l, d_lo, V, Hd, NB))
+        return RNNTB200_STATUS_EXECUTION_FAILED;
+    Problem p0{enc, bias, penc, rows_enc, He, (rows_enc + 127) / 128};
+    Problem p1{dec, nullptr, pdec, rows_dec, Hd, (rows_dec + 127) / 128};
+    const SmemP L = smem_layout_p(NB);
+    cudaError_t e = cudaFuncSetAttribute(proj_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
+    if (e != cudaSuccess) return status_from_cuda(e);
+    proj_tc_kernel<<<p0.tiles + p1.tiles, kThreads, L.total, stream>>>(m0h, m0l, m1h, m1l, p0, p1, V, NB);
+    return launch_status();
+}
+
+}  // namespace rnntb200

@@ -65,8 +65,7 @@ def joint_rnnt_costs(enc: Tensor, dec: Tensor, weight: Tensor, bias: Optional[Te
         if weight.shape[1] != He + dec.size(-1):
             raise RuntimeError("fc.weight must be [V, enc_dim + dec_dim] in concat_gelu mode")
         # two small projections (B*(T+U1) rows instead of B*T*U1); autograd carries them back
-        penc = F.linear(F.gelu(enc.float(), approximate="tanh"), weight[:, :He].float(), bias.float())
-        pdec = F.linear(F.gelu(dec.float(), approximate="tanh"), weight[:, He:].float())
+        penc, pdec = _loss.project_concat_gelu(enc, dec, weight, bias)
         return _loss._ConcatGeluRNNT.apply(penc, pdec, labels, act_lens, label_lens, int(blank),
                                            bool(deterministic))
     if mode == "add_tanh":

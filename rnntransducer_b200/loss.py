@@ -151,6 +151,56 @@ class _ConcatGeluRNNT(torch.autograd.Function):
         return d_penc, d_pdec, None, None, None, None, None
 
 
+class _CgProject(torch.autograd.Function):
+    """penc = gelu_tanh(enc) W[:, :He]^T + b,  pdec = gelu_tanh(dec) W[:, He:]^T on the tensor cores at
+    fp32 accuracy (rnntb200_joint_cg_project).  Backward: library GEMMs on the recomputed GELU."""
+
+    @staticmethod
+    def forward(ctx, enc, dec, weight, bias):
+        B, T, He = enc.shape
+        U1, Hd = dec.shape[1], dec.shape[2]
+        V = weight.shape[0]
+        lib = _lib.load()
+        ws_bytes = lib.rnntb200_joint_cg_project_workspace_bytes(V, He, Hd)
+        enc, dec = enc.contiguous(), dec.contiguous()
+        weight, bias = weight.contiguous(), bias.contiguous()
+        penc = torch.empty(B, T, V, device=enc.device, dtype=torch.float32)
+        pdec = torch.empty(B, U1, V, device=enc.device, dtype=torch.float32)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=enc.device)
+        with torch.cuda.device(enc.device):
+            _lib.check(lib.rnntb200_joint_cg_project(
+                _ptr(enc), _ptr(dec), _ptr(weight), _ptr(bias), B * T, B * U1, He, Hd, V, _ptr(penc),
+                _ptr(pdec), _ptr(ws), ws_bytes, _stream()), "rnntb200_joint_cg_project")
+        ctx.save_for_backward(enc, dec, weight)
+        return penc, pdec
+
+    @staticmethod
+    def backward(ctx, d_penc, d_pdec):
+        enc, dec, weight = ctx.saved_tensors
+        He = enc.shape[-1]
+        V = weight.shape[0]
+        gelu = lambda x: torch.nn.functional.gelu(x, approximate="tanh")
+        dpe, dpd = d_penc.reshape(-1, V), d_pdec.reshape(-1, V)
+        d_w = torch.cat((dpe.t() @ gelu(enc).reshape(-1, He), dpd.t() @ gelu(dec).reshape(-1, dec.shape[-1])), 1)
+        d_b = dpe.sum(0)
+        d_enc = torch.ops.aten.gelu_backward(d_penc @ weight[:, :He], enc, approximate="tanh")
+        d_dec = torch.ops.aten.gelu_backward(d_pdec @ weight[:, He:], dec, approximate="tanh")
+        return d_enc, d_dec, d_w, d_b
+
+
+def project_concat_gelu(enc, dec, weight, bias):
+    """(P_enc, P_dec) of the factorised reference joint.  Tensor-core kernel when the shape is
+    supported (V <= 80, widths multiples of 64), otherwise library GEMMs."""
+    He, Hd, V = enc.size(-1), dec.size(-1), weight.shape[0]
+    if enc.is_cuda and enc.dtype == torch.float32 and weight.dtype == torch.float32 and \
+            _lib.load().rnntb200_joint_cg_project_workspace_bytes(V, He, Hd) > 0:
+        return _CgProject.apply(enc, dec, weight, bias)
+    F = torch.nn.functional
+    penc = F.linear(F.gelu(enc.float(), approximate="tanh"), weight[:, :He].float(), bias.float())
+    pdec = F.linear(F.gelu(dec.float(), approximate="tanh"), weight[:, He:].float())
+    return penc, pdec
+
+
 def _reduce(costs, reduction, warp_compat):
     if reduction == "none":
         return costs

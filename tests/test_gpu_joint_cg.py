@@ -110,6 +110,34 @@ def test_fused_extreme_logit_ranges(cuda_lib, oracle_lib, scale):
             np.testing.assert_allclose(r[k], ref64[k], atol=param_atol(ref64[k], 1e-4 * scale), err_msg=k)
 
 
+@pytest.mark.parametrize("shape", [(3, 50, 9, 73, 64, 64), (2, 130, 20, 73, 512, 512), (1, 7, 3, 40, 128, 320)])
+def test_tensor_core_projection_matches_fp64(cuda_lib, shape):
+    """rnntb200_joint_cg_project (bf16 hi/lo split, 3 tcgen05 MMAs per product) against an fp64
+    evaluation of gelu_tanh(x) W^T + b: fp32-class accuracy (2e-5 absolute on O(1) outputs), and its
+    backward against autograd through the fp64 expression."""
+    from rnntransducer_b200.loss import project_concat_gelu
+    B, T, U, V, He, Hd = shape
+    g = torch.Generator().manual_seed(5)
+    enc = torch.randn(B, T, He, generator=g).cuda().requires_grad_(True)
+    dec = torch.randn(B, U + 1, Hd, generator=g).cuda().requires_grad_(True)
+    w = ((torch.rand(V, He + Hd, generator=g) - 0.5) * 0.1).cuda().requires_grad_(True)
+    b = ((torch.rand(V, generator=g) - 0.5) * 0.1).cuda().requires_grad_(True)
+    assert cuda_lib.rnntb200_joint_cg_project_workspace_bytes(V, He, Hd) > 0
+    penc, pdec = project_concat_gelu(enc, dec, w, b)
+    up_e = torch.randn(penc.shape, generator=g).cuda()
+    up_d = torch.randn(pdec.shape, generator=g).cuda()
+    ((penc * up_e).sum() + (pdec * up_d).sum()).backward()
+    e64, d64, w64, b64 = (t.detach().double().requires_grad_(True) for t in (enc, dec, w, b))
+    gelu = lambda x: torch.nn.functional.gelu(x, approximate="tanh")
+    re = gelu(e64) @ w64[:, :He].T + b64
+    rd = gelu(d64) @ w64[:, He:].T
+    ((re * up_e.double()).sum() + (rd * up_d.double()).sum()).backward()
+    torch.testing.assert_close(penc.double(), re, atol=2e-5, rtol=0)
+    torch.testing.assert_close(pdec.double(), rd, atol=2e-5, rtol=0)
+    for ours, ref in ((enc, e64), (dec, d64), (w, w64), (b, b64)):
+        torch.testing.assert_close(ours.grad.double(), ref.grad, atol=param_atol(ref.grad.cpu().numpy()), rtol=0)
+
+
 def test_deterministic_mode_is_bit_reproducible(cuda_lib):
     d = synthetic.make_batch(4, 64, 17, 73, 32, ragged=True, seed=5, device="cuda")
     a = fused_step(d, deterministic=True)
