@@ -113,6 +113,12 @@ size_t at_workspace_bytes(int V, int H, int gemm);
 
 bool proj_tc_supported(int V, int He, int Hd);
 size_t proj_tc_workspace_bytes(int V, int He, int Hd);
+bool proj_tc_bwd_supported(int V, int He, int Hd);
+size_t proj_tc_bwd_workspace_bytes(int V, int He, int Hd);
+int launch_proj_tc_bwd(const float* enc, const float* dec, const float* weight, const float* d_penc,
+                       const float* d_pdec, int rows_enc, int rows_dec, int He, int Hd, int V, float* d_enc,
+                       float* d_dec, float* d_weight, float* d_bias, void* workspace, size_t workspace_bytes,
+                       cudaStream_t stream);
 int launch_proj_tc(const float* enc, const float* dec, const float* weight, const float* bias, int rows_enc,
                    int rows_dec, int He, int Hd, int V, float* penc, float* pdec, void* workspace,
                    size_t workspace_bytes, cudaStream_t stream);

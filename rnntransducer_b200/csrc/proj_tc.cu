@@ -233,6 +233,10 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
+inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+}  // namespace
+
 // TMA view [K/8][V][8] of a dense bf16 [V, K] matrix, box {8, NB, 8}: lands as UMMA core matrices
 bool make_w_map(CUtensorMap* map, void* w, int V, int K, int NB) {
     EncodeTiledFn encode = encode_fn();
@@ -245,10 +249,6 @@ bool make_w_map(CUtensorMap* map, void* w, int V, int K, int NB) {
                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
-
-inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
-
-}  // namespace
 
 bool proj_tc_supported(int V, int He, int Hd) {
     return V >= 1 && V <= 80 && He >= kKB && Hd >= kKB && He % kKB == 0 && Hd % kKB == 0;

@@ -1,0 +1,359 @@
+// proj_tc_bwd.cu -- backward of the two projections of the reference-exact joint (proj_tc.cu) on
+// the tensor cores at fp32 accuracy (bf16 hi/lo split, three tcgen05 MMAs per product):
+//     d_x   = (dP W_s) .* gelu_tanh'(x)            [rows, K]     K' = V
+//     d_W_s^T += gelu_tanh(x)^T dP                 [K, V]        K' = rows   (TMEM-resident per tile)
+//     d_b   += dP^T 1                              [V]           (encoder projection only)
+// for (x, W_s) = (enc, W[:, :He]) and (dec, W[:, He:]).  A tile is 128 consecutive rows; one CTA per
+// tile.  dP (hi/lo) stays in shared memory for the whole tile and is read K-major by the d_x
+// product and MN-major by the d_W product; gelu(x) streams through a 2-stage ring of 128-column
+// blocks; W K-blocks arrive by TMA and are read MN-major (K' = V).
+#include <algorithm>
+
+#include "tc_common.cuh"
+
+namespace rnntb200 {
+
+using namespace tc;
+
+namespace {
+
+constexpr int kKB = 64;
+constexpr int kThreads = 14 * 32;
+constexpr int kGroup = 2048;              // 128 rows x 16 B
+constexpr int kGxHalf = 16 * kGroup;      // 128 columns of gelu(x), hi (lo follows): 32 KiB
+constexpr int kRBytes = 16 * 256;         // ones selector, K-major [16 rows][128]
+constexpr int kColDX = 320, kColDB = 448;
+constexpr int kTmemCols = 512;
+
+struct ProblemB {
+    const float* x;   // [rows, K]
+    const float* dp;  // [rows, V]
+    float* dx;        // [rows, K]
+    int rows, K, tiles, w_col0, with_bias;
+};
+
+struct SmemPB {
+    int dp, gx, w, r, bars, total, dp_half, w_half;
+};
+__host__ __device__ inline SmemPB smem_layout_pb(int NB) {
+    SmemPB s;
+    s.dp = 0;
+    s.dp_half = (NB / 8) * kGroup;
+    s.gx = 2 * s.dp_half;
+    s.w = s.gx + 2 * 2 * kGxHalf;
+    s.w_half = NB * kKB * 2;
+    s.r = s.w + 2 * 2 * s.w_half;
+    s.bars = s.r + kRBytes;
+    s.total = s.bars + 24 * 8 + 16;
+    return s;
+}
+
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+    const __nv_bfloat162 h = __halves2bfloat162(ah, bh);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(a - __bfloat162float(ah), b - __bfloat162float(bh));
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// sigmoid(2y), y = sqrt(2/pi)(x + 0.044715 x^3):  gelu = x s,  gelu' = s + x s (1 - s) d(2y)/dx
+__device__ __forceinline__ float gelu_sig(float x) {
+    const float y2 = 1.5957691216057308f * fmaf(0.044715f * x * x, x, x);
+    return __frcp_rn(1.f + fast_ex2(-y2 * kLog2e));
+}
+__device__ __forceinline__ float gelu_val(float x) { return x * gelu_sig(x); }
+__device__ __forceinline__ float gelu_grad(float x) {
+    const float s = gelu_sig(x);
+    const float dy2 = 1.5957691216057308f * fmaf(0.134145f * x, x, 1.f);
+    return fmaf(x * s * (1.f - s), dy2, s);
+}
+
+__global__ void split_weight_kernel_b(const float* __restrict__ w, int ldw, int col0, int V, int K,
+                                      __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < V * K; i += gridDim.x * blockDim.x) {
+        const int v = i / K, k = i - v * K;
+        const float x = w[(size_t)v * ldw + col0 + k];
+        const __nv_bfloat16 h = __float2bfloat16_rn(x);
+        hi[i] = h;
+        lo[i] = __float2bfloat16_rn(x - __bfloat162float(h));
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+proj_tc_bwd_kernel(const __grid_constant__ CUtensorMap w0_hi, const __grid_constant__ CUtensorMap w0_lo,
+                   const __grid_constant__ CUtensorMap w1_hi, const __grid_constant__ CUtensorMap w1_lo,
+                   ProblemB p0, ProblemB p1, int V, int NB, float* __restrict__ d_weight, int ldw,
+                   float* __restrict__ d_bias) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const SmemPB L = smem_layout_pb(NB);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool second = (int)blockIdx.x >= p0.tiles;
+    const ProblemB P = second ? p1 : p0;
+    const int row0 = (second ? blockIdx.x - p0.tiles : blockIdx.x) * 128;
+    const int n_blk = P.K / 128, n_kb = P.K / kKB;
+
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t dp_hi = sbase + L.dp, dp_lo = dp_hi + L.dp_half, gx_base = sbase + L.gx,
+                   w_base = sbase + L.w, r_base = sbase + L.r, bars = sbase + L.bars;
+    const uint32_t dp_full = bars;
+    auto gx_full = [&](int i) { return bars + 8 * (1 + i); };
+    auto gx_empty = [&](int i) { return bars + 8 * (3 + i); };
+    auto w_full = [&](int i) { return bars + 8 * (5 + i); };
+    auto w_empty = [&](int i) { return bars + 8 * (7 + i); };
+    auto dx_full = [&](int i) { return bars + 8 * (9 + i); };
+    auto dx_empty = [&](int i) { return bars + 8 * (11 + i); };
+    const uint32_t done = bars + 8 * 13;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.bars + 24 * 8);
+
+    if (threadIdx.x == 0) {
+        mbar_init(dp_full, 8);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(gx_full(i), 8);
+            mbar_init(gx_empty(i), 1);
+            mbar_init(w_full(i), 1);
+            mbar_init(w_empty(i), 1);
+            mbar_init(dx_full(i), 1);
+            mbar_init(dx_empty(i), 4);
+        }
+        mbar_init(done, 1);
+        fence_barrier_init();
+    }
+    // ones selector (K-major B operand, 16 rows x 128): row 0 = 1 -> column 0 of the product = sum over rows
+    for (int i = threadIdx.x; i < 16 * 128; i += kThreads) {
+        const int n = i >> 7, k = i & 127;
+        *reinterpret_cast<__nv_bfloat16*>(smem + L.r + (k >> 3) * 256 + (n >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2) =
+            __float2bfloat16_rn(n == 0 ? 1.f : 0.f);
+    }
+    fence_async_smem();
+    if (warp == 9) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "n"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp < 8) {
+        // ===== producers =====
+        const int r = threadIdx.x & 127, half = threadIdx.x >> 7;
+        const int row = row0 + r;
+        const bool row_ok = row < P.rows;
+        // (1) dP tile -> (hi, lo), [v-group][row][8 v]
+        const float* dprow = P.dp + (size_t)min(row, P.rows - 1) * V;
+        for (int gi = half; gi < NB / 8; gi += 2) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int col = gi * 8 + j;
+                v[j] = (row_ok && col < V) ? __ldg(dprow + col) : 0.f;
+            }
+            uint4 hi, lo;
+            split2(v[0], v[1], hi.x, lo.x);
+            split2(v[2], v[3], hi.y, lo.y);
+            split2(v[4], v[5], hi.z, lo.z);
+            split2(v[6], v[7], hi.w, lo.w);
+            *reinterpret_cast<uint4*>(smem + L.dp + gi * kGroup + r * 16) = hi;
+            *reinterpret_cast<uint4*>(smem + L.dp + L.dp_half + gi * kGroup + r * 16) = lo;
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(dp_full);
+        // (2) gelu(x) in 128-column blocks -> (hi, lo), [h-group][row][8 h]
+        const float4* xrow = reinterpret_cast<const float4*>(P.x + (size_t)min(row, P.rows - 1) * P.K);
+        for (int blk = 0; blk < n_blk; ++blk) {
+            float4 xv[16];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                xv[2 * i] = __ldg(xrow + blk * 32 + (half + 2 * i) * 2);
+                xv[2 * i + 1] = __ldg(xrow + blk * 32 + (half + 2 * i) * 2 + 1);
+            }
+            const int st = blk & 1;
+            mbar_wait(gx_empty(st), ((blk >> 1) & 1) ^ 1);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int kc = half + 2 * i;
+                const float4 x0 = xv[2 * i], x1 = xv[2 * i + 1];
+                uint4 hi, lo;
+                split2(gelu_val(x0.x), gelu_val(x0.y), hi.x, lo.x);
+                split2(gelu_val(x0.z), gelu_val(x0.w), hi.y, lo.y);
+                split2(gelu_val(x1.x), gelu_val(x1.y), hi.z, lo.z);
+                split2(gelu_val(x1.z), gelu_val(x1.w), hi.w, lo.w);
+                if (!row_ok) hi = lo = make_uint4(0, 0, 0, 0);  // rows past the end must not reach d_W
+                unsigned char* dst = smem + L.gx + st * 2 * kGxHalf + kc * kGroup + r * 16;
+                *reinterpret_cast<uint4*>(dst) = hi;
+                *reinterpret_cast<uint4*>(dst + kGxHalf) = lo;
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(gx_full(st));
+        }
+    } else if (warp == 8) {
+        if (lane == 0) {
+            const CUtensorMap* mh = second ? &w1_hi : &w0_hi;
+            const CUtensorMap* ml = second ? &w1_lo : &w0_lo;
+            for (int kb = 0; kb < n_kb; ++kb) {
+                const int st = kb & 1;
+                mbar_wait(w_empty(st), ((kb >> 1) & 1) ^ 1);
+                mbar_arrive_expect_tx(w_full(st), 2u * (uint32_t)L.w_half);
+                tma_load_3d(w_base + st * 2 * L.w_half, mh, 0, 0, kb * (kKB / 8), w_full(st));
+                tma_load_3d(w_base + st * 2 * L.w_half + L.w_half, ml, 0, 0, kb * (kKB / 8), w_full(st));
+            }
+        }
+    } else if (warp == 9) {
+        if (lane == 0) {
+            const uint32_t id_db = umma_idesc_bf16(16, true, false);   // dP^T (MN) x ones (K-major)
+            const uint32_t id_dw = umma_idesc_bf16(NB, true, true);    // gelu(x)^T (MN) x dP (MN)
+            const uint32_t id_dx = umma_idesc_bf16(kKB, false, true);  // dP (K-major) x W (MN)
+            const uint32_t w_sbo = NB * 16;
+            mbar_wait(dp_full, 0);
+            tc_fence_after();
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+                const uint64_t ones = umma_desc(r_base + ks * 2 * 256, 256, 128);
+                umma_bf16(tmem + kColDB, umma_desc(dp_lo + ks * 256, 128, kGroup), ones, id_db, ks != 0);
+                umma_bf16(tmem + kColDB, umma_desc(dp_hi + ks * 256, 128, kGroup), ones, id_db, 1);
+            }
+            for (int blk = 0; blk < n_blk; ++blk) {
+                const int st = blk & 1;
+                mbar_wait(gx_full(st), (blk >> 1) & 1);
+                tc_fence_after();
+                const uint32_t gh = gx_base + st * 2 * kGxHalf, gl = gh + kGxHalf;
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {
+                    const uint64_t ah = umma_desc(gh + ks * 256, 128, kGroup), al = umma_desc(gl + ks * 256, 128, kGroup);
+                    const uint64_t bh = umma_desc(dp_hi + ks * 256, 128, kGroup), bl = umma_desc(dp_lo + ks * 256, 128, kGroup);
+                    umma_bf16(tmem + blk * NB, al, bh, id_dw, ks != 0);
+                    umma_bf16(tmem + blk * NB, ah, bl, id_dw, 1);
+                    umma_bf16(tmem + blk * NB, ah, bh, id_dw, 1);
+                }
+                umma_commit(gx_empty(st));
+                for (int h2 = 0; h2 < 2; ++h2) {
+                    const int kb = blk * 2 + h2, ws = kb & 1, buf = kb & 1;
+                    mbar_wait(w_full(ws), (kb >> 1) & 1);
+                    mbar_wait(dx_empty(buf), ((kb >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t wh = w_base + ws * 2 * L.w_half, wl = wh + L.w_half;
+                    for (int j = 0; j < NB / 16; ++j) {
+                        const uint64_t ah = umma_desc(dp_hi + j * 2 * kGroup, kGroup, 128), al = umma_desc(dp_lo + j * 2 * kGroup, kGroup, 128);
+                        const uint64_t bh = umma_desc(wh + j * 256, 128, w_sbo), bl = umma_desc(wl + j * 256, 128, w_sbo);
+                        umma_bf16(tmem + kColDX + buf * kKB, al, bh, id_dx, j != 0);
+                        umma_bf16(tmem + kColDX + buf * kKB, ah, bl, id_dx, 1);
+                        umma_bf16(tmem + kColDX + buf * kKB, ah, bh, id_dx, 1);
+                    }
+                    umma_commit(w_empty(ws));
+                    umma_commit(dx_full(buf));
+                }
+            }
+            umma_commit(done);
+        }
+    } else {
+        // ===== epilogue: one row per thread =====
+        const int q = warp & 3, r = q * 32 + lane;
+        const int row = row0 + r;
+        const bool row_ok = row < P.rows;
+        const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+        const float4* xrow = reinterpret_cast<const float4*>(P.x + (size_t)min(row, P.rows - 1) * P.K);
+        float4* dxrow = reinterpret_cast<float4*>(P.dx + (size_t)min(row, P.rows - 1) * P.K);
+        for (int kb = 0; kb < n_kb; ++kb) {
+            const int buf = kb & 1;
+            float4 xv[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) xv[i] = __ldg(xrow + kb * 16 + i);
+            mbar_wait(dx_full(buf), (kb >> 1) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int pc = 0; pc < 4; ++pc) {
+                float v[16];
+                tmem_ld16(tmem + kColDX + buf * kKB + pc * 16 + lane_sel, v);
+                if (row_ok) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 x = xv[pc * 4 + i];
+                        dxrow[kb * 16 + pc * 4 + i] =
+                            make_float4(v[4 * i] * gelu_grad(x.x), v[4 * i + 1] * gelu_grad(x.y),
+                                        v[4 * i + 2] * gelu_grad(x.z), v[4 * i + 3] * gelu_grad(x.w));
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(dx_empty(buf));
+        }
+        mbar_wait(done, 0);
+        tc_fence_after();
+        for (int blk = 0; blk < n_blk; ++blk)
+            for (int pc = 0; pc < NB / 16; ++pc) {
+                float v[16];
+                tmem_ld16(tmem + blk * NB + pc * 16 + lane_sel, v);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int col = pc * 16 + i;
+                    if (col < V) atomicAdd(d_weight + (size_t)col * ldw + P.w_col0 + blk * 128 + r, v[i]);
+                }
+            }
+        if (P.with_bias) {
+            float v[16];
+            tmem_ld16(tmem + kColDB + lane_sel, v);
+            if (r < V) atomicAdd(d_bias + r, v[0]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols) : "memory");
+    }
+}
+
+inline size_t align256b(size_t x) { return (x + 255) & ~(size_t)255; }
+
+}  // namespace
+
+bool make_w_map(CUtensorMap* map, void* w, int V, int K, int NB);  // proj_tc.cu
+
+bool proj_tc_bwd_supported(int V, int He, int Hd) {
+    return V >= 1 && V <= 80 && He >= 128 && Hd >= 128 && He % 128 == 0 && Hd % 128 == 0 && He <= 512 && Hd <= 512;
+}
+
+size_t proj_tc_bwd_workspace_bytes(int V, int He, int Hd) {
+    return 2 * align256b((size_t)V * He * 2) + 2 * align256b((size_t)V * Hd * 2);
+}
+
+int launch_proj_tc_bwd(const float* enc, const float* dec, const float* weight, const float* d_penc,
+                       const float* d_pdec, int rows_enc, int rows_dec, int He, int Hd, int V, float* d_enc,
+                       float* d_dec, float* d_weight, float* d_bias, void* workspace, size_t workspace_bytes,
+                       cudaStream_t stream) {
+    if (!proj_tc_bwd_supported(V, He, Hd)) return RNNTB200_STATUS_INVALID_VALUE;
+    if (!workspace || workspace_bytes < proj_tc_bwd_workspace_bytes(V, He, Hd) || ((uintptr_t)workspace & 15))
+        return RNNTB200_STATUS_INVALID_VALUE;
+    const int ldw = He + Hd;
+    if (cudaMemsetAsync(d_weight, 0, (size_t)V * ldw * sizeof(float), stream) != cudaSuccess ||
+        cudaMemsetAsync(d_bias, 0, (size_t)V * sizeof(float), stream) != cudaSuccess)
+        return RNNTB200_STATUS_MEMOPS_FAILED;
+    if (rows_enc + rows_dec == 0) return RNNTB200_STATUS_SUCCESS;
+    const int NB = ((V + 15) / 16) * 16;
+    unsigned char* ws = static_cast<unsigned char*>(workspace);
+    __nv_bfloat16* e_hi = reinterpret_cast<__nv_bfloat16*>(ws);
+    __nv_bfloat16* e_lo = reinterpret_cast<__nv_bfloat16*>(ws + align256b((size_t)V * He * 2));
+    __nv_bfloat16* d_hi = reinterpret_cast<__nv_bfloat16*>(ws + 2 * align256b((size_t)V * He * 2));
+    __nv_bfloat16* d_lo = reinterpret_cast<__nv_bfloat16*>(ws + 2 * align256b((size_t)V * He * 2) + align256b((size_t)V * Hd * 2));
+    split_weight_kernel_b<<<std::min((V * He + 255) / 256, 592), 256, 0, stream>>>(weight, ldw, 0, V, He, e_hi, e_lo);
+    split_weight_kernel_b<<<std::min((V * Hd + 255) / 256, 592), 256, 0, stream>>>(weight, ldw, He, V, Hd, d_hi, d_lo);
+    CUtensorMap m0h, m0l, m1h, m1l;
+    if (!make_w_map(&m0h, e_hi, V, He, NB) || !make_w_map(&m0l, e_lo, V, He, NB) ||
+        !make_w_map(&m1h, d_hi, V, Hd, NB) || !make_w_map(&m1l, d_lo, V, Hd, NB))
+        return RNNTB200_STATUS_EXECUTION_FAILED;
+    ProblemB p0{enc, d_penc, d_enc, rows_enc, He, (rows_enc + 127) / 128, 0, 1};
+    ProblemB p1{dec, d_pdec, d_dec, rows_dec, Hd, (rows_dec + 127) / 128, He, 0};
+    const SmemPB L = smem_layout_pb(NB);
+    cudaError_t e = cudaFuncSetAttribute(proj_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
+    if (e != cudaSuccess) return status_from_cuda(e);
+    proj_tc_bwd_kernel<<<p0.tiles + p1.tiles, kThreads, L.total, stream>>>(m0h, m0l, m1h, m1l, p0, p1, V, NB,
+                                                                           d_weight, ldw, d_bias);
+    return launch_status();
+}
+
+}  // namespace rnntb200
