@@ -184,7 +184,7 @@ cg_grad_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec
     extern __shared__ float smem[];
     float* As = smem;                  // [32][Vs]  A = 2^(P_enc - max)
     float* Bs = As + kGT2 * Vs;        // [48][Vs]  B chunk
-    float* Xs = Bs + kGUC2 * Vs;       // [32][Vs]  exact-path additions to d_penc (cold)
+    float* Xs = Bs + kGUC2 * Vs;       // [32][Vs]  corrections of d_penc: -(blank, label terms) (+ exact path)
     float* Cs = Xs + kGT2 * Vs;        // [32][49]  C chunk
     float* CBs = Cs + kGT2 * kCs;      // [32][49]  blank corrections
     float* CLs = CBs + kGT2 * kCs;     // [32][49]  label corrections
@@ -219,15 +219,14 @@ cg_grad_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec
     const int rows_t = min(kGT2, Tb - t0);
 
     for (int i = tid; i < kGT2 * Vs; i += 128) Xs[i] = 0.f;
-    if (tid < kGT2) rb[tid] = 0.f;
     if (tid == 0) n_exact = 0;
     stage_rows_exp(As, mA, lAb, blank, penc + ((size_t)b * T + t0) * V, kGT2, rows_t, V, Vs);
 
-    float E[4][NC], EL[4][NC];  // (C B)[t][v] and the label correction sum_{u: y_u = v} cl[t][u]
+    float E[4][NC];  // (C B)[t][v]
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int c = 0; c < NC; ++c) E[i][c] = EL[i][c] = 0.f;
+        for (int c = 0; c < NC; ++c) E[i][c] = 0.f;
 
     for (int u0 = 0; u0 < U1; u0 += kGUC2) {
         if (!slab && u0 > Ub) break;  // nothing left to add (slabs must be written in full)
@@ -291,11 +290,18 @@ cg_grad_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec
             }
         }
         __syncthreads();
-        // fixed-order row / column sums of the corrections
+        // corrections, in a fixed order.  Row r of d_penc loses cb at the blank column and cl at the
+        // label column of every position: one thread per frame walks the positions sequentially
+        // (two positions may share a label, so this must not be a parallel scatter).
         if (tid < kGT2) {
+            float* xr = Xs + tid * Vs;
             float sb = 0.f;
-            for (int uu = 0; uu < kGUC2; ++uu) sb += CBs[tid * kCs + uu];
-            rb[tid] += sb;
+            for (int uu = 0; uu < rows_u; ++uu) {
+                sb += CBs[tid * kCs + uu];
+                const int y = ys[uu];
+                if (y >= 0) xr[y] -= CLs[tid * kCs + uu];
+            }
+            xr[blank] -= sb;
         } else if (tid >= 64 && tid < 64 + kGUC2) {
             const int uu = tid - 64;
             float sb = 0.f, sl = 0.f;
@@ -303,23 +309,16 @@ cg_grad_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec
             ub[uu] = sb;
             ul[uu] = sl;
         }
-        // E += C B, EL += CL Y   (K = label positions of the chunk; Y[u][v] = [v == y_u])
+        // E += C B   (K = label positions of the chunk)
         for (int uu = 0; uu < rows_u; ++uu) {
-            float bv[NC], yv[NC];
-            const int y = ys[uu];
+            float bv[NC];
 #pragma unroll
-            for (int c = 0; c < NC; ++c) {
-                bv[c] = Bs[uu * Vs + tx + 16 * c];
-                yv[c] = (tx + 16 * c == y) ? 1.f : 0.f;
-            }
+            for (int c = 0; c < NC; ++c) bv[c] = Bs[uu * Vs + tx + 16 * c];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const float cv = Cs[(4 * ty + i) * kCs + uu], cl = CLs[(4 * ty + i) * kCs + uu];
+                const float cv = Cs[(4 * ty + i) * kCs + uu];
 #pragma unroll
-                for (int c = 0; c < NC; ++c) {
-                    E[i][c] = fmaf(cv, bv[c], E[i][c]);
-                    EL[i][c] = fmaf(cl, yv[c], EL[i][c]);
-                }
+                for (int c = 0; c < NC; ++c) E[i][c] = fmaf(cv, bv[c], E[i][c]);
             }
         }
         // D = C^T A   (K = frames of the tile), then d_pdec partial = B .* D - corrections
@@ -381,7 +380,7 @@ cg_grad_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec
         }
     }
     __syncthreads();
-    // d_penc = A .* E - blank correction (+ exact-path cells); padded rows come out as zeros
+    // d_penc = A .* E + corrections (+ exact-path cells); padded rows come out as zeros
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int r = 4 * ty + i;
@@ -390,8 +389,7 @@ cg_grad_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec
         for (int c = 0; c < NC; ++c) {
             const int v = tx + 16 * c;
             if (v >= V) continue;
-            const float g = fmaf(As[r * Vs + v], E[i][c], -EL[i][c]);
-            d_penc[((size_t)b * T + t0 + r) * V + v] = g + Xs[r * Vs + v] - (v == blank ? rb[r] : 0.f);
+            d_penc[((size_t)b * T + t0 + r) * V + v] = fmaf(As[r * Vs + v], E[i][c], Xs[r * Vs + v]);
         }
     }
 }
