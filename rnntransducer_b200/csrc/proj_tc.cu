@@ -6,11 +6,11 @@
 // accumulate hi*hi + hi*lo + lo*hi in fp32 TMEM; the dropped lo*lo term is 2^-18 relative.
 // One launch covers both projections: a tile is 128 consecutive rows of enc or of dec.
 //
-//   warps 0-7   A producers: x -> gelu_tanh(x) (= x * sigmoid(2y), one EX2 + one RCP) -> (hi, lo)
+//   warps 0-15  A producers: x -> gelu_tanh(x) (= x * sigmoid(2y), one EX2 + one RCP) -> (hi, lo)
 //               bf16 pair, written in UMMA K-major core-matrix layout, one 64-wide K block per stage
-//   warp  8     TMA: the matching K blocks of W_hi and W_lo (bf16 copies made by a prologue kernel)
-//   warp  9     MMA issuer: 3 x 4 tcgen05.mma per K block
-//   warps 10-13 epilogue: TMEM -> registers -> + bias -> global (one output row per thread)
+//   warp  16    TMA: the matching K blocks of W_hi and W_lo (bf16 copies made by a prologue kernel)
+//   warp  17    MMA issuer: 3 x 4 tcgen05.mma per K block
+//   warps 18-21 epilogue: TMEM -> registers -> + bias -> global (one output row per thread)
 #include <algorithm>
 
 #include "tc_common.cuh"
@@ -22,7 +22,9 @@ using namespace tc;
 namespace {
 
 constexpr int kKB = 64;
-constexpr int kThreads = 14 * 32;
+constexpr int kProducerWarps = 16;  // gelu + hi/lo split is the long pole: 4 threads per row
+constexpr int kTmaWarp = 16, kMmaWarp = 17;
+constexpr int kThreads = 22 * 32;
 constexpr int kStages = 4;
 constexpr int kAHalf = 128 * kKB * 2;  // 16 KiB: one K block of A_hi (A_lo follows)
 constexpr int kTmemCols = 128;
@@ -96,7 +98,7 @@ proj_tc_kernel(const __grid_constant__ CUtensorMap w0_hi, const __grid_constant_
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kStages; ++i) {
-            mbar_init(a_full(i), 8);
+            mbar_init(a_full(i), kProducerWarps);
             mbar_init(a_empty(i), 1);
             mbar_init(w_full(i), 1);
             mbar_init(w_empty(i), 1);
@@ -104,7 +106,7 @@ proj_tc_kernel(const __grid_constant__ CUtensorMap w0_hi, const __grid_constant_
         mbar_init(acc_full, 1);
         fence_barrier_init();
     }
-    if (warp == 9) {
+    if (warp == kMmaWarp) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                      "n"(kTmemCols)
                      : "memory");
@@ -115,30 +117,30 @@ proj_tc_kernel(const __grid_constant__ CUtensorMap w0_hi, const __grid_constant_
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp < 8) {
-        // ===== A producers: thread = (row r, K chunks kc0, kc0+2, kc0+4, kc0+6 of each block) =====
+    if (warp < kProducerWarps) {
+        // ===== A producers: thread = (row r, K chunks kc0 and kc0+4 of each block) =====
         const int r = threadIdx.x & 127, kc0 = threadIdx.x >> 7;
         const int row = min(row0 + r, P.rows - 1);  // rows past the end are computed but never stored
         const float4* xrow = reinterpret_cast<const float4*>(P.x + (size_t)row * P.K);
-        float4 cur[8], nxt[8];
+        float4 cur[4], nxt[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            cur[2 * i] = __ldg(xrow + (kc0 + 2 * i) * 2);
-            cur[2 * i + 1] = __ldg(xrow + (kc0 + 2 * i) * 2 + 1);
+        for (int i = 0; i < 2; ++i) {
+            cur[2 * i] = __ldg(xrow + (kc0 + 4 * i) * 2);
+            cur[2 * i + 1] = __ldg(xrow + (kc0 + 4 * i) * 2 + 1);
         }
         for (int kb = 0; kb < n_kb; ++kb) {
             if (kb + 1 < n_kb) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    nxt[2 * i] = __ldg(xrow + (kb + 1) * (kKB / 4) + (kc0 + 2 * i) * 2);
-                    nxt[2 * i + 1] = __ldg(xrow + (kb + 1) * (kKB / 4) + (kc0 + 2 * i) * 2 + 1);
+                for (int i = 0; i < 2; ++i) {
+                    nxt[2 * i] = __ldg(xrow + (kb + 1) * (kKB / 4) + (kc0 + 4 * i) * 2);
+                    nxt[2 * i + 1] = __ldg(xrow + (kb + 1) * (kKB / 4) + (kc0 + 4 * i) * 2 + 1);
                 }
             }
             const int st = kb % kStages;
             mbar_wait(a_empty(st), ((kb / kStages) & 1) ^ 1);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int kc = kc0 + 2 * i;
+            for (int i = 0; i < 2; ++i) {
+                const int kc = kc0 + 4 * i;
                 const float4 x0 = cur[2 * i], x1 = cur[2 * i + 1];
                 uint4 hi, lo;
                 split_store(gelu_tanh(x0.x), gelu_tanh(x0.y), hi.x, lo.x);
@@ -150,12 +152,12 @@ proj_tc_kernel(const __grid_constant__ CUtensorMap w0_hi, const __grid_constant_
                 *reinterpret_cast<uint4*>(dst + kAHalf) = lo;
             }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
+            for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(a_full(st));
         }
-    } else if (warp == 8) {
+    } else if (warp == kTmaWarp) {
         if (lane == 0) {
             const CUtensorMap* mh = second ? &w1_hi : &w0_hi;
             const CUtensorMap* ml = second ? &w1_lo : &w0_lo;
@@ -167,7 +169,7 @@ proj_tc_kernel(const __grid_constant__ CUtensorMap w0_hi, const __grid_constant_
                 tma_load_3d(w_base + st * 2 * L.w_half + L.w_half, ml, 0, 0, kb * (kKB / 8), w_full(st));
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == kMmaWarp) {
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_bf16(NB, false, false);
             const uint32_t b_lbo = NB * 16;
@@ -211,7 +213,7 @@ proj_tc_kernel(const __grid_constant__ CUtensorMap w0_hi, const __grid_constant_
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 9) {
+    if (warp == kMmaWarp) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols) : "memory");
     }

@@ -18,7 +18,7 @@ using namespace tc;
 namespace {
 
 constexpr int kKB = 64;
-constexpr int kThreads = 14 * 32;
+constexpr int kThreads = 18 * 32;  // 8 producer warps, TMA, MMA, 2 x 4 epilogue warps (one group per dX buffer)
 constexpr int kGroup = 2048;              // 128 rows x 16 B
 constexpr int kGxHalf = 16 * kGroup;      // 128 columns of gelu(x), hi (lo follows): 32 KiB
 constexpr int kRBytes = 16 * 256;         // ones selector, K-major [16 rows][128]
@@ -250,15 +250,17 @@ proj_tc_bwd_kernel(const __grid_constant__ CUtensorMap w0_hi, const __grid_const
             umma_commit(done);
         }
     } else {
-        // ===== epilogue: one row per thread =====
+        // ===== epilogue: one row per thread; group g (warps 10-13 / 14-17) owns dX buffer g, i.e. the
+        // even / odd 64-column pieces, and half of the final d_W flush =====
+        const int grp = (warp - 10) >> 2;
         const int q = warp & 3, r = q * 32 + lane;
         const int row = row0 + r;
         const bool row_ok = row < P.rows;
         const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
         const float4* xrow = reinterpret_cast<const float4*>(P.x + (size_t)min(row, P.rows - 1) * P.K);
         float4* dxrow = reinterpret_cast<float4*>(P.dx + (size_t)min(row, P.rows - 1) * P.K);
-        for (int kb = 0; kb < n_kb; ++kb) {
-            const int buf = kb & 1;
+        for (int kb = grp; kb < n_kb; kb += 2) {
+            const int buf = grp;
             float4 xv[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) xv[i] = __ldg(xrow + kb * 16 + i);
@@ -284,7 +286,7 @@ proj_tc_bwd_kernel(const __grid_constant__ CUtensorMap w0_hi, const __grid_const
         }
         mbar_wait(done, 0);
         tc_fence_after();
-        for (int blk = 0; blk < n_blk; ++blk)
+        for (int blk = grp; blk < n_blk; blk += 2)
             for (int pc = 0; pc < NB / 16; ++pc) {
                 float v[16];
                 tmem_ld16(tmem + blk * NB + pc * 16 + lane_sel, v);
@@ -294,7 +296,7 @@ proj_tc_bwd_kernel(const __grid_constant__ CUtensorMap w0_hi, const __grid_const
                     if (col < V) atomicAdd(d_weight + (size_t)col * ldw + P.w_col0 + blk * 128 + r, v[i]);
                 }
             }
-        if (P.with_bias) {
+        if (P.with_bias && grp == 0) {
             float v[16];
             tmem_ld16(tmem + kColDB + lane_sel, v);
             if (r < V) atomicAdd(d_bias + r, v[0]);
