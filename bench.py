@@ -50,6 +50,7 @@ def parse_args():
     p.add_argument("--mode", default="concat_gelu", choices=["concat_gelu", "add_tanh"])
     p.add_argument("--gemm", default=None, choices=["fp32", "bf16"])
     p.add_argument("--ragged", action="store_true")
+    p.add_argument("--batch", type=int, default=None, help="override the config's utterances per GPU")
     p.add_argument("--eager", action="store_true", help="do not replay the step from a CUDA graph")
     p.add_argument("--deterministic", action="store_true")
     p.add_argument("--no-cpu-baseline", action="store_true")
@@ -68,7 +69,9 @@ def hbm_peak():
 
 def workload_config(args, world):
     from rnntransducer_b200 import synthetic
-    c = synthetic.CONFIGS[args.cfg]
+    c = dict(synthetic.CONFIGS[args.cfg])
+    if args.batch:
+        c["B"] = args.batch
     gemm = args.gemm or ("fp32" if args.mode == "concat_gelu" or args.cfg == 2 else "bf16")
     return c, gemm, {
         "workload": f"BASELINE cfg{args.cfg}: B={c['B']} T={c['T']} U={c['U']} V={c['V']} H={c['H']} per GPU, "

@@ -4,16 +4,16 @@
 //
 // One persistent CTA per SM walks tiles of 128 lattice cells (16 t x 8 u of one utterance):
 //
-//   warps 0-7   A producers: z = tanh(e_t + d_u) on the CUDA cores (MUFU.TANH), rounded to bf16 and
+//   warps 0-15  A producers: z = tanh(e_t + d_u) on the CUDA cores (MUFU.TANH), rounded to bf16 and
 //               written straight into the UMMA K-major core-matrix layout, one 64-wide K block per
 //               shared-memory slot (the A operand is computed, never loaded);
-//   warp  8     TMA producer: streams W (bf16 copy, [V,H]) as [N-chunk x 64] K blocks through a
+//   warp  16    TMA producer: streams W (bf16 copy, [V,H]) as [N-chunk x 64] K blocks through a
 //               ring of shared-memory stages with cp.async.bulk.tensor (3-D view so that the
 //               box lands directly in core-matrix order; rows >= V are zero-filled by the TMA);
-//   warp  9     MMA issuer: one elected thread issues tcgen05.mma (M = 128 cells, N = chunk of the
+//   warp  17    MMA issuer: one elected thread issues tcgen05.mma (M = 128 cells, N = chunk of the
 //               vocabulary, K = 16 per instruction), accumulating in TMEM; tcgen05.commit releases
 //               W stages / A slots and publishes the accumulator;
-//   warps 10-13 epilogue: each thread owns one lattice cell (one TMEM lane), reads its logits with
+//   warps 18-21 epilogue: each thread owns one lattice cell (one TMEM lane), reads its logits with
 //               tcgen05.ld, adds the bias and runs an online log-sum-exp across vocabulary chunks
 //               (two accumulator stages in TMEM, so chunk c+1 is multiplied while chunk c is
 //               reduced), picks the blank / label columns and writes 12 bytes per cell.
@@ -33,9 +33,10 @@ namespace {
 
 constexpr int kTT = 16, kUU = 8;       // tile = 16 frames x 8 label positions = 128 cells (MMA M)
 constexpr int kKB = 64;                // K elements per A slot / W stage
-constexpr int kProducerThreads = 256;  // warps 0-7
-constexpr int kTmaWarp = 8, kMmaWarp = 9;  // warps 10-13: epilogue
-constexpr int kThreads = 14 * 32;
+constexpr int kProducerWarps = 16;
+constexpr int kProducerThreads = kProducerWarps * 32;  // warps 0-7
+constexpr int kTmaWarp = 16, kMmaWarp = 17;  // warps 10-13: epilogue
+constexpr int kThreads = 22 * 32;
 constexpr int kMaxWStages = 8;  // W K-blocks in flight (TMA latency ~1 us: a 2-deep ring starves the MMA)
 constexpr int kAccStride = 128;        // TMEM columns per accumulator stage
 constexpr int kTmemCols = 256;
@@ -94,7 +95,7 @@ at_lse_tc_kernel(const __grid_constant__ CUtensorMap w_map, const float* __restr
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.bars + 40 * 8);
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kMaxSlots; ++i) { mbar_init(a_full(i), 8); mbar_init(a_empty(i), 1); }
+        for (int i = 0; i < kMaxSlots; ++i) { mbar_init(a_full(i), kProducerWarps); mbar_init(a_empty(i), 1); }
         for (int i = 0; i < kMaxWStages; ++i) { mbar_init(w_full(i), 1); mbar_init(w_empty(i), 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), 4); }
         fence_barrier_init();
@@ -122,7 +123,7 @@ at_lse_tc_kernel(const __grid_constant__ CUtensorMap w_map, const float* __restr
         return t0 < min(__ldg(act_lens + b), T) && u0 <= min(__ldg(label_lens + b), U1 - 1);
     };
 
-    if (warp < 8) {
+    if (warp < kProducerWarps) {
         // ===== A producers =====
         const int p = threadIdx.x;
         const int r = p & 127, kc0 = p >> 7;  // cell row of the tile, first 8-wide K chunk
@@ -133,7 +134,7 @@ at_lse_tc_kernel(const __grid_constant__ CUtensorMap w_map, const float* __restr
             if (!decode(tile, b, t0, u0)) continue;
             // stage the tile's 8 predictor rows (each is reused by all 16 frames); the encoder rows
             // are read straight from global memory: every element is needed by exactly one warp
-            asm volatile("bar.sync 1, 256;" ::: "memory");  // previous tile's readers are done
+            asm volatile("bar.sync 1, 512;" ::: "memory");  // previous tile's readers are done
             const int H4 = H / 4;
             for (int i = p; i < kUU * H4; i += kProducerThreads) {
                 const int row = i / H4, c4 = i - row * H4;
@@ -141,27 +142,27 @@ at_lse_tc_kernel(const __grid_constant__ CUtensorMap w_map, const float* __restr
                 *reinterpret_cast<float4*>(dd + row * L.dd_stride + 4 * c4) =
                     __ldg(reinterpret_cast<const float4*>(src) + c4);
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            asm volatile("bar.sync 1, 512;" ::: "memory");
             const float4* erow = reinterpret_cast<const float4*>(enc + ((size_t)b * T + min(t0 + tt, T - 1)) * H);
             const float* drow = dd + uu * L.dd_stride;
-            float4 ecur[8], enxt[8];  // this thread's 4 x 8 encoder values of a K block, double-buffered
+            float4 ecur[4], enxt[4];  // this thread's 2 x 8 encoder values of a K block, double-buffered
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                ecur[2 * i] = __ldg(erow + (kc0 + 2 * i) * 2);
-                ecur[2 * i + 1] = __ldg(erow + (kc0 + 2 * i) * 2 + 1);
+            for (int i = 0; i < 2; ++i) {
+                ecur[2 * i] = __ldg(erow + (kc0 + 4 * i) * 2);
+                ecur[2 * i + 1] = __ldg(erow + (kc0 + 4 * i) * 2 + 1);
             }
             for (int kb = 0; kb < n_slots; ++kb) {
                 if (kb + 1 < n_slots) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        enxt[2 * i] = __ldg(erow + ((kb + 1) * kKB / 4) + (kc0 + 2 * i) * 2);
-                        enxt[2 * i + 1] = __ldg(erow + ((kb + 1) * kKB / 4) + (kc0 + 2 * i) * 2 + 1);
+                    for (int i = 0; i < 2; ++i) {
+                        enxt[2 * i] = __ldg(erow + ((kb + 1) * kKB / 4) + (kc0 + 4 * i) * 2);
+                        enxt[2 * i + 1] = __ldg(erow + ((kb + 1) * kKB / 4) + (kc0 + 4 * i) * 2 + 1);
                     }
                 }
                 mbar_wait(a_empty(kb), (n & 1) ^ 1);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int kc = kc0 + 2 * i;
+                for (int i = 0; i < 2; ++i) {
+                    const int kc = kc0 + 4 * i;
                     const int k = kb * kKB + kc * 8;
                     const float4 e0 = ecur[2 * i], e1 = ecur[2 * i + 1];
                     const float4 d0 = *reinterpret_cast<const float4*>(drow + k);
@@ -175,7 +176,7 @@ at_lse_tc_kernel(const __grid_constant__ CUtensorMap w_map, const float* __restr
                     *reinterpret_cast<uint4*>(smem + L.a + kb * kASlotBytes + kc * 2048 + r * 16) = out;
                 }
 #pragma unroll
-                for (int i = 0; i < 8; ++i) ecur[i] = enxt[i];
+                for (int i = 0; i < 4; ++i) ecur[i] = enxt[i];
                 fence_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
                 __syncwarp();
                 if (lane == 0) mbar_arrive(a_full(kb));

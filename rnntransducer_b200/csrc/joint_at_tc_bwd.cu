@@ -15,8 +15,8 @@
 // K-major operand by one product and as an MN-major operand by another (core matrices are 8 x 16 B
 // either way; only the descriptor strides and the major bits of the instruction descriptor change).
 //
-// Warp roles (one persistent CTA per SM): warps 0-7 build z; warp 8 streams W by TMA (twice per
-// tile: for S and for dZ); warp 9 issues every MMA; warps 10-13 own one lattice cell (TMEM lane)
+// Warp roles (one persistent CTA per SM): warps 0-15 build z; warp 16 streams W by TMA (twice per
+// tile: for S and for dZ); warp 17 issues every MMA; warps 18-21 own one lattice cell (TMEM lane)
 // each: they turn S into G, dZ into dP, and move the reduced d_enc / d_dec tiles to HBM (fp32
 // atomics).  mbarrier-only synchronisation.  TMEM map (512 columns): dW^T [0,320) | S [320,400) |
 // dZ piece [400,464) | d_enc^T/d_dec^T [320,448) (aliases S and dZ, both dead by then) | db [464,480).
@@ -35,9 +35,10 @@ namespace {
 
 constexpr int kTT = 16, kUU = 8;
 constexpr int kKB = 64;
-constexpr int kProducerThreads = 256;
-constexpr int kTmaWarp = 8, kMmaWarp = 9;
-constexpr int kThreads = 14 * 32;
+constexpr int kProducerWarps = 16;
+constexpr int kProducerThreads = kProducerWarps * 32;
+constexpr int kTmaWarp = 16, kMmaWarp = 17;
+constexpr int kThreads = 22 * 32;
 constexpr int kMaxWStages = 8;
 constexpr int kASlotBytes = 128 * kKB * 2;  // one 64-wide K block of z: 16 KiB
 constexpr int kGroupBytes = 2048;           // 128 rows x 16 B: one 8-element column group of z / G
@@ -109,7 +110,7 @@ at_grad_tc_kernel(const __grid_constant__ CUtensorMap w_map, const float* __rest
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.bars + 40 * 8);
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 8; ++i) mbar_init(z_full(i), 8);
+        for (int i = 0; i < 8; ++i) mbar_init(z_full(i), kProducerWarps);
         mbar_init(z_empty, 1);
         for (int i = 0; i < kMaxWStages; ++i) { mbar_init(w_full(i), 1); mbar_init(w_empty(i), 1); }
         mbar_init(s_full, 1);
@@ -152,7 +153,7 @@ at_grad_tc_kernel(const __grid_constant__ CUtensorMap w_map, const float* __rest
         return t0 < min(__ldg(act_lens + b), T) && u0 <= min(__ldg(label_lens + b), U1 - 1);
     };
 
-    if (warp < 8) {
+    if (warp < kProducerWarps) {
         // ===== producers: z = tanh(e_t + d_u) -> bf16, core-matrix layout, one K block per slot =====
         const int p = threadIdx.x;
         const int r = p & 127, kc0 = p >> 7;
@@ -164,7 +165,7 @@ at_grad_tc_kernel(const __grid_constant__ CUtensorMap w_map, const float* __rest
             mbar_wait(z_empty, (n & 1) ^ 1);  // every reader of the previous tile's z / dP is done
             // stage the tile's 8 predictor rows (each is reused by all 16 frames); the encoder rows
             // are read straight from global memory: every element is needed by exactly one warp
-            asm volatile("bar.sync 1, 256;" ::: "memory");  // previous tile's readers are done
+            asm volatile("bar.sync 1, 512;" ::: "memory");  // previous tile's readers are done
             const int H4 = H / 4;
             for (int i = p; i < kUU * H4; i += kProducerThreads) {
                 const int row = i / H4, c4 = i - row * H4;
@@ -172,27 +173,27 @@ at_grad_tc_kernel(const __grid_constant__ CUtensorMap w_map, const float* __rest
                 *reinterpret_cast<float4*>(dd + row * L.dd_stride + 4 * c4) =
                     __ldg(reinterpret_cast<const float4*>(src) + c4);
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            asm volatile("bar.sync 1, 512;" ::: "memory");
             const float4* erow = reinterpret_cast<const float4*>(enc + ((size_t)b * T + min(t0 + tt, T - 1)) * H);
             const float* drow = dd + uu * L.dd_stride;
-            float4 ecur[8], enxt[8];  // this thread's 4 x 8 encoder values of a K block, double-buffered
+            float4 ecur[4], enxt[4];  // this thread's 2 x 8 encoder values of a K block, double-buffered
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                ecur[2 * i] = __ldg(erow + (kc0 + 2 * i) * 2);
-                ecur[2 * i + 1] = __ldg(erow + (kc0 + 2 * i) * 2 + 1);
+            for (int i = 0; i < 2; ++i) {
+                ecur[2 * i] = __ldg(erow + (kc0 + 4 * i) * 2);
+                ecur[2 * i + 1] = __ldg(erow + (kc0 + 4 * i) * 2 + 1);
             }
             for (int kb = 0; kb < n_slots; ++kb) {
                 if (kb + 1 < n_slots) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        enxt[2 * i] = __ldg(erow + ((kb + 1) * kKB / 4) + (kc0 + 2 * i) * 2);
-                        enxt[2 * i + 1] = __ldg(erow + ((kb + 1) * kKB / 4) + (kc0 + 2 * i) * 2 + 1);
+                    for (int i = 0; i < 2; ++i) {
+                        enxt[2 * i] = __ldg(erow + ((kb + 1) * kKB / 4) + (kc0 + 4 * i) * 2);
+                        enxt[2 * i + 1] = __ldg(erow + ((kb + 1) * kKB / 4) + (kc0 + 4 * i) * 2 + 1);
                     }
                 }
                 
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int kc = kc0 + 2 * i;
+                for (int i = 0; i < 2; ++i) {
+                    const int kc = kc0 + 4 * i;
                     const int k = kb * kKB + kc * 8;
                     const float4 e0 = ecur[2 * i], e1 = ecur[2 * i + 1];
                     const float4 d0 = *reinterpret_cast<const float4*>(drow + k);
@@ -205,7 +206,7 @@ at_grad_tc_kernel(const __grid_constant__ CUtensorMap w_map, const float* __rest
                     *reinterpret_cast<uint4*>(smem + L.z + kb * kASlotBytes + kc * kGroupBytes + r * 16) = out;
                 }
 #pragma unroll
-                for (int i = 0; i < 8; ++i) ecur[i] = enxt[i];
+                for (int i = 0; i < 4; ++i) ecur[i] = enxt[i];
                 fence_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
                 __syncwarp();
                 if (lane == 0) mbar_arrive(z_full(kb));

@@ -110,3 +110,14 @@ def test_add_tanh_module_end_to_end(cuda_lib):
     assert abs(float(loss) - float(loss2)) < 1e-5 * abs(float(loss2))
     for n, p in net.named_parameters():
         torch.testing.assert_close(fused[n], p.grad, atol=1e-4, rtol=1e-3, msg=n)
+
+
+def test_add_tanh_tensor_core_large_vocab(cuda_lib):
+    """V = 1024, H = 512 (BASELINE cfg 4's joint): the tcgen05 forward runs 8 vocabulary chunks with
+    the online log-sum-exp across them; checked against the fp32 CUDA-core kernels (bf16 bound)."""
+    d = synthetic.make_batch(2, 48, 10, 1024, 512, mode="add_tanh", ragged=True, seed=1239, device="cuda")
+    a = rb.joint_rnnt_costs(d["enc"], d["dec"], d["weight"], d["bias"], d["labels"], d["act_lens"],
+                            d["label_lens"], 0, "add_tanh", "bf16")
+    b = rb.joint_rnnt_costs(d["enc"], d["dec"], d["weight"], d["bias"], d["labels"], d["act_lens"],
+                            d["label_lens"], 0, "add_tanh", "fp32")
+    torch.testing.assert_close(a, b, rtol=5e-3, atol=0)

@@ -202,3 +202,43 @@ def test_jointnet_module_end_to_end(cuda_lib):
     assert abs(results[True][0] - results[False][0]) < 1e-5 * abs(results[False][0])
     for n, gr in results[False][1].items():
         torch.testing.assert_close(results[True][1][n], gr, atol=1e-4, rtol=1e-3, msg=n)
+
+
+def test_full_size_cfg3_long_utterances(cuda_lib):
+    """BASELINE cfg 3 (B=8, T=1500, U=300, V=73, H=512; 1800 anti-diagonals, 10-warp sweeps): fused path
+    against our dense-logits path on the same inputs (1.05 GB of logits), plus the size-independent
+    properties."""
+    c = synthetic.CONFIGS[3]
+    d = synthetic.make_batch(c["B"], c["T"], c["U"], c["V"], c["H"], ragged=True, seed=1237, device="cuda")
+    fused = fused_step(d)
+    assert np.isfinite(fused["costs"]).all() and (fused["costs"] > 0).all()
+    with torch.no_grad():
+        logits = rb.joint_dense(d["enc"], d["dec"], d["weight"], d["bias"])
+    logits.requires_grad_(True)
+    costs = rb.rnnt_costs(logits, d["labels"], d["act_lens"], d["label_lens"])
+    np.testing.assert_allclose(fused["costs"], costs.detach().cpu().numpy(), rtol=LOSS_RTOL)
+    costs.mean().backward()
+    g = logits.grad  # d loss / d logits: its reductions are the gradients of the two projections' bias
+    d_bias_dense = g.sum((0, 1, 2)).cpu().numpy()
+    np.testing.assert_allclose(fused["d_bias"], d_bias_dense, atol=param_atol(d_bias_dense))
+    assert abs(float(fused["d_bias"].sum())) < param_atol(fused["d_bias"])
+    al = d["act_lens"].cpu().numpy()
+    for b in range(c["B"]):
+        assert np.all(fused["d_enc"][b, al[b]:] == 0)
+
+
+def test_large_vocab_cfg4_generic_kernels(cuda_lib):
+    """V = 1024 (BASELINE cfg 4's vocabulary) takes the generic concat-GELU kernels (the factorised
+    ones keep <= 128 columns in registers): fused against the dense path at B = 3."""
+    c = synthetic.CONFIGS[4]
+    d = synthetic.make_batch(3, c["T"], c["U"], c["V"], c["H"], ragged=True, seed=1238, device="cuda")
+    fused = fused_step(d)
+    t = {k: d[k].clone().requires_grad_(True) for k in ("enc", "dec", "weight", "bias")}
+    logits = rb.joint_dense(t["enc"], t["dec"], t["weight"], t["bias"])
+    costs = rb.rnnt_costs(logits, d["labels"], d["act_lens"], d["label_lens"])
+    costs.mean().backward()
+    np.testing.assert_allclose(fused["costs"], costs.detach().cpu().numpy(), rtol=LOSS_RTOL)
+    for k in ("enc", "dec", "weight", "bias"):
+        ref = t[k].grad.cpu().numpy()
+        np.testing.assert_allclose(fused["d_" + k], ref, err_msg=k,
+                                   atol=param_atol(ref) if k in ("weight", "bias") else GRAD_ATOL)
