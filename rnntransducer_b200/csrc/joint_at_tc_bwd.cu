@@ -15,11 +15,11 @@
 // K-major operand by one product and as an MN-major operand by another (core matrices are 8 x 16 B
 // either way; only the descriptor strides and the major bits of the instruction descriptor change).
 //
-// Warp roles (one persistent CTA per SM): warps 0-15 build z; warp 16 streams W by TMA (twice per
-// tile: for S and for dZ); warp 17 issues every MMA; warps 18-21 own one lattice cell (TMEM lane)
+// Warp roles (one persistent CTA per SM): warps 0-7 build z; warp 8 streams W by TMA (twice per
+// tile: for S and for dZ); warp 9 issues every MMA; warps 10-17 (two groups) own one lattice cell (TMEM lane)
 // each: they turn S into G, dZ into dP, and move the reduced d_enc / d_dec tiles to HBM (fp32
 // atomics).  mbarrier-only synchronisation.  TMEM map (512 columns): dW^T [0,320) | S [320,400) |
-// dZ piece [400,464) | d_enc^T/d_dec^T [320,448) (aliases S and dZ, both dead by then) | db [464,480).
+// dZ pieces [400,464) and [320,384) (the second aliases S, dead by then) | d_enc^T/d_dec^T [320,448) (aliases S and dZ, both dead by then) | db [464,480).
 //
 // Supported: V <= 80 (one vocabulary chunk; KsponSpeech has 73), H a multiple of 128, H <= 512.
 // Other shapes use the CUDA-core kernel in joint_at.cu.
@@ -35,10 +35,10 @@ namespace {
 
 constexpr int kTT = 16, kUU = 8;
 constexpr int kKB = 64;
-constexpr int kProducerWarps = 16;
+constexpr int kProducerWarps = 8;   // z production is not the long pole here
 constexpr int kProducerThreads = kProducerWarps * 32;
-constexpr int kTmaWarp = 16, kMmaWarp = 17;
-constexpr int kThreads = 22 * 32;
+constexpr int kTmaWarp = 8, kMmaWarp = 9;    // warps 10-13 / 14-17: epilogue groups 0 / 1
+constexpr int kThreads = 18 * 32;
 constexpr int kMaxWStages = 8;
 constexpr int kASlotBytes = 128 * kKB * 2;  // one 64-wide K block of z: 16 KiB
 constexpr int kGroupBytes = 2048;           // 128 rows x 16 B: one 8-element column group of z / G
@@ -104,9 +104,10 @@ at_grad_tc_kernel(const __grid_constant__ CUtensorMap w_map, const float* __rest
     const uint32_t z_empty = bars + 8 * 8;
     auto w_full = [&](int i) { return bars + 8 * (9 + i); };
     auto w_empty = [&](int i) { return bars + 8 * (17 + i); };
-    const uint32_t s_full = bars + 8 * 25, g_full = bars + 8 * 26, dz_full = bars + 8 * 27,
-                   dz_empty = bars + 8 * 28, p_full = bars + 8 * 29, r_full = bars + 8 * 30,
-                   r_empty = bars + 8 * 31, done = bars + 8 * 32;
+    const uint32_t s_full = bars + 8 * 25, g_full = bars + 8 * 26, p_full = bars + 8 * 29,
+                   r_full = bars + 8 * 30, r_empty = bars + 8 * 31, done = bars + 8 * 32;
+    auto dz_full = [&](int i) { return bars + 8 * (33 + i); };   // one dZ piece buffer per epilogue group
+    auto dz_empty = [&](int i) { return bars + 8 * (35 + i); };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.bars + 40 * 8);
 
     if (threadIdx.x == 0) {
@@ -114,12 +115,11 @@ at_grad_tc_kernel(const __grid_constant__ CUtensorMap w_map, const float* __rest
         mbar_init(z_empty, 1);
         for (int i = 0; i < kMaxWStages; ++i) { mbar_init(w_full(i), 1); mbar_init(w_empty(i), 1); }
         mbar_init(s_full, 1);
-        mbar_init(g_full, 4);
-        mbar_init(dz_full, 1);
-        mbar_init(dz_empty, 4);
-        mbar_init(p_full, 4);
+        mbar_init(g_full, 8);
+        for (int i = 0; i < 2; ++i) { mbar_init(dz_full(i), 1); mbar_init(dz_empty(i), 4); }
+        mbar_init(p_full, 8);
         mbar_init(r_full, 1);
-        mbar_init(r_empty, 4);
+        mbar_init(r_empty, 8);
         mbar_init(done, 1);
         fence_barrier_init();
     }
@@ -165,7 +165,7 @@ at_grad_tc_kernel(const __grid_constant__ CUtensorMap w_map, const float* __rest
             mbar_wait(z_empty, (n & 1) ^ 1);  // every reader of the previous tile's z / dP is done
             // stage the tile's 8 predictor rows (each is reused by all 16 frames); the encoder rows
             // are read straight from global memory: every element is needed by exactly one warp
-            asm volatile("bar.sync 1, 512;" ::: "memory");  // previous tile's readers are done
+            asm volatile("bar.sync 1, 256;" ::: "memory");  // previous tile's readers are done
             const int H4 = H / 4;
             for (int i = p; i < kUU * H4; i += kProducerThreads) {
                 const int row = i / H4, c4 = i - row * H4;
@@ -173,27 +173,27 @@ at_grad_tc_kernel(const __grid_constant__ CUtensorMap w_map, const float* __rest
                 *reinterpret_cast<float4*>(dd + row * L.dd_stride + 4 * c4) =
                     __ldg(reinterpret_cast<const float4*>(src) + c4);
             }
-            asm volatile("bar.sync 1, 512;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             const float4* erow = reinterpret_cast<const float4*>(enc + ((size_t)b * T + min(t0 + tt, T - 1)) * H);
             const float* drow = dd + uu * L.dd_stride;
-            float4 ecur[4], enxt[4];  // this thread's 2 x 8 encoder values of a K block, double-buffered
+            float4 ecur[8], enxt[8];  // this thread's 4 x 8 encoder values of a K block, double-buffered
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                ecur[2 * i] = __ldg(erow + (kc0 + 4 * i) * 2);
-                ecur[2 * i + 1] = __ldg(erow + (kc0 + 4 * i) * 2 + 1);
+            for (int i = 0; i < 4; ++i) {
+                ecur[2 * i] = __ldg(erow + (kc0 + 2 * i) * 2);
+                ecur[2 * i + 1] = __ldg(erow + (kc0 + 2 * i) * 2 + 1);
             }
             for (int kb = 0; kb < n_slots; ++kb) {
                 if (kb + 1 < n_slots) {
 #pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        enxt[2 * i] = __ldg(erow + ((kb + 1) * kKB / 4) + (kc0 + 4 * i) * 2);
-                        enxt[2 * i + 1] = __ldg(erow + ((kb + 1) * kKB / 4) + (kc0 + 4 * i) * 2 + 1);
+                    for (int i = 0; i < 4; ++i) {
+                        enxt[2 * i] = __ldg(erow + ((kb + 1) * kKB / 4) + (kc0 + 2 * i) * 2);
+                        enxt[2 * i + 1] = __ldg(erow + ((kb + 1) * kKB / 4) + (kc0 + 2 * i) * 2 + 1);
                     }
                 }
                 
 #pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    const int kc = kc0 + 4 * i;
+                for (int i = 0; i < 4; ++i) {
+                    const int kc = kc0 + 2 * i;
                     const int k = kb * kKB + kc * 8;
                     const float4 e0 = ecur[2 * i], e1 = ecur[2 * i + 1];
                     const float4 d0 = *reinterpret_cast<const float4*>(drow + k);
@@ -206,7 +206,7 @@ at_grad_tc_kernel(const __grid_constant__ CUtensorMap w_map, const float* __rest
                     *reinterpret_cast<uint4*>(smem + L.z + kb * kASlotBytes + kc * kGroupBytes + r * 16) = out;
                 }
 #pragma unroll
-                for (int i = 0; i < 4; ++i) ecur[i] = enxt[i];
+                for (int i = 0; i < 8; ++i) ecur[i] = enxt[i];
                 fence_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
                 __syncwarp();
                 if (lane == 0) mbar_arrive(z_full(kb));
@@ -276,14 +276,16 @@ at_grad_tc_kernel(const __grid_constant__ CUtensorMap w_map, const float* __rest
                 // (3) dZ = G W, one 64-column piece per W K-block
                 for (int kb = 0; kb < n_slots; ++kb, ++wi, ++pi) {
                     const int st = wi % kWStages;
-                    mbar_wait(dz_empty, (pi & 1) ^ 1);
+                    const int buf = kb & 1;  // n_slots is even: buffer b sees pieces b, b+2, ...
+                    mbar_wait(dz_empty(buf), ((pi >> 1) & 1) ^ 1);
                     mbar_wait(w_full(st), (wi / kWStages) & 1);
                     tc_fence_after();
                     for (int j = 0; j < NB / 16; ++j)
-                        umma_bf16(tmem + kColDZ, umma_desc(g_base + j * 2 * kGroupBytes, kGroupBytes, 128),
+                        umma_bf16(tmem + (buf ? kColS : kColDZ),
+                                  umma_desc(g_base + j * 2 * kGroupBytes, kGroupBytes, 128),
                                   umma_desc(w_base + st * L.w_stage_bytes + j * 256, 128, w_sbo), id_dz, j != 0);
                     umma_commit(w_empty(st));
-                    umma_commit(dz_full);
+                    umma_commit(dz_full(buf));
                 }
                 // (4) d_enc^T | d_dec^T = dP^T R
                 mbar_wait(p_full, ph);
@@ -301,7 +303,11 @@ at_grad_tc_kernel(const __grid_constant__ CUtensorMap w_map, const float* __rest
             umma_commit(done);
         }
     } else {
-        // ===== epilogue: one lattice cell (TMEM lane) per thread =====
+        // ===== epilogue: one lattice cell (TMEM lane) per thread, two groups of four warps.  Both
+        // groups see all 128 cells; they split the work by columns: group g turns the vocabulary
+        // pieces pc = g, g+2, .. of S into G, owns dZ buffer g (pieces kb = g, g+2, ..), and moves the
+        // reduced tiles / accumulators of the row blocks mt = g, g+2, .. =====
+        const int grp = (warp - 10) >> 2;
         const int q = warp & 3;
         const int r = q * 32 + lane;
         const int tt = r / kUU, uu = r % kUU;
@@ -332,7 +338,7 @@ at_grad_tc_kernel(const __grid_constant__ CUtensorMap w_map, const float* __rest
             // (a) S -> G (bf16, [v-group][cell][8 v])
             mbar_wait(s_full, ph);
             tc_fence_after();
-            for (int pc = 0; pc < NB / 16; ++pc) {
+            for (int pc = grp; pc < NB / 16; pc += 2) {
                 float v[16];
                 tmem_ld16(tmem + kColS + pc * 16 + lane_sel, v);
 #pragma unroll
@@ -360,13 +366,13 @@ at_grad_tc_kernel(const __grid_constant__ CUtensorMap w_map, const float* __rest
             __syncwarp();
             if (lane == 0) mbar_arrive(g_full);
             // (c) dZ pieces -> dP = dZ * (1 - z^2), bf16, over z
-            for (int kb = 0; kb < n_slots; ++kb, ++pi) {
-                mbar_wait(dz_full, pi & 1);
+            for (int kb = grp; kb < n_slots; kb += 2, ++pi) {
+                mbar_wait(dz_full(grp), pi & 1);
                 tc_fence_after();
 #pragma unroll
                 for (int pc = 0; pc < 4; ++pc) {
                     float v[16];
-                    tmem_ld16(tmem + kColDZ + pc * 16 + lane_sel, v);
+                    tmem_ld16(tmem + (grp ? kColS : kColDZ) + pc * 16 + lane_sel, v);
 #pragma unroll
                     for (int hgrp = 0; hgrp < 2; ++hgrp) {
                         uint4* zp = reinterpret_cast<uint4*>(smem + L.z + kb * kASlotBytes +
@@ -385,7 +391,7 @@ at_grad_tc_kernel(const __grid_constant__ CUtensorMap w_map, const float* __rest
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(dz_empty);
+                if (lane == 0) mbar_arrive(dz_empty(grp));
             }
             fence_async_smem();
             __syncwarp();
@@ -393,7 +399,7 @@ at_grad_tc_kernel(const __grid_constant__ CUtensorMap w_map, const float* __rest
             // (d) reduced tiles: TMEM lane = h within the 128-row block, columns = frame / position
             mbar_wait(r_full, ph);
             tc_fence_after();
-            for (int mt = 0; mt < n_mt; ++mt) {
+            for (int mt = grp; mt < n_mt; mt += 2) {
                 float ve[16], vd[16];
                 tmem_ld16(tmem + kColRed + mt * 32 + lane_sel, ve);
                 tmem_ld16(tmem + kColRed + mt * 32 + 16 + lane_sel, vd);
@@ -414,7 +420,7 @@ at_grad_tc_kernel(const __grid_constant__ CUtensorMap w_map, const float* __rest
         if (n > 0) {
             mbar_wait(done, 0);
             tc_fence_after();
-            for (int mt = 0; mt < n_mt; ++mt)
+            for (int mt = grp; mt < n_mt; mt += 2)
                 for (int pc = 0; pc < NB / 16; ++pc) {
                     float v[16];
                     tmem_ld16(tmem + kColDW + mt * NB + pc * 16 + lane_sel, v);
@@ -424,9 +430,11 @@ at_grad_tc_kernel(const __grid_constant__ CUtensorMap w_map, const float* __rest
                         if (col < V) atomicAdd(d_w + (size_t)col * H + mt * 128 + r, v[i]);
                     }
                 }
-            float v[16];
-            tmem_ld16(tmem + kColDB + lane_sel, v);
-            if (r < V) atomicAdd(d_b + r, v[8]);  // column 8 = selector row 24 = all cells
+            if (grp == 0) {
+                float v[16];
+                tmem_ld16(tmem + kColDB + lane_sel, v);
+                if (r < V) atomicAdd(d_b + r, v[8]);  // column 8 = selector row 24 = all cells
+            }
         }
     }
 
