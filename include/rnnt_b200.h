@@ -136,13 +136,16 @@ RNNTB200_API int rnntb200_joint_cg_project(const float* enc, const float* dec, c
 
 /* Backward of rnntb200_joint_cg_project, same arithmetic: d_enc [rows_enc, He], d_dec [rows_dec, Hd],
  * d_weight [V, He+Hd] and d_bias [V] are fully overwritten.  Supported when the workspace query
- * returns > 0 (V <= 80; He, Hd multiples of 128, <= 512). */
+ * returns > 0 (V <= 80; He, Hd multiples of 128, <= 512).  workspace_holds_split != 0: `workspace`
+ * is the very buffer rnntb200_joint_cg_project filled for the same weight (same layout and size),
+ * so the bf16 split of the weight is not redone. */
 RNNTB200_API size_t rnntb200_joint_cg_project_bwd_workspace_bytes(int V, int He, int Hd);
 
 RNNTB200_API int rnntb200_joint_cg_project_bwd(const float* enc, const float* dec, const float* weight,
                                   const float* d_penc, const float* d_pdec, int rows_enc, int rows_dec,
                                   int He, int Hd, int V, float* d_enc, float* d_dec, float* d_weight,
-                                  float* d_bias, void* workspace, size_t workspace_bytes, void* stream);
+                                  float* d_bias, void* workspace, size_t workspace_bytes,
+                                  int workspace_holds_split, void* stream);
 
 RNNTB200_API int rnntb200_joint_cg_fwd(const float* penc, const float* pdec, const int32_t* labels,
                           const int32_t* act_lens, const int32_t* label_lens, int B, int T, int U1,

@@ -118,7 +118,7 @@ size_t proj_tc_bwd_workspace_bytes(int V, int He, int Hd);
 int launch_proj_tc_bwd(const float* enc, const float* dec, const float* weight, const float* d_penc,
                        const float* d_pdec, int rows_enc, int rows_dec, int He, int Hd, int V, float* d_enc,
                        float* d_dec, float* d_weight, float* d_bias, void* workspace, size_t workspace_bytes,
-                       cudaStream_t stream);
+                       int workspace_holds_split, cudaStream_t stream);
 int launch_proj_tc(const float* enc, const float* dec, const float* weight, const float* bias, int rows_enc,
                    int rows_dec, int He, int Hd, int V, float* penc, float* pdec, void* workspace,
                    size_t workspace_bytes, cudaStream_t stream);

@@ -63,15 +63,23 @@ __device__ __forceinline__ void split_store(float a, float b, uint32_t& hi, uint
     lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
-// W[:, col0 : col0 + K] (row stride ldw) -> bf16 hi and lo copies, [V, K] dense
-__global__ void split_weight_kernel(const float* __restrict__ w, int ldw, int col0, int V, int K,
-                                    __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < V * K; i += gridDim.x * blockDim.x) {
-        const int v = i / K, k = i - v * K;
-        const float x = w[(size_t)v * ldw + col0 + k];
+// fc.weight [V, He+Hd] -> dense bf16 hi / lo copies of both column slices ([V, He] and [V, Hd])
+__global__ void split_weight_kernel(const float* __restrict__ w, int V, int He, int Hd,
+                                    __nv_bfloat16* __restrict__ e_hi, __nv_bfloat16* __restrict__ e_lo,
+                                    __nv_bfloat16* __restrict__ d_hi, __nv_bfloat16* __restrict__ d_lo) {
+    const int ldw = He + Hd;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < V * ldw; i += gridDim.x * blockDim.x) {
+        const int v = i / ldw, k = i - v * ldw;
+        const float x = w[i];
         const __nv_bfloat16 h = __float2bfloat16_rn(x);
-        hi[i] = h;
-        lo[i] = __float2bfloat16_rn(x - __bfloat162float(h));
+        const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+        if (k < He) {
+            e_hi[v * He + k] = h;
+            e_lo[v * He + k] = l;
+        } else {
+            d_hi[v * Hd + k - He] = h;
+            d_lo[v * Hd + k - He] = l;
+        }
     }
 }
 
@@ -260,32 +268,41 @@ size_t proj_tc_workspace_bytes(int V, int He, int Hd) {
     return 2 * align256((size_t)V * He * 2) + 2 * align256((size_t)V * Hd * 2);
 }
 
-int launch_proj_tc(const float* enc, const float* dec, const float* weight, const float* bias, int rows_enc,
-                   int rows_dec, int He, int Hd, int V, float* penc, float* pdec, void* workspace,
-                   size_t workspace_bytes, cudaStream_t stream) {
-    if (!proj_tc_supported(V, He, Hd)) return RNNTB200_STATUS_INVALID_VALUE;
+// Splits the weight into the workspace (unless the caller says it already holds this weight's
+// split, e.g. the backward reusing the forward's workspace) and builds the four TMA descriptors.
+int proj_tc_prepare(const float* weight, int V, int He, int Hd, int NB, void* workspace, size_t workspace_bytes,
+                    bool already_split, CUtensorMap maps[4], cudaStream_t stream) {
     if (!workspace || workspace_bytes < proj_tc_workspace_bytes(V, He, Hd) || ((uintptr_t)workspace & 15))
         return RNNTB200_STATUS_INVALID_VALUE;
-    if (rows_enc + rows_dec == 0) return RNNTB200_STATUS_SUCCESS;
-    const int NB = ((V + 15) / 16) * 16;
     unsigned char* ws = static_cast<unsigned char*>(workspace);
     __nv_bfloat16* e_hi = reinterpret_cast<__nv_bfloat16*>(ws);
     __nv_bfloat16* e_lo = reinterpret_cast<__nv_bfloat16*>(ws + align256((size_t)V * He * 2));
     __nv_bfloat16* d_hi = reinterpret_cast<__nv_bfloat16*>(ws + 2 * align256((size_t)V * He * 2));
     __nv_bfloat16* d_lo = reinterpret_cast<__nv_bfloat16*>(ws + 2 * align256((size_t)V * He * 2) + align256((size_t)V * Hd * 2));
-    const int ldw = He + Hd;
-    split_weight_kernel<<<std::min((V * He + 255) / 256, 592), 256, 0, stream>>>(weight, ldw, 0, V, He, e_hi, e_lo);
-    split_weight_kernel<<<std::min((V * Hd + 255) / 256, 592), 256, 0, stream>>>(weight, ldw, He, V, Hd, d_hi, d_lo);
-    CUtensorMap m0h, m0l, m1h, m1l;
-    if (!make_w_map(&m0h, e_hi, V, He, NB) || !make_w_map(&m0l, e_lo, V, He, NB) ||
-        !make_w_map(&m1h, d_hi, V, Hd, NB) || !make_w_map(&m1l, d_lo, V, Hd, NB))
+    if (!already_split)
+        split_weight_kernel<<<std::min((V * (He + Hd) + 255) / 256, 592), 256, 0, stream>>>(weight, V, He, Hd, e_hi,
+                                                                                           e_lo, d_hi, d_lo);
+    if (!make_w_map(&maps[0], e_hi, V, He, NB) || !make_w_map(&maps[1], e_lo, V, He, NB) ||
+        !make_w_map(&maps[2], d_hi, V, Hd, NB) || !make_w_map(&maps[3], d_lo, V, Hd, NB))
         return RNNTB200_STATUS_EXECUTION_FAILED;
+    return launch_status();
+}
+
+int launch_proj_tc(const float* enc, const float* dec, const float* weight, const float* bias, int rows_enc,
+                   int rows_dec, int He, int Hd, int V, float* penc, float* pdec, void* workspace,
+                   size_t workspace_bytes, cudaStream_t stream) {
+    if (!proj_tc_supported(V, He, Hd)) return RNNTB200_STATUS_INVALID_VALUE;
+    const int NB = ((V + 15) / 16) * 16;
+    CUtensorMap m[4];
+    int st = proj_tc_prepare(weight, V, He, Hd, NB, workspace, workspace_bytes, false, m, stream);
+    if (st != RNNTB200_STATUS_SUCCESS) return st;
+    if (rows_enc + rows_dec == 0) return RNNTB200_STATUS_SUCCESS;
     Problem p0{enc, bias, penc, rows_enc, He, (rows_enc + 127) / 128};
     Problem p1{dec, nullptr, pdec, rows_dec, Hd, (rows_dec + 127) / 128};
     const SmemP L = smem_layout_p(NB);
     cudaError_t e = cudaFuncSetAttribute(proj_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
     if (e != cudaSuccess) return status_from_cuda(e);
-    proj_tc_kernel<<<p0.tiles + p1.tiles, kThreads, L.total, stream>>>(m0h, m0l, m1h, m1l, p0, p1, V, NB);
+    proj_tc_kernel<<<p0.tiles + p1.tiles, kThreads, L.total, stream>>>(m[0], m[1], m[2], m[3], p0, p1, V, NB);
     return launch_status();
 }
 

@@ -68,17 +68,6 @@ __device__ __forceinline__ float gelu_grad(float x) {
     return fmaf(x * s * (1.f - s), dy2, s);
 }
 
-__global__ void split_weight_kernel_b(const float* __restrict__ w, int ldw, int col0, int V, int K,
-                                      __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < V * K; i += gridDim.x * blockDim.x) {
-        const int v = i / K, k = i - v * K;
-        const float x = w[(size_t)v * ldw + col0 + k];
-        const __nv_bfloat16 h = __float2bfloat16_rn(x);
-        hi[i] = h;
-        lo[i] = __float2bfloat16_rn(x - __bfloat162float(h));
-    }
-}
-
 __global__ void __launch_bounds__(kThreads, 1)
 proj_tc_bwd_kernel(const __grid_constant__ CUtensorMap w0_hi, const __grid_constant__ CUtensorMap w0_lo,
                    const __grid_constant__ CUtensorMap w1_hi, const __grid_constant__ CUtensorMap w1_lo,
@@ -310,50 +299,39 @@ proj_tc_bwd_kernel(const __grid_constant__ CUtensorMap w0_hi, const __grid_const
     }
 }
 
-inline size_t align256b(size_t x) { return (x + 255) & ~(size_t)255; }
-
 }  // namespace
 
-bool make_w_map(CUtensorMap* map, void* w, int V, int K, int NB);  // proj_tc.cu
+// proj_tc.cu
+size_t proj_tc_workspace_bytes(int V, int He, int Hd);
+int proj_tc_prepare(const float* weight, int V, int He, int Hd, int NB, void* workspace, size_t workspace_bytes,
+                    bool already_split, CUtensorMap maps[4], cudaStream_t stream);
 
 bool proj_tc_bwd_supported(int V, int He, int Hd) {
     return V >= 1 && V <= 80 && He >= 128 && Hd >= 128 && He % 128 == 0 && Hd % 128 == 0 && He <= 512 && Hd <= 512;
 }
 
-size_t proj_tc_bwd_workspace_bytes(int V, int He, int Hd) {
-    return 2 * align256b((size_t)V * He * 2) + 2 * align256b((size_t)V * Hd * 2);
-}
+size_t proj_tc_bwd_workspace_bytes(int V, int He, int Hd) { return proj_tc_workspace_bytes(V, He, Hd); }
 
 int launch_proj_tc_bwd(const float* enc, const float* dec, const float* weight, const float* d_penc,
                        const float* d_pdec, int rows_enc, int rows_dec, int He, int Hd, int V, float* d_enc,
                        float* d_dec, float* d_weight, float* d_bias, void* workspace, size_t workspace_bytes,
-                       cudaStream_t stream) {
+                       int workspace_holds_split, cudaStream_t stream) {
     if (!proj_tc_bwd_supported(V, He, Hd)) return RNNTB200_STATUS_INVALID_VALUE;
-    if (!workspace || workspace_bytes < proj_tc_bwd_workspace_bytes(V, He, Hd) || ((uintptr_t)workspace & 15))
-        return RNNTB200_STATUS_INVALID_VALUE;
     const int ldw = He + Hd;
     if (cudaMemsetAsync(d_weight, 0, (size_t)V * ldw * sizeof(float), stream) != cudaSuccess ||
         cudaMemsetAsync(d_bias, 0, (size_t)V * sizeof(float), stream) != cudaSuccess)
         return RNNTB200_STATUS_MEMOPS_FAILED;
-    if (rows_enc + rows_dec == 0) return RNNTB200_STATUS_SUCCESS;
     const int NB = ((V + 15) / 16) * 16;
-    unsigned char* ws = static_cast<unsigned char*>(workspace);
-    __nv_bfloat16* e_hi = reinterpret_cast<__nv_bfloat16*>(ws);
-    __nv_bfloat16* e_lo = reinterpret_cast<__nv_bfloat16*>(ws + align256b((size_t)V * He * 2));
-    __nv_bfloat16* d_hi = reinterpret_cast<__nv_bfloat16*>(ws + 2 * align256b((size_t)V * He * 2));
-    __nv_bfloat16* d_lo = reinterpret_cast<__nv_bfloat16*>(ws + 2 * align256b((size_t)V * He * 2) + align256b((size_t)V * Hd * 2));
-    split_weight_kernel_b<<<std::min((V * He + 255) / 256, 592), 256, 0, stream>>>(weight, ldw, 0, V, He, e_hi, e_lo);
-    split_weight_kernel_b<<<std::min((V * Hd + 255) / 256, 592), 256, 0, stream>>>(weight, ldw, He, V, Hd, d_hi, d_lo);
-    CUtensorMap m0h, m0l, m1h, m1l;
-    if (!make_w_map(&m0h, e_hi, V, He, NB) || !make_w_map(&m0l, e_lo, V, He, NB) ||
-        !make_w_map(&m1h, d_hi, V, Hd, NB) || !make_w_map(&m1l, d_lo, V, Hd, NB))
-        return RNNTB200_STATUS_EXECUTION_FAILED;
+    CUtensorMap m[4];
+    int st = proj_tc_prepare(weight, V, He, Hd, NB, workspace, workspace_bytes, workspace_holds_split != 0, m, stream);
+    if (st != RNNTB200_STATUS_SUCCESS) return st;
+    if (rows_enc + rows_dec == 0) return RNNTB200_STATUS_SUCCESS;
     ProblemB p0{enc, d_penc, d_enc, rows_enc, He, (rows_enc + 127) / 128, 0, 1};
     ProblemB p1{dec, d_pdec, d_dec, rows_dec, Hd, (rows_dec + 127) / 128, He, 0};
     const SmemPB L = smem_layout_pb(NB);
     cudaError_t e = cudaFuncSetAttribute(proj_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
     if (e != cudaSuccess) return status_from_cuda(e);
-    proj_tc_bwd_kernel<<<p0.tiles + p1.tiles, kThreads, L.total, stream>>>(m0h, m0l, m1h, m1l, p0, p1, V, NB,
+    proj_tc_bwd_kernel<<<p0.tiles + p1.tiles, kThreads, L.total, stream>>>(m[0], m[1], m[2], m[3], p0, p1, V, NB,
                                                                            d_weight, ldw, d_bias);
     return launch_status();
 }

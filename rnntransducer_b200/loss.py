@@ -171,12 +171,12 @@ class _CgProject(torch.autograd.Function):
             _lib.check(lib.rnntb200_joint_cg_project(
                 _ptr(enc), _ptr(dec), _ptr(weight), _ptr(bias), B * T, B * U1, He, Hd, V, _ptr(penc),
                 _ptr(pdec), _ptr(ws), ws_bytes, _stream()), "rnntb200_joint_cg_project")
-        ctx.save_for_backward(enc, dec, weight)
+        ctx.save_for_backward(enc, dec, weight, ws)  # ws: the weight's bf16 hi/lo split, reused by backward
         return penc, pdec
 
     @staticmethod
     def backward(ctx, d_penc, d_pdec):
-        enc, dec, weight = ctx.saved_tensors
+        enc, dec, weight, ws_fwd = ctx.saved_tensors
         He, Hd = enc.shape[-1], dec.shape[-1]
         V = weight.shape[0]
         lib = _lib.load()
@@ -185,12 +185,13 @@ class _CgProject(torch.autograd.Function):
             d_penc, d_pdec = d_penc.contiguous().float(), d_pdec.contiguous().float()
             d_enc, d_dec = torch.empty_like(enc), torch.empty_like(dec)
             d_w, d_b = torch.empty_like(weight), torch.empty(V, device=enc.device, dtype=torch.float32)
-            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=enc.device)
+            reuse = ws_fwd.numel() >= ws_bytes
+            ws = ws_fwd if reuse else torch.empty(ws_bytes, dtype=torch.uint8, device=enc.device)
             with torch.cuda.device(enc.device):
                 _lib.check(lib.rnntb200_joint_cg_project_bwd(
                     _ptr(enc), _ptr(dec), _ptr(weight), _ptr(d_penc), _ptr(d_pdec), enc.shape[0] * enc.shape[1],
                     dec.shape[0] * dec.shape[1], He, Hd, V, _ptr(d_enc), _ptr(d_dec), _ptr(d_w), _ptr(d_b),
-                    _ptr(ws), ws_bytes, _stream()), "rnntb200_joint_cg_project_bwd")
+                    _ptr(ws), ws_bytes, int(reuse), _stream()), "rnntb200_joint_cg_project_bwd")
             return d_enc, d_dec, d_w, d_b
         gelu = lambda x: torch.nn.functional.gelu(x, approximate="tanh")
         dpe, dpd = d_penc.reshape(-1, V), d_pdec.reshape(-1, V)
