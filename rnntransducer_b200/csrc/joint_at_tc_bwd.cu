@@ -21,8 +21,8 @@
 // atomics).  mbarrier-only synchronisation.  TMEM map (512 columns): dW^T [0,320) | S [320,400) |
 // dZ pieces [400,464) and [320,384) (the second aliases S, dead by then) | d_enc^T/d_dec^T [320,448) (aliases S and dZ, both dead by then) | db [464,480).
 //
-// Supported: V <= 80 (one vocabulary chunk; KsponSpeech has 73), H a multiple of 128, H <= 512.
-// Other shapes use the CUDA-core kernel in joint_at.cu.
+// Supported: H a multiple of 128, H <= 512; any V (one launch per chunk of 80 vocabulary columns;
+// KsponSpeech's 73 is a single pass).  Other shapes use the CUDA-core kernel in joint_at.cu.
 #include <algorithm>
 
 #include "tc_common.cuh"
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 at_grad_tc_kernel(const __grid_constant__ CUtensorMap w_map, const float* __restrict__ enc,
                   const float* __restrict__ dec, const float* __restrict__ bias,
                   const int32_t* __restrict__ labels, const int32_t* __restrict__ act_lens,
-                  const int32_t* __restrict__ label_lens, int B, int T, int U1, int V, int H, int NB,
+                  const int32_t* __restrict__ label_lens, int B, int T, int U1, int V, int H, int NB, int v0,
                   int blank, const float2* __restrict__ lp2, const float* __restrict__ lse,
                   const int32_t* __restrict__ alpha, const int32_t* __restrict__ beta,
                   const float* __restrict__ grad_costs, float* __restrict__ d_enc,
@@ -225,7 +225,7 @@ at_grad_tc_kernel(const __grid_constant__ CUtensorMap w_map, const float* __rest
                         const int st = wi % kWStages;
                         mbar_wait(w_empty(st), ((wi / kWStages) & 1) ^ 1);
                         mbar_arrive_expect_tx(w_full(st), (uint32_t)L.w_stage_bytes);
-                        tma_load_3d(w_base + st * L.w_stage_bytes, &w_map, 0, 0, kb * (kKB / 8), w_full(st));
+                        tma_load_3d(w_base + st * L.w_stage_bytes, &w_map, 0, v0, kb * (kKB / 8), w_full(st));
                     }
             }
         }
@@ -343,7 +343,7 @@ at_grad_tc_kernel(const __grid_constant__ CUtensorMap w_map, const float* __rest
                 tmem_ld16(tmem + kColS + pc * 16 + lane_sel, v);
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    const int col = pc * 16 + i;
+                    const int col = v0 + pc * 16 + i;  // vocabulary column of this launch's chunk
                     float g = 0.f;
                     if (col < V) {
                         g = fast_ex2(fmaf(v[i], kLog2e, __ldg(bias + col) * kLog2e) + c_all);
@@ -426,14 +426,14 @@ at_grad_tc_kernel(const __grid_constant__ CUtensorMap w_map, const float* __rest
                     tmem_ld16(tmem + kColDW + mt * NB + pc * 16 + lane_sel, v);
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        const int col = pc * 16 + i;
+                        const int col = v0 + pc * 16 + i;
                         if (col < V) atomicAdd(d_w + (size_t)col * H + mt * 128 + r, v[i]);
                     }
                 }
             if (grp == 0) {
                 float v[16];
                 tmem_ld16(tmem + kColDB + lane_sel, v);
-                if (r < V) atomicAdd(d_b + r, v[8]);  // column 8 = selector row 24 = all cells
+                if (r < NB && v0 + r < V) atomicAdd(d_b + v0 + r, v[8]);  // column 8 = selector row 24 = all cells
             }
         }
     }
@@ -452,7 +452,7 @@ at_grad_tc_kernel(const __grid_constant__ CUtensorMap w_map, const float* __rest
 int at_tc_prepare_weight(const float* weight, int V, int H, int NB, void* workspace, size_t workspace_bytes,
                          CUtensorMap* map, cudaStream_t stream);
 
-bool at_tc_bwd_supported(int V, int H) { return V >= 1 && V <= 80 && H >= 128 && H % 128 == 0 && H <= 512; }
+bool at_tc_bwd_supported(int V, int H) { return V >= 1 && H >= 128 && H % 128 == 0 && H <= 512; }
 
 int launch_at_grad_tc(const float* enc, const float* dec, const float* weight, const float* bias,
                       const int32_t* labels, const int32_t* act_lens, const int32_t* label_lens, int B, int T,
@@ -460,7 +460,10 @@ int launch_at_grad_tc(const float* enc, const float* dec, const float* weight, c
                       const int32_t* beta, const float* grad_costs, float* d_enc, float* d_dec, float* d_weight,
                       float* d_bias, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
     if (!at_tc_bwd_supported(V, H)) return RNNTB200_STATUS_INVALID_VALUE;
-    const int NB = ((V + 15) / 16) * 16;
+    // Vocabularies beyond 80 columns run one pass per chunk of 80: the softmax is normalised by the
+    // saved log-sum-exp, so every chunk's G, dW rows and its share of dZ are independent; d_enc and
+    // d_dec simply accumulate over the passes (z is recomputed per pass).
+    const int NB = std::min(((V + 15) / 16) * 16, 80);
     CUtensorMap map;
     int st = at_tc_prepare_weight(weight, V, H, NB, workspace, workspace_bytes, &map, stream);
     if (st != RNNTB200_STATUS_SUCCESS) return st;
@@ -471,10 +474,13 @@ int launch_at_grad_tc(const float* enc, const float* dec, const float* weight, c
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int n_tiles = B * ((T + kTT - 1) / kTT) * ((U1 + kUU - 1) / kUU);
-    at_grad_tc_kernel<<<std::min(n_tiles, sms), kThreads, L.total, stream>>>(
-        map, enc, dec, bias, labels, act_lens, label_lens, B, T, U1, V, H, NB, blank, lp2, lse, alpha, beta,
-        grad_costs, d_enc, d_dec, d_weight, d_bias);
-    return launch_status();
+    for (int v0 = 0; v0 < V; v0 += NB) {
+        at_grad_tc_kernel<<<std::min(n_tiles, sms), kThreads, L.total, stream>>>(
+            map, enc, dec, bias, labels, act_lens, label_lens, B, T, U1, V, H, NB, v0, blank, lp2, lse, alpha, beta,
+            grad_costs, d_enc, d_dec, d_weight, d_bias);
+        if ((st = launch_status()) != RNNTB200_STATUS_SUCCESS) return st;
+    }
+    return RNNTB200_STATUS_SUCCESS;
 }
 
 }  // namespace rnntb200
