@@ -98,11 +98,41 @@ __device__ __forceinline__ void cp_async_wait() {
 // There is no special-casing of the lattice borders inside the loop: the ring starts zeroed
 // (log-prob 0 = factor 1) and every absent term is the "zero" (1, kZeroExp), which loses every
 // addition, so a thread that has not reached its first cell yet just carries zeros along.
-template <int DIR, bool kMultiWarp>
+__device__ __forceinline__ unsigned cluster_ctarank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ unsigned cluster_nctarank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_barrier() {  // release / acquire at cluster scope
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// store {x, y} at the same shared-memory offset in CTA `rank` of the cluster (DSMEM)
+__device__ __forceinline__ void st_cluster_v2(const void* local_smem, unsigned rank, int x, int y) {
+    unsigned laddr = (unsigned)__cvta_generic_to_shared(local_smem), raddr;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(laddr), "r"(rank));
+    asm volatile("st.shared::cluster.v2.u32 [%0], {%1, %2};" ::"r"(raddr), "r"(x), "r"(y) : "memory");
+}
+
+// kMode 0: one warp.  1: several warps of one CTA (block barrier every kLag diagonals).
+// 2: the warps of one sweep are spread over a thread-block cluster (<= 4 warps per CTA, <= 8 CTAs):
+//    a long label sequence (U1 = 301 is ten warps) then issues from several SMs instead of
+//    queueing on the four schedulers of one.  The warp-boundary value crosses CTAs through
+//    distributed shared memory (written into the consumer's ring) and the barrier is the cluster's;
+//    the kLag-diagonal skew between consecutive warps hides the DSMEM latency.
+template <int DIR, int kMode>
 __device__ __forceinline__ void sweep(const float2* __restrict__ lp2, int Tb, int Ub, int T, int U1, int b,
                                       int32_t* __restrict__ out, float* __restrict__ costs,
                                       float* __restrict__ ll_alpha, float2* ring, int2 (*edge)[33]) {
-    const int j = threadIdx.x;  // position along the sweep
+    constexpr bool kMultiWarp = kMode != 0;
+    const unsigned rank = kMode == 2 ? cluster_ctarank() : 0, n_rank = kMode == 2 ? cluster_nctarank() : 1;
+    const int wl = threadIdx.x >> 5, wpc = blockDim.x >> 5;  // warp within the CTA, warps per CTA
+    const int j = rank * blockDim.x + threadIdx.x;            // position along the sweep
     const int lane = j & 31, warp = j >> 5;
     const int U1b = Ub + 1;
     const bool lane_on = j < U1b;
@@ -121,15 +151,17 @@ __device__ __forceinline__ void sweep(const float2* __restrict__ lp2, int Tb, in
     const float2* src = lp2 + first;    // + off : cell consumed at the current step
     const float2* src_pf = src + (long long)(kDepth - 1) * stride;  // + off : cell being prefetched
     int32_t* dst = out + first;
-    float2* cur = ring + (size_t)j * kRingStride;  // ring half of steps s0 .. s0+7
-    float2* oth = cur + kUnroll;                   // ring half of the next 8 steps
-    const int edge_col = (kMultiWarp && warp > 0) ? warp - 1 : 32;  // column 32 always holds zero
+    float2* cur = ring + (size_t)threadIdx.x * kRingStride;  // ring half of steps s0 .. s0+7
+    float2* oth = cur + kUnroll;                             // ring half of the next 8 steps
+    // where lane 0 finds its neighbour's value: column wl-1 (written by the previous warp of this
+    // CTA), column 31 (written through DSMEM by the last warp of the previous CTA), or column 32 (zero)
+    const int edge_col = !kMultiWarp ? 32 : wl > 0 ? wl - 1 : rank > 0 ? 31 : 32;
 
     // zero ring (factor 1 for steps without a cell), "zero" edge values
 #pragma unroll
     for (int k = 0; k < kDepth; ++k) cur[k] = make_float2(0.f, 0.f);
     if (kMultiWarp)
-        for (int i = j; i < kEdgeRing * 33; i += blockDim.x) edge[i / 33][i % 33] = make_int2(0x3f800000, kZeroExp);
+        for (int i = threadIdx.x; i < kEdgeRing * 33; i += blockDim.x) edge[i / 33][i % 33] = make_int2(0x3f800000, kZeroExp);
 
     // prologue: cells of steps 0 .. kDepth-2 (slot of step s = s mod 16: cur[0..7], oth[0..6])
 #pragma unroll
@@ -152,7 +184,9 @@ __device__ __forceinline__ void sweep(const float2* __restrict__ lp2, int Tb, in
 
 #pragma unroll 1
     for (int s0 = 0; s0 < S; s0 += kUnroll) {
-        if (kMultiWarp) __syncthreads();  // kLag == kUnroll: one barrier per 8 diagonals
+        // kLag == kUnroll: one barrier per 8 diagonals
+        if (kMode == 1) __syncthreads();
+        if (kMode == 2) cluster_barrier();
 #pragma unroll
         for (int k = 0; k < kUnroll; ++k) {
             // hand-off from the u-1 neighbour (its value on diagonal d-1)
@@ -184,7 +218,10 @@ __device__ __forceinline__ void sweep(const float2* __restrict__ lp2, int Tb, in
             if (tau == t_last) last = DIR == 0 ? own : val;  // terminal cell (t_last = -1 elsewhere)
             if (kMultiWarp) {
                 es = (es + 1) & (kEdgeRing - 1);  // now the slot of diagonal d
-                if (lane == 31) edge[es][warp] = make_int2(__float_as_int(share.m), share.e);
+                if (lane == 31) {
+                    if (kMode == 1 || wl < wpc - 1) edge[es][wl] = make_int2(__float_as_int(share.m), share.e);
+                    else if (rank + 1 < n_rank) st_cluster_v2(&edge[es][31], rank + 1, __float_as_int(share.m), share.e);
+                }
             }
             pb = pbn;
             pl = pln;
@@ -196,6 +233,7 @@ __device__ __forceinline__ void sweep(const float2* __restrict__ lp2, int Tb, in
         oth = tmp;
     }
     cp_async_wait<0>();
+    if (kMode == 2) cluster_barrier();  // no CTA may exit while a neighbour can still write into its ring
     if (t_last >= 0) {
         if (DIR == 0) {
             if (ll_alpha) ll_alpha[b] = (float)me_ln(me_normalize(last));
@@ -205,8 +243,8 @@ __device__ __forceinline__ void sweep(const float2* __restrict__ lp2, int Tb, in
     }
 }
 
-template <bool kMultiWarp>
-__global__ void __launch_bounds__(1024, 1)
+template <int kMode>
+__global__ void __launch_bounds__(kMode == 2 ? 128 : 1024, 1)
 lattice_sweep_kernel(const float2* __restrict__ lp2, const int32_t* __restrict__ act_lens,
                      const int32_t* __restrict__ label_lens, int T, int U1,
                      int32_t* __restrict__ alpha, int32_t* __restrict__ beta,
@@ -214,13 +252,13 @@ lattice_sweep_kernel(const float2* __restrict__ lp2, const int32_t* __restrict__
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* ring = reinterpret_cast<float2*>(smem_raw);  // [blockDim.x][kRingStride]
     __shared__ int2 edge[kEdgeRing][33];
-    const int b = blockIdx.x;
+    const int b = kMode == 2 ? blockIdx.x / cluster_nctarank() : blockIdx.x;
     const int Tb = min(max(act_lens[b], 1), T);
     const int Ub = min(max(label_lens[b], 0), U1 - 1);
     if (blockIdx.y == 0)
-        sweep<0, kMultiWarp>(lp2, Tb, Ub, T, U1, b, alpha, costs, ll_alpha, ring, edge);
+        sweep<0, kMode>(lp2, Tb, Ub, T, U1, b, alpha, costs, ll_alpha, ring, edge);
     else
-        sweep<1, kMultiWarp>(lp2, Tb, Ub, T, U1, b, beta, costs, ll_alpha, ring, edge);
+        sweep<1, kMode>(lp2, Tb, Ub, T, U1, b, beta, costs, ll_alpha, ring, edge);
 }
 
 }  // namespace
@@ -230,21 +268,37 @@ int launch_lattice_sweep(const float2* lp2, const int32_t* act_lens, const int32
                          cudaStream_t stream) {
     if (B == 0) return RNNTB200_STATUS_SUCCESS;
     if (U1 > 1024) return RNNTB200_STATUS_INVALID_VALUE;
-    const int threads = ((U1 + 31) / 32) * 32;
-    const size_t smem = (size_t)kRingStride * threads * sizeof(float2);  // <= 136 KiB at U1 = 1024
-    dim3 grid(B, 2);
-    if (threads <= 32) {
-        lattice_sweep_kernel<false><<<grid, threads, smem, stream>>>(lp2, act_lens, label_lens, T, U1,
-                                                                      alpha, beta, costs, ll_alpha);
-    } else {
-        // static (edge ring, 8 KiB) + dynamic may exceed the 48 KiB default: always opt in
-        cudaError_t e = cudaFuncSetAttribute(lattice_sweep_kernel<true>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return status_from_cuda(e);
-        lattice_sweep_kernel<true><<<grid, threads, smem, stream>>>(lp2, act_lens, label_lens, T, U1,
-                                                                     alpha, beta, costs, ll_alpha);
+    const int warps = (U1 + 31) / 32;
+    if (warps == 1) {
+        const size_t smem = (size_t)kRingStride * 32 * sizeof(float2);
+        lattice_sweep_kernel<0><<<dim3(B, 2), 32, smem, stream>>>(lp2, act_lens, label_lens, T, U1, alpha, beta,
+                                                                  costs, ll_alpha);
+        return launch_status();
     }
-    return launch_status();
+    if (warps <= 4) {  // one CTA: its warps sit on different schedulers of one SM
+        const size_t smem = (size_t)kRingStride * warps * 32 * sizeof(float2);
+        lattice_sweep_kernel<1><<<dim3(B, 2), warps * 32, smem, stream>>>(lp2, act_lens, label_lens, T, U1, alpha,
+                                                                          beta, costs, ll_alpha);
+        return launch_status();
+    }
+    // longer label sequences: spread the sweep over a cluster, <= 4 warps per CTA, <= 8 CTAs
+    const int wpc = (warps + 7) / 8, cs = (warps + wpc - 1) / wpc;
+    const size_t smem = (size_t)kRingStride * wpc * 32 * sizeof(float2);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(B * cs), 2);
+    cfg.blockDim = dim3((unsigned)(wpc * 32));
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, lattice_sweep_kernel<2>, lp2, act_lens, label_lens, T, U1, alpha, beta,
+                                       costs, ll_alpha);
+    return e == cudaSuccess ? launch_status() : status_from_cuda(e);
 }
 
 }  // namespace rnntb200
