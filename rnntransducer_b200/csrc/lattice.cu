@@ -39,6 +39,8 @@ constexpr int kUnroll = 8;        // steps per loop body = half a ring = kLag
 constexpr int kRingStride = 17;   // float2 slots per thread (+1 pad: conflict-free 8-byte accesses)
 constexpr int kLag = 8;           // diagonals warp w trails warp w-1
 constexpr int kEdgeRing = 32;     // >= 2*kLag + 1 slots for warp-boundary values
+constexpr int kLagX = 32;         // diagonals the first warp of a CTA trails the last warp of the previous CTA
+constexpr int kEdgeRingX = 128;   // >= 2*kLagX + 1 slots for the value crossing CTAs (cluster mode)
 constexpr int kZeroExp = -(1 << 29);  // (1, kZeroExp) stands for 0: it never wins an addition
 
 struct ME {  // value = m * 2^e; m in [1,2) after normalize(), in [0.7, 5.7) before
@@ -128,7 +130,7 @@ __device__ __forceinline__ void st_cluster_v2(const void* local_smem, unsigned r
 template <int DIR, int kMode>
 __device__ __forceinline__ void sweep(const float2* __restrict__ lp2, int Tb, int Ub, int T, int U1, int b,
                                       int32_t* __restrict__ out, float* __restrict__ costs,
-                                      float* __restrict__ ll_alpha, float2* ring, int2 (*edge)[33]) {
+                                      float* __restrict__ ll_alpha, float2* ring, int2 (*edge)[33], int2* xedge) {
     constexpr bool kMultiWarp = kMode != 0;
     const unsigned rank = kMode == 2 ? cluster_ctarank() : 0, n_rank = kMode == 2 ? cluster_nctarank() : 1;
     const int wl = threadIdx.x >> 5, wpc = blockDim.x >> 5;  // warp within the CTA, warps per CTA
@@ -138,10 +140,15 @@ __device__ __forceinline__ void sweep(const float2* __restrict__ lp2, int Tb, in
     const bool lane_on = j < U1b;
     const unsigned Tb_eff = lane_on ? Tb : 0;  // (unsigned)tau < Tb_eff  <=>  this thread has a cell
     const int u = DIR == 0 ? j : Ub - j;
-    const int lag = kMultiWarp ? warp * kLag : 0;
+    // consecutive warps of a CTA run kLag diagonals apart (block barrier every kLag steps); across a
+    // CTA boundary the skew is kLagX and the (expensive) cluster barrier comes every kLagX steps
+    const int lag = !kMultiWarp ? 0 : warp * kLag + (kMode == 2 ? (int)rank * (kLagX - kLag) : 0);
     const int n_warps_on = (U1b + 31) >> 5;
-    // every warp runs the same number of steps (uniform barriers), rounded up to the unroll
-    const int S = (Tb + Ub + (kMultiWarp ? (n_warps_on - 1) * kLag : 0) + kUnroll - 1) / kUnroll * kUnroll;
+    const int max_lag = !kMultiWarp ? 0
+                        : (n_warps_on - 1) * kLag + (kMode == 2 ? ((n_warps_on - 1) / wpc) * (kLagX - kLag) : 0);
+    // every warp runs the same number of steps (uniform barriers), rounded up to the barrier period
+    const int round_to = kMode == 2 ? kLagX : kUnroll;
+    const int S = (Tb + Ub + max_lag + round_to - 1) / round_to * round_to;
 
     // this thread's cell at progress tau: row t = tau (alpha) or T_b-1-tau (beta)
     const int stride = DIR == 0 ? U1 : -U1;
@@ -154,14 +161,17 @@ __device__ __forceinline__ void sweep(const float2* __restrict__ lp2, int Tb, in
     float2* cur = ring + (size_t)threadIdx.x * kRingStride;  // ring half of steps s0 .. s0+7
     float2* oth = cur + kUnroll;                             // ring half of the next 8 steps
     // where lane 0 finds its neighbour's value: column wl-1 (written by the previous warp of this
-    // CTA), column 31 (written through DSMEM by the last warp of the previous CTA), or column 32 (zero)
-    const int edge_col = !kMultiWarp ? 32 : wl > 0 ? wl - 1 : rank > 0 ? 31 : 32;
+    // CTA), the xedge ring (written through DSMEM by the last warp of the previous CTA), or column 32 (zero)
+    const int edge_col = !kMultiWarp ? 32 : wl > 0 ? wl - 1 : 32;
+    const bool from_x = kMode == 2 && wl == 0 && rank > 0;
 
     // zero ring (factor 1 for steps without a cell), "zero" edge values
 #pragma unroll
     for (int k = 0; k < kDepth; ++k) cur[k] = make_float2(0.f, 0.f);
     if (kMultiWarp)
         for (int i = threadIdx.x; i < kEdgeRing * 33; i += blockDim.x) edge[i / 33][i % 33] = make_int2(0x3f800000, kZeroExp);
+    if (kMode == 2)
+        for (int i = threadIdx.x; i < kEdgeRingX; i += blockDim.x) xedge[i] = make_int2(0x3f800000, kZeroExp);
 
     // prologue: cells of steps 0 .. kDepth-2 (slot of step s = s mod 16: cur[0..7], oth[0..6])
 #pragma unroll
@@ -170,6 +180,7 @@ __device__ __forceinline__ void sweep(const float2* __restrict__ lp2, int Tb, in
         cp_async_commit();
     }
     int es = (-lag - 1) & (kEdgeRing - 1);  // edge slot of diagonal d-1
+    int ex = (-lag - 1) & (kEdgeRingX - 1);  // same in the cross-CTA ring
 
     // alpha: own = alpha(t-1,u) P_blank(t-1,u), share = alpha(t,u) P_label(t,u); the first cell gets
     // alpha(0,0) = 1 as own.  beta: own = share = beta(t+1,u) / beta(t,u+1); the first cell gets 1 so
@@ -186,14 +197,18 @@ __device__ __forceinline__ void sweep(const float2* __restrict__ lp2, int Tb, in
     for (int s0 = 0; s0 < S; s0 += kUnroll) {
         // kLag == kUnroll: one barrier per 8 diagonals
         if (kMode == 1) __syncthreads();
-        if (kMode == 2) cluster_barrier();
+        if (kMode == 2) {
+            if ((s0 & (kLagX - 1)) == 0) cluster_barrier();
+            else __syncthreads();
+        }
 #pragma unroll
         for (int k = 0; k < kUnroll; ++k) {
             // hand-off from the u-1 neighbour (its value on diagonal d-1)
             ME in;
             in.m = __shfl_up_sync(0xffffffffu, share.m, 1);
             in.e = __shfl_up_sync(0xffffffffu, share.e, 1);
-            const int2 ev = kMultiWarp ? edge[es][edge_col] : make_int2(0x3f800000, kZeroExp);
+            int2 ev = kMultiWarp ? edge[es][edge_col] : make_int2(0x3f800000, kZeroExp);
+            if (kMode == 2 && from_x) ev = xedge[ex];
 
             // off the dependent chain: refill the ring, fetch and split the factors of step s+1
             if ((unsigned)(tau + kDepth - 1) < Tb_eff) cp_async_8(k == 0 ? oth + kUnroll - 1 : cur + k - 1, src_pf + off);
@@ -218,9 +233,10 @@ __device__ __forceinline__ void sweep(const float2* __restrict__ lp2, int Tb, in
             if (tau == t_last) last = DIR == 0 ? own : val;  // terminal cell (t_last = -1 elsewhere)
             if (kMultiWarp) {
                 es = (es + 1) & (kEdgeRing - 1);  // now the slot of diagonal d
+                if (kMode == 2) ex = (ex + 1) & (kEdgeRingX - 1);
                 if (lane == 31) {
                     if (kMode == 1 || wl < wpc - 1) edge[es][wl] = make_int2(__float_as_int(share.m), share.e);
-                    else if (rank + 1 < n_rank) st_cluster_v2(&edge[es][31], rank + 1, __float_as_int(share.m), share.e);
+                    else if (rank + 1 < n_rank) st_cluster_v2(&xedge[ex], rank + 1, __float_as_int(share.m), share.e);
                 }
             }
             pb = pbn;
@@ -252,13 +268,14 @@ lattice_sweep_kernel(const float2* __restrict__ lp2, const int32_t* __restrict__
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* ring = reinterpret_cast<float2*>(smem_raw);  // [blockDim.x][kRingStride]
     __shared__ int2 edge[kEdgeRing][33];
+    __shared__ int2 xedge[kMode == 2 ? kEdgeRingX : 1];
     const int b = kMode == 2 ? blockIdx.x / cluster_nctarank() : blockIdx.x;
     const int Tb = min(max(act_lens[b], 1), T);
     const int Ub = min(max(label_lens[b], 0), U1 - 1);
     if (blockIdx.y == 0)
-        sweep<0, kMode>(lp2, Tb, Ub, T, U1, b, alpha, costs, ll_alpha, ring, edge);
+        sweep<0, kMode>(lp2, Tb, Ub, T, U1, b, alpha, costs, ll_alpha, ring, edge, xedge);
     else
-        sweep<1, kMode>(lp2, Tb, Ub, T, U1, b, beta, costs, ll_alpha, ring, edge);
+        sweep<1, kMode>(lp2, Tb, Ub, T, U1, b, beta, costs, ll_alpha, ring, edge, xedge);
 }
 
 }  // namespace
