@@ -298,35 +298,21 @@ int launch_lattice_sweep(const float2* lp2, const int32_t* act_lens, const int32
                                                                           beta, costs, ll_alpha);
         return launch_status();
     }
-    // longer label sequences: spread the sweep over a thread-block cluster.  Preferred: one warp per
-    // CTA (every warp gets an SM's schedulers to itself), which needs a non-portable cluster size
-    // beyond 8 warps; otherwise the portable shape (<= 4 warps per CTA, <= 8 CTAs).
+    // longer label sequences: spread the sweep over a cluster, <= 4 warps per CTA, <= 8 CTAs
+    const int wpc = (warps + 7) / 8, cs = (warps + wpc - 1) / wpc;
+    const size_t smem = (size_t)kRingStride * wpc * 32 * sizeof(float2);
     cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(B * cs), 2);
+    cfg.blockDim = dim3((unsigned)(wpc * 32));
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cs;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cfg.stream = stream;
-    int wpc = (warps + 7) / 8, cs = (warps + wpc - 1) / wpc;
-    if (warps > 8 && warps <= 16 &&
-        cudaFuncSetAttribute(lattice_sweep_kernel<2>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
-        cfg.gridDim = dim3((unsigned)(B * warps), 2);
-        cfg.blockDim = dim3(32);
-        cfg.dynamicSmemBytes = (size_t)kRingStride * 32 * sizeof(float2);
-        attr[0].val.clusterDim.x = (unsigned)warps;
-        int n_clusters = 0;
-        if (cudaOccupancyMaxActiveClusters(&n_clusters, lattice_sweep_kernel<2>, &cfg) == cudaSuccess && n_clusters > 0) {
-            wpc = 1;
-            cs = warps;
-        }
-        (void)cudaGetLastError();
-    }
-    cfg.gridDim = dim3((unsigned)(B * cs), 2);
-    cfg.blockDim = dim3((unsigned)(wpc * 32));
-    cfg.dynamicSmemBytes = (size_t)kRingStride * wpc * 32 * sizeof(float2);
-    attr[0].val.clusterDim.x = (unsigned)cs;
     cudaError_t e = cudaLaunchKernelEx(&cfg, lattice_sweep_kernel<2>, lp2, act_lens, label_lens, T, U1, alpha, beta,
                                        costs, ll_alpha);
     return e == cudaSuccess ? launch_status() : status_from_cuda(e);
