@@ -67,6 +67,21 @@ def hbm_peak():
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(kernel, c, args):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture
+    (profiles/dram_traffic.json, written by scripts/summarize_profiles.py).  The capture is of the
+    default workload (cfg 2, full-length): null for anything else."""
+    if args.cfg != 2 or args.batch or args.ragged:
+        return None
+    keys = {"proj_tc_kernel": "proj_tc_kernel", "proj_tc_bwd_kernel": "proj_tc_bwd_kernel", "cg_lse_kernel": "cg_lse", "cg_grad_kernel": "cg_grad",
+            "lattice_sweep_kernel": "lattice_sweep", "at_lse_kernel": "at_lse_tc", "at_grad_kernel": "at_grad_tc"}
+    try:
+        with open(os.path.join(ROOT, "profiles", "dram_traffic.json")) as f:
+            return json.load(f)[keys[kernel]]["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 def workload_config(args, world):
     from rnntransducer_b200 import synthetic
     c = dict(synthetic.CONFIGS[args.cfg])
@@ -400,7 +415,8 @@ def run_ours(args):
             k["frac_hbm"] = k["GBps"] / peak
         top = max((k for k in kernels.values() if k.get("ours")), key=lambda k: k["us"])
         roofline = {"kernel": top["name"], "bound": "hbm", "achieved": top["GBps"], "peak": peak,
-                    "unit": "GB/s", "frac": top["frac_hbm"], "traffic": None, "peak_source": peak_src,
+                    "unit": "GB/s", "frac": top["frac_hbm"], "traffic": ncu_traffic(top["name"], c, args),
+                    "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": top["bytes"], "us_per_launch": top["us"]}
 
     if rank != 0:
@@ -498,6 +514,15 @@ def per_kernel(lib, st, mode, gemm, det, B, T, U1, V, H, cells, flush_buf, iters
                 p(penc), p(pdec), p(lab), p(al), p(ll), B, T, U1, V, 0, p(lse), p(alpha), p(beta),
                 p(gcosts), p(d_penc), p(d_pdec), int(det), p(ws), ws_bytes, stream)),
                 12 * cells + 2 * io)
+            bws_bytes = lib.rnntb200_joint_cg_project_bwd_workspace_bytes(V, He, dec.shape[-1])
+            if bws_bytes:
+                bws = torch.empty(bws_bytes, dtype=torch.uint8, device=dev)
+                d_enc, d_dec, d_w, d_b = (torch.empty_like(t) for t in (enc, dec, w, b))
+                bench("proj_tc_bwd_kernel", lambda: _lib.check(lib.rnntb200_joint_cg_project_bwd(
+                    p(enc), p(dec), p(w), p(d_penc), p(d_pdec), B * T, B * U1, He, dec.shape[-1], V, p(d_enc),
+                    p(d_dec), p(d_w), p(d_b), p(bws), bws_bytes, 0, stream)),
+                    8 * (enc.numel() + dec.numel() + w.numel()) + io)
+                res["proj_tc_bwd_kernel"]["flops"] = 4.0 * V * (He * B * T + dec.shape[-1] * B * U1)
         else:
             d_enc, d_dec = torch.empty_like(enc), torch.empty_like(dec)
             d_w, d_b = torch.empty_like(w), torch.empty_like(b)

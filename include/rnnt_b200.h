@@ -22,7 +22,7 @@
  *   - lattice planes are [B, T, U1] row-major, 4 bytes per cell, U1 = max_label_len + 1:
  *       lp2   float2  (log p(blank|t,u), log p(y_{u+1}|t,u)), natural log
  *       lse   float   log-sum-exp of the cell's logits, natural log
- *       alpha, beta   rnntb200_q16_t: a 32-bit wide-exponent float ("e16m16"), value =
+ *       alpha, beta   rnntb200_e16m16_t: a 32-bit wide-exponent float ("e16m16"), value =
  *                     (1 + (q & 0xFFFF) / 65536) * 2^(q >> 16)  (arithmetic shift), i.e.
  *                     ln(alpha) = ((q >> 16) + log2(1 + (q & 0xFFFF) / 65536)) * ln(2).
  *                     2^-17 relative precision at any magnitude (|log2| < 32768), so the
@@ -64,7 +64,7 @@ typedef enum {
 typedef enum { RNNTB200_F32 = 0, RNNTB200_F16 = 1, RNNTB200_BF16 = 2 } rnntb200_dtype_t;
 
 /* alpha / beta plane element: e16m16 wide-exponent float (see conventions above) */
-typedef int32_t rnntb200_q16_t;
+typedef int32_t rnntb200_e16m16_t;
 
 /* joint function.  CONCAT_GELU is the reference's joint (transducer.py:64-69):
  *   logits = fc(gelu_tanh([enc_t ; dec_u])), fc.weight [V, He+Hd].
@@ -90,7 +90,7 @@ RNNTB200_API const char* rnntb200_status_string(int status);
  * Replaces warp-transducer compute_alphas/compute_betas and torchaudio's
  * ComputeAlphasBetasCosts.  Requires U1 <= 1024. */
 RNNTB200_API int rnntb200_lattice_sweep(const void* lp2, const int32_t* act_lens, const int32_t* label_lens,
-                           int B, int T, int U1, rnntb200_q16_t* alpha, rnntb200_q16_t* beta,
+                           int B, int T, int U1, rnntb200_e16m16_t* alpha, rnntb200_e16m16_t* beta,
                            float* costs, float* ll_alpha, void* stream);
 
 /* ------------------------------------------------------------------------------------------
@@ -102,12 +102,12 @@ RNNTB200_API int rnntb200_lattice_sweep(const void* lp2, const int32_t* act_lens
 RNNTB200_API int rnntb200_loss_dense_fwd(const void* logits, int dtype, const int32_t* labels,
                             const int32_t* act_lens, const int32_t* label_lens, int B, int T,
                             int U1, int V, int blank, float* costs, void* lp2, float* lse,
-                            rnntb200_q16_t* alpha, rnntb200_q16_t* beta, void* stream);
+                            rnntb200_e16m16_t* alpha, rnntb200_e16m16_t* beta, void* stream);
 
 RNNTB200_API int rnntb200_loss_dense_bwd(const void* logits, int dtype, const int32_t* labels,
                             const int32_t* act_lens, const int32_t* label_lens, int B, int T,
-                            int U1, int V, int blank, const float* lse, const rnntb200_q16_t* alpha,
-                            const rnntb200_q16_t* beta, const float* grad_costs,
+                            int U1, int V, int blank, const float* lse, const rnntb200_e16m16_t* alpha,
+                            const rnntb200_e16m16_t* beta, const float* grad_costs,
                             void* grad_logits, void* stream);
 
 /* ------------------------------------------------------------------------------------------
@@ -150,14 +150,14 @@ RNNTB200_API int rnntb200_joint_cg_project_bwd(const float* enc, const float* de
 RNNTB200_API int rnntb200_joint_cg_fwd(const float* penc, const float* pdec, const int32_t* labels,
                           const int32_t* act_lens, const int32_t* label_lens, int B, int T, int U1,
                           int V, int blank, float* costs, void* lp2, float* lse,
-                          rnntb200_q16_t* alpha, rnntb200_q16_t* beta, void* stream);
+                          rnntb200_e16m16_t* alpha, rnntb200_e16m16_t* beta, void* stream);
 
 RNNTB200_API size_t rnntb200_joint_cg_bwd_workspace_bytes(int B, int T, int U1, int V, int deterministic);
 
 RNNTB200_API int rnntb200_joint_cg_bwd(const float* penc, const float* pdec, const int32_t* labels,
                           const int32_t* act_lens, const int32_t* label_lens, int B, int T, int U1,
-                          int V, int blank, const float* lse, const rnntb200_q16_t* alpha,
-                          const rnntb200_q16_t* beta, const float* grad_costs, float* d_penc,
+                          int V, int blank, const float* lse, const rnntb200_e16m16_t* alpha,
+                          const rnntb200_e16m16_t* beta, const float* grad_costs, float* d_penc,
                           float* d_pdec, int deterministic, void* workspace, size_t workspace_bytes,
                           void* stream);
 
@@ -175,14 +175,14 @@ RNNTB200_API int rnntb200_joint_at_fwd(const float* enc, const float* dec, const
                           const float* bias, int gemm, const int32_t* labels,
                           const int32_t* act_lens, const int32_t* label_lens, int B, int T, int U1,
                           int V, int H, int blank, float* costs, void* lp2, float* lse,
-                          rnntb200_q16_t* alpha, rnntb200_q16_t* beta, void* workspace,
+                          rnntb200_e16m16_t* alpha, rnntb200_e16m16_t* beta, void* workspace,
                           size_t workspace_bytes, void* stream);
 
 RNNTB200_API int rnntb200_joint_at_bwd(const float* enc, const float* dec, const float* weight,
                           const float* bias, int gemm, const int32_t* labels,
                           const int32_t* act_lens, const int32_t* label_lens, int B, int T, int U1,
                           int V, int H, int blank, const void* lp2, const float* lse,
-                          const rnntb200_q16_t* alpha, const rnntb200_q16_t* beta,
+                          const rnntb200_e16m16_t* alpha, const rnntb200_e16m16_t* beta,
                           const float* grad_costs, float* d_enc, float* d_dec, float* d_weight,
                           float* d_bias, void* workspace, size_t workspace_bytes, void* stream);
 

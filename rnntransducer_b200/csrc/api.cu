@@ -34,7 +34,7 @@ RNNTB200_API const char* rnntb200_status_string(int status) {
 }
 
 RNNTB200_API int rnntb200_lattice_sweep(const void* lp2, const int32_t* act_lens, const int32_t* label_lens,
-                           int B, int T, int U1, rnntb200_q16_t* alpha, rnntb200_q16_t* beta,
+                           int B, int T, int U1, rnntb200_e16m16_t* alpha, rnntb200_e16m16_t* beta,
                            float* costs, float* ll_alpha, void* stream) {
     if (B < 0 || T <= 0 || U1 <= 0) return RNNTB200_STATUS_INVALID_VALUE;
     if (B > 0 && (!lp2 || !act_lens || !label_lens || !alpha || !beta || !costs))
@@ -46,7 +46,7 @@ RNNTB200_API int rnntb200_lattice_sweep(const void* lp2, const int32_t* act_lens
 RNNTB200_API int rnntb200_loss_dense_fwd(const void* logits, int dtype, const int32_t* labels,
                             const int32_t* act_lens, const int32_t* label_lens, int B, int T,
                             int U1, int V, int blank, float* costs, void* lp2, float* lse,
-                            rnntb200_q16_t* alpha, rnntb200_q16_t* beta, void* stream) {
+                            rnntb200_e16m16_t* alpha, rnntb200_e16m16_t* beta, void* stream) {
     if (bad_shape(B, T, U1, V, blank) || bad_dtype(dtype)) return RNNTB200_STATUS_INVALID_VALUE;
     if (B > 0 && (!logits || !act_lens || !label_lens || !costs || !lp2 || !lse || !alpha || !beta))
         return RNNTB200_STATUS_INVALID_VALUE;
@@ -61,8 +61,8 @@ RNNTB200_API int rnntb200_loss_dense_fwd(const void* logits, int dtype, const in
 
 RNNTB200_API int rnntb200_loss_dense_bwd(const void* logits, int dtype, const int32_t* labels,
                             const int32_t* act_lens, const int32_t* label_lens, int B, int T,
-                            int U1, int V, int blank, const float* lse, const rnntb200_q16_t* alpha,
-                            const rnntb200_q16_t* beta, const float* grad_costs,
+                            int U1, int V, int blank, const float* lse, const rnntb200_e16m16_t* alpha,
+                            const rnntb200_e16m16_t* beta, const float* grad_costs,
                             void* grad_logits, void* stream) {
     if (bad_shape(B, T, U1, V, blank) || bad_dtype(dtype)) return RNNTB200_STATUS_INVALID_VALUE;
     if (B > 0 && (!logits || !act_lens || !label_lens || !lse || !alpha || !beta ||
@@ -111,7 +111,7 @@ RNNTB200_API int rnntb200_joint_cg_project_bwd(const float* enc, const float* de
 RNNTB200_API int rnntb200_joint_cg_fwd(const float* penc, const float* pdec, const int32_t* labels,
                           const int32_t* act_lens, const int32_t* label_lens, int B, int T, int U1,
                           int V, int blank, float* costs, void* lp2, float* lse,
-                          rnntb200_q16_t* alpha, rnntb200_q16_t* beta, void* stream) {
+                          rnntb200_e16m16_t* alpha, rnntb200_e16m16_t* beta, void* stream) {
     if (bad_shape(B, T, U1, V, blank)) return RNNTB200_STATUS_INVALID_VALUE;
     if (B > 0 && (!penc || !pdec || !act_lens || !label_lens || !costs || !lp2 || !lse || !alpha || !beta))
         return RNNTB200_STATUS_INVALID_VALUE;
@@ -131,8 +131,8 @@ RNNTB200_API size_t rnntb200_joint_cg_bwd_workspace_bytes(int B, int T, int U1, 
 
 RNNTB200_API int rnntb200_joint_cg_bwd(const float* penc, const float* pdec, const int32_t* labels,
                           const int32_t* act_lens, const int32_t* label_lens, int B, int T, int U1,
-                          int V, int blank, const float* lse, const rnntb200_q16_t* alpha,
-                          const rnntb200_q16_t* beta, const float* grad_costs, float* d_penc,
+                          int V, int blank, const float* lse, const rnntb200_e16m16_t* alpha,
+                          const rnntb200_e16m16_t* beta, const float* grad_costs, float* d_penc,
                           float* d_pdec, int deterministic, void* workspace, size_t workspace_bytes,
                           void* stream) {
     if (bad_shape(B, T, U1, V, blank)) return RNNTB200_STATUS_INVALID_VALUE;
@@ -154,7 +154,7 @@ RNNTB200_API int rnntb200_joint_at_fwd(const float* enc, const float* dec, const
                           const float* bias, int gemm, const int32_t* labels,
                           const int32_t* act_lens, const int32_t* label_lens, int B, int T, int U1,
                           int V, int H, int blank, float* costs, void* lp2, float* lse,
-                          rnntb200_q16_t* alpha, rnntb200_q16_t* beta, void* workspace,
+                          rnntb200_e16m16_t* alpha, rnntb200_e16m16_t* beta, void* workspace,
                           size_t workspace_bytes, void* stream) {
     if (bad_shape(B, T, U1, V, blank) || H <= 0 || bad_gemm(gemm)) return RNNTB200_STATUS_INVALID_VALUE;
     if (B > 0 && (!enc || !dec || !weight || !bias || !act_lens || !label_lens || !costs || !lp2 ||
@@ -173,7 +173,7 @@ RNNTB200_API int rnntb200_joint_at_bwd(const float* enc, const float* dec, const
                           const float* bias, int gemm, const int32_t* labels,
                           const int32_t* act_lens, const int32_t* label_lens, int B, int T, int U1,
                           int V, int H, int blank, const void* lp2, const float* lse,
-                          const rnntb200_q16_t* alpha, const rnntb200_q16_t* beta,
+                          const rnntb200_e16m16_t* alpha, const rnntb200_e16m16_t* beta,
                           const float* grad_costs, float* d_enc, float* d_dec, float* d_weight,
                           float* d_bias, void* workspace, size_t workspace_bytes, void* stream) {
     if (bad_shape(B, T, U1, V, blank) || H <= 0 || bad_gemm(gemm)) return RNNTB200_STATUS_INVALID_VALUE;

@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import csv
 import io
+import json
 import os
 import subprocess
 import sys
@@ -77,6 +78,26 @@ def summarize_full(tag):
     path = os.path.join(PROF, f"{tag}_ncu_full.md")
     with open(path, "w") as f:
         f.write("\n".join(lines) + "\n")
+    # DRAM traffic per launch of every kernel seen (bench.py's roofline.traffic reads this file)
+    traffic_path = os.path.join(PROF, "dram_traffic.json")
+    try:
+        traffic = json.load(open(traffic_path))
+    except Exception:
+        traffic = {}
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for r in rows:
+        d, u = dict(zip(hdr, r)), dict(zip(hdr, units))
+        try:
+            tot = sum(float(d[k]) * scale.get(u.get(k, "byte"), 1) for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+        except (KeyError, ValueError):
+            continue
+        name = d.get("Kernel Name", "?")
+        for key in ("proj_tc_bwd_kernel", "proj_tc_kernel", "cg_lse", "cg_grad", "lattice_sweep", "at_lse_tc", "at_grad_tc"):
+            if key in name:
+                traffic[key] = {"dram_bytes_per_launch": tot, "source": f"{tag}_prof.ncu-rep (ncu --set full)"}
+                break
+    with open(traffic_path, "w") as f:
+        json.dump(traffic, f, indent=1, sort_keys=True)
     return path
 
 
