@@ -15,8 +15,8 @@
 // K-major operand by one product and as an MN-major operand by another (core matrices are 8 x 16 B
 // either way; only the descriptor strides and the major bits of the instruction descriptor change).
 //
-// Warp roles (one persistent CTA per SM): warps 0-7 build z; warp 8 streams W by TMA (twice per
-// tile: for S and for dZ); warp 9 issues every MMA; warps 10-17 (two groups) own one lattice cell (TMEM lane)
+// Warp roles (one persistent CTA per SM): warps 0-15 build z; warp 16 streams W by TMA (twice per
+// tile: for S and for dZ); warp 17 issues every MMA; warps 18-25 (two groups) own one lattice cell (TMEM lane)
 // each: they turn S into G, dZ into dP, and move the reduced d_enc / d_dec tiles to HBM (fp32
 // atomics).  mbarrier-only synchronisation.  TMEM map (512 columns): dW^T [0,320) | S [320,400) |
 // dZ pieces [400,464) and [320,384) (the second aliases S, dead by then) | d_enc^T/d_dec^T [320,448) (aliases S and dZ, both dead by then) | db [464,480).
@@ -35,10 +35,10 @@ namespace {
 
 constexpr int kTT = 16, kUU = 8;
 constexpr int kKB = 64;
-constexpr int kProducerWarps = 8;   // z production is not the long pole here
+constexpr int kProducerWarps = 16;
 constexpr int kProducerThreads = kProducerWarps * 32;
-constexpr int kTmaWarp = 8, kMmaWarp = 9;    // warps 10-13 / 14-17: epilogue groups 0 / 1
-constexpr int kThreads = 18 * 32;
+constexpr int kTmaWarp = 16, kMmaWarp = 17;  // warps 18-21 / 22-25: epilogue groups 0 / 1
+constexpr int kThreads = 26 * 32;
 constexpr int kMaxWStages = 8;
 constexpr int kASlotBytes = 128 * kKB * 2;  // one 64-wide K block of z: 16 KiB
 constexpr int kGroupBytes = 2048;           // 128 rows x 16 B: one 8-element column group of z / G
@@ -165,7 +165,7 @@ at_grad_tc_kernel(const __grid_constant__ CUtensorMap w_map, const float* __rest
             mbar_wait(z_empty, (n & 1) ^ 1);  // every reader of the previous tile's z / dP is done
             // stage the tile's 8 predictor rows (each is reused by all 16 frames); the encoder rows
             // are read straight from global memory: every element is needed by exactly one warp
-            asm volatile("bar.sync 1, 256;" ::: "memory");  // previous tile's readers are done
+            asm volatile("bar.sync 1, 512;" ::: "memory");  // previous tile's readers are done
             const int H4 = H / 4;
             for (int i = p; i < kUU * H4; i += kProducerThreads) {
                 const int row = i / H4, c4 = i - row * H4;
@@ -173,29 +173,29 @@ at_grad_tc_kernel(const __grid_constant__ CUtensorMap w_map, const float* __rest
                 *reinterpret_cast<float4*>(dd + row * L.dd_stride + 4 * c4) =
                     __ldg(reinterpret_cast<const float4*>(src) + c4);
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            asm volatile("bar.sync 1, 512;" ::: "memory");
             const float4* erow = reinterpret_cast<const float4*>(enc + ((size_t)b * T + min(t0 + tt, T - 1)) * H);
             const float* drow = dd + uu * L.dd_stride;
-            float4 ecur[8], enxt[8];  // this thread's 4 x 8 encoder values of a K block, double-buffered
+            // this thread's 2 x 8 encoder values per K block, fetched two K blocks ahead (L2 latency
+            // is several hundred cycles, one block of tanh work is not enough to cover it)
+            float4 e0buf[4], e1buf[4], e2buf[4];
+            auto load_e = [&](float4* dst, int kb) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                ecur[2 * i] = __ldg(erow + (kc0 + 2 * i) * 2);
-                ecur[2 * i + 1] = __ldg(erow + (kc0 + 2 * i) * 2 + 1);
-            }
-            for (int kb = 0; kb < n_slots; ++kb) {
-                if (kb + 1 < n_slots) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        enxt[2 * i] = __ldg(erow + ((kb + 1) * kKB / 4) + (kc0 + 2 * i) * 2);
-                        enxt[2 * i + 1] = __ldg(erow + ((kb + 1) * kKB / 4) + (kc0 + 2 * i) * 2 + 1);
-                    }
+                for (int i = 0; i < 2; ++i) {
+                    dst[2 * i] = __ldg(erow + kb * (kKB / 4) + (kc0 + 4 * i) * 2);
+                    dst[2 * i + 1] = __ldg(erow + kb * (kKB / 4) + (kc0 + 4 * i) * 2 + 1);
                 }
+            };
+            load_e(e0buf, 0);
+            if (n_slots > 1) load_e(e1buf, 1);
+            for (int kb = 0; kb < n_slots; ++kb) {
+                if (kb + 2 < n_slots) load_e(e2buf, kb + 2);
                 
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int kc = kc0 + 2 * i;
+                for (int i = 0; i < 2; ++i) {
+                    const int kc = kc0 + 4 * i;
                     const int k = kb * kKB + kc * 8;
-                    const float4 e0 = ecur[2 * i], e1 = ecur[2 * i + 1];
+                    const float4 e0 = e0buf[2 * i], e1 = e0buf[2 * i + 1];
                     const float4 d0 = *reinterpret_cast<const float4*>(drow + k);
                     const float4 d1 = *reinterpret_cast<const float4*>(drow + k + 4);
                     uint4 out;
@@ -206,7 +206,7 @@ at_grad_tc_kernel(const __grid_constant__ CUtensorMap w_map, const float* __rest
                     *reinterpret_cast<uint4*>(smem + L.z + kb * kASlotBytes + kc * kGroupBytes + r * 16) = out;
                 }
 #pragma unroll
-                for (int i = 0; i < 8; ++i) ecur[i] = enxt[i];
+                for (int i = 0; i < 4; ++i) { e0buf[i] = e1buf[i]; e1buf[i] = e2buf[i]; }
                 fence_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
                 __syncwarp();
                 if (lane == 0) mbar_arrive(z_full(kb));
@@ -307,7 +307,7 @@ at_grad_tc_kernel(const __grid_constant__ CUtensorMap w_map, const float* __rest
         // groups see all 128 cells; they split the work by columns: group g turns the vocabulary
         // pieces pc = g, g+2, .. of S into G, owns dZ buffer g (pieces kb = g, g+2, ..), and moves the
         // reduced tiles / accumulators of the row blocks mt = g, g+2, .. =====
-        const int grp = (warp - 10) >> 2;
+        const int grp = (warp - 18) >> 2;
         const int q = warp & 3;
         const int r = q * 32 + lane;
         const int tt = r / kUU, uu = r % kUU;
