@@ -145,26 +145,27 @@ at_lse_tc_kernel(const __grid_constant__ CUtensorMap w_map, const float* __restr
             asm volatile("bar.sync 1, 512;" ::: "memory");
             const float4* erow = reinterpret_cast<const float4*>(enc + ((size_t)b * T + min(t0 + tt, T - 1)) * H);
             const float* drow = dd + uu * L.dd_stride;
-            // this thread's 2 x 8 encoder values per K block, fetched two K blocks ahead (L2 latency
-            // is several hundred cycles, one block of tanh work is not enough to cover it)
-            float4 e0buf[4], e1buf[4], e2buf[4];
-            auto load_e = [&](float4* dst, int kb) {
+            // This thread's 2 x 8 encoder values per K block live in three register buffers that take
+            // turns (the K loop is unrolled by three so the roles are compile-time: no register copy
+            // ever has to wait for a load): the values of block kb+2 are requested while block kb is
+            // computed, which covers the L2 latency with two blocks of tanh work.
+            float4 eb0[4], eb1[4], eb2[4];
+            auto load_e = [&](float4(&dst)[4], int kb) {
+                if (kb < n_slots) {
 #pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    dst[2 * i] = __ldg(erow + kb * (kKB / 4) + (kc0 + 4 * i) * 2);
-                    dst[2 * i + 1] = __ldg(erow + kb * (kKB / 4) + (kc0 + 4 * i) * 2 + 1);
+                    for (int i = 0; i < 2; ++i) {
+                        dst[2 * i] = __ldg(erow + kb * (kKB / 4) + (kc0 + 4 * i) * 2);
+                        dst[2 * i + 1] = __ldg(erow + kb * (kKB / 4) + (kc0 + 4 * i) * 2 + 1);
+                    }
                 }
             };
-            load_e(e0buf, 0);
-            if (n_slots > 1) load_e(e1buf, 1);
-            for (int kb = 0; kb < n_slots; ++kb) {
-                if (kb + 2 < n_slots) load_e(e2buf, kb + 2);
+            auto block = [&](const float4(&e)[4], int kb) {
                 mbar_wait(a_empty(kb), (n & 1) ^ 1);
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
                     const int kc = kc0 + 4 * i;
                     const int k = kb * kKB + kc * 8;
-                    const float4 e0 = e0buf[2 * i], e1 = e0buf[2 * i + 1];
+                    const float4 e0 = e[2 * i], e1 = e[2 * i + 1];
                     const float4 d0 = *reinterpret_cast<const float4*>(drow + k);
                     const float4 d1 = *reinterpret_cast<const float4*>(drow + k + 4);
                     uint4 out;
@@ -175,11 +176,23 @@ at_lse_tc_kernel(const __grid_constant__ CUtensorMap w_map, const float* __restr
                     // core-matrix layout: K chunk kc at kc * 2048, cell row r at r * 16
                     *reinterpret_cast<uint4*>(smem + L.a + kb * kASlotBytes + kc * 2048 + r * 16) = out;
                 }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) { e0buf[i] = e1buf[i]; e1buf[i] = e2buf[i]; }
                 fence_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
                 __syncwarp();
                 if (lane == 0) mbar_arrive(a_full(kb));
+            };
+            load_e(eb0, 0);
+            load_e(eb1, 1);
+            for (int kb = 0; kb < n_slots; kb += 3) {
+                load_e(eb2, kb + 2);
+                block(eb0, kb);
+                if (kb + 1 < n_slots) {
+                    load_e(eb0, kb + 3);
+                    block(eb1, kb + 1);
+                }
+                if (kb + 2 < n_slots) {
+                    load_e(eb1, kb + 4);
+                    block(eb2, kb + 2);
+                }
             }
             ++n;
         }

@@ -176,26 +176,24 @@ at_grad_tc_kernel(const __grid_constant__ CUtensorMap w_map, const float* __rest
             asm volatile("bar.sync 1, 512;" ::: "memory");
             const float4* erow = reinterpret_cast<const float4*>(enc + ((size_t)b * T + min(t0 + tt, T - 1)) * H);
             const float* drow = dd + uu * L.dd_stride;
-            // this thread's 2 x 8 encoder values per K block, fetched two K blocks ahead (L2 latency
-            // is several hundred cycles, one block of tanh work is not enough to cover it)
-            float4 e0buf[4], e1buf[4], e2buf[4];
-            auto load_e = [&](float4* dst, int kb) {
+            // three register buffers take turns (K loop unrolled by three, roles are compile-time):
+            // block kb+2 is requested while block kb is computed
+            float4 eb0[4], eb1[4], eb2[4];
+            auto load_e = [&](float4(&dst)[4], int kb) {
+                if (kb < n_slots) {
 #pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    dst[2 * i] = __ldg(erow + kb * (kKB / 4) + (kc0 + 4 * i) * 2);
-                    dst[2 * i + 1] = __ldg(erow + kb * (kKB / 4) + (kc0 + 4 * i) * 2 + 1);
+                    for (int i = 0; i < 2; ++i) {
+                        dst[2 * i] = __ldg(erow + kb * (kKB / 4) + (kc0 + 4 * i) * 2);
+                        dst[2 * i + 1] = __ldg(erow + kb * (kKB / 4) + (kc0 + 4 * i) * 2 + 1);
+                    }
                 }
             };
-            load_e(e0buf, 0);
-            if (n_slots > 1) load_e(e1buf, 1);
-            for (int kb = 0; kb < n_slots; ++kb) {
-                if (kb + 2 < n_slots) load_e(e2buf, kb + 2);
-                
+            auto block = [&](const float4(&e)[4], int kb) {
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
                     const int kc = kc0 + 4 * i;
                     const int k = kb * kKB + kc * 8;
-                    const float4 e0 = e0buf[2 * i], e1 = e0buf[2 * i + 1];
+                    const float4 e0 = e[2 * i], e1 = e[2 * i + 1];
                     const float4 d0 = *reinterpret_cast<const float4*>(drow + k);
                     const float4 d1 = *reinterpret_cast<const float4*>(drow + k + 4);
                     uint4 out;
@@ -205,11 +203,23 @@ at_grad_tc_kernel(const __grid_constant__ CUtensorMap w_map, const float* __rest
                     out.w = pack_bf16(tanh_fast(e1.z + d1.z), tanh_fast(e1.w + d1.w));
                     *reinterpret_cast<uint4*>(smem + L.z + kb * kASlotBytes + kc * kGroupBytes + r * 16) = out;
                 }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) { e0buf[i] = e1buf[i]; e1buf[i] = e2buf[i]; }
-                fence_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
+                fence_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(z_full(kb));
+            };
+            load_e(eb0, 0);
+            load_e(eb1, 1);
+            for (int kb = 0; kb < n_slots; kb += 3) {
+                load_e(eb2, kb + 2);
+                block(eb0, kb);
+                if (kb + 1 < n_slots) {
+                    load_e(eb0, kb + 3);
+                    block(eb1, kb + 1);
+                }
+                if (kb + 2 < n_slots) {
+                    load_e(eb1, kb + 4);
+                    block(eb2, kb + 2);
+                }
             }
             ++n;
         }
