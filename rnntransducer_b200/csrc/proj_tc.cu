@@ -130,26 +130,25 @@ proj_tc_kernel(const __grid_constant__ CUtensorMap w0_hi, const __grid_constant_
         const int r = threadIdx.x & 127, kc0 = threadIdx.x >> 7;
         const int row = min(row0 + r, P.rows - 1);  // rows past the end are computed but never stored
         const float4* xrow = reinterpret_cast<const float4*>(P.x + (size_t)row * P.K);
-        float4 cur[4], nxt[4];
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            cur[2 * i] = __ldg(xrow + (kc0 + 4 * i) * 2);
-            cur[2 * i + 1] = __ldg(xrow + (kc0 + 4 * i) * 2 + 1);
-        }
-        for (int kb = 0; kb < n_kb; ++kb) {
-            if (kb + 1 < n_kb) {
+        // three register buffers take turns (K loop unrolled by three, compile-time roles, no copy
+        // ever waits on a load): block kb+2 is requested while block kb is computed
+        float4 xb0[4], xb1[4], xb2[4];
+        auto load_x = [&](float4(&dst)[4], int kb) {
+            if (kb < n_kb) {
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
-                    nxt[2 * i] = __ldg(xrow + (kb + 1) * (kKB / 4) + (kc0 + 4 * i) * 2);
-                    nxt[2 * i + 1] = __ldg(xrow + (kb + 1) * (kKB / 4) + (kc0 + 4 * i) * 2 + 1);
+                    dst[2 * i] = __ldg(xrow + kb * (kKB / 4) + (kc0 + 4 * i) * 2);
+                    dst[2 * i + 1] = __ldg(xrow + kb * (kKB / 4) + (kc0 + 4 * i) * 2 + 1);
                 }
             }
+        };
+        auto block = [&](const float4(&x)[4], int kb) {
             const int st = kb % kStages;
             mbar_wait(a_empty(st), ((kb / kStages) & 1) ^ 1);
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
                 const int kc = kc0 + 4 * i;
-                const float4 x0 = cur[2 * i], x1 = cur[2 * i + 1];
+                const float4 x0 = x[2 * i], x1 = x[2 * i + 1];
                 uint4 hi, lo;
                 split_store(gelu_tanh(x0.x), gelu_tanh(x0.y), hi.x, lo.x);
                 split_store(gelu_tanh(x0.z), gelu_tanh(x0.w), hi.y, lo.y);
@@ -159,11 +158,23 @@ proj_tc_kernel(const __grid_constant__ CUtensorMap w0_hi, const __grid_constant_
                 *reinterpret_cast<uint4*>(dst) = hi;
                 *reinterpret_cast<uint4*>(dst + kAHalf) = lo;
             }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(a_full(st));
+        };
+        load_x(xb0, 0);
+        load_x(xb1, 1);
+        for (int kb = 0; kb < n_kb; kb += 3) {
+            load_x(xb2, kb + 2);
+            block(xb0, kb);
+            if (kb + 1 < n_kb) {
+                load_x(xb0, kb + 3);
+                block(xb1, kb + 1);
+            }
+            if (kb + 2 < n_kb) {
+                load_x(xb1, kb + 4);
+                block(xb2, kb + 2);
+            }
         }
     } else if (warp == kTmaWarp) {
         if (lane == 0) {

@@ -152,19 +152,23 @@ proj_tc_bwd_kernel(const __grid_constant__ CUtensorMap w0_hi, const __grid_const
         if (lane == 0) mbar_arrive(dp_full);
         // (2) gelu(x) in 128-column blocks -> (hi, lo), [h-group][row][8 h]
         const float4* xrow = reinterpret_cast<const float4*>(P.x + (size_t)min(row, P.rows - 1) * P.K);
-        for (int blk = 0; blk < n_blk; ++blk) {
-            float4 xv[16];
+        // each 128-column block is produced as two 64-column halves from two register buffers that
+        // alternate: the loads of the next half are in flight while the current one is computed
+        float4 xa[8], xb[8];
+        auto load_half = [&](float4(&dst)[8], int blk, int hf) {  // h-groups 8*hf + half + 2i
+            if (blk < n_blk) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                xv[2 * i] = __ldg(xrow + blk * 32 + (half + 2 * i) * 2);
-                xv[2 * i + 1] = __ldg(xrow + blk * 32 + (half + 2 * i) * 2 + 1);
+                for (int i = 0; i < 4; ++i) {
+                    dst[2 * i] = __ldg(xrow + blk * 32 + (8 * hf + half + 2 * i) * 2);
+                    dst[2 * i + 1] = __ldg(xrow + blk * 32 + (8 * hf + half + 2 * i) * 2 + 1);
+                }
             }
-            const int st = blk & 1;
-            mbar_wait(gx_empty(st), ((blk >> 1) & 1) ^ 1);
+        };
+        auto do_half = [&](const float4(&x)[8], int st, int hf) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int kc = half + 2 * i;
-                const float4 x0 = xv[2 * i], x1 = xv[2 * i + 1];
+            for (int i = 0; i < 4; ++i) {
+                const int kc = 8 * hf + half + 2 * i;
+                const float4 x0 = x[2 * i], x1 = x[2 * i + 1];
                 uint4 hi, lo;
                 split2(gelu_val(x0.x), gelu_val(x0.y), hi.x, lo.x);
                 split2(gelu_val(x0.z), gelu_val(x0.w), hi.y, lo.y);
@@ -175,6 +179,15 @@ proj_tc_bwd_kernel(const __grid_constant__ CUtensorMap w0_hi, const __grid_const
                 *reinterpret_cast<uint4*>(dst) = hi;
                 *reinterpret_cast<uint4*>(dst + kGxHalf) = lo;
             }
+        };
+        load_half(xa, 0, 0);
+        for (int blk = 0; blk < n_blk; ++blk) {
+            const int st = blk & 1;
+            load_half(xb, blk, 1);
+            mbar_wait(gx_empty(st), ((blk >> 1) & 1) ^ 1);
+            do_half(xa, st, 0);
+            load_half(xa, blk + 1, 0);
+            do_half(xb, st, 1);
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(gx_full(st));
