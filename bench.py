@@ -429,9 +429,10 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    # our kernels per step: concat_gelu = weight split x2 + projection + lse + sweep + grad (+ slab
-    # reduction); add_tanh = weight convert + lse + sweep + (weight convert +) grad
-    launches = {"concat_gelu": 6 + int(det), "add_tanh": 5 if gemm == "bf16" else 3}[mode]
+    # our kernels per step: concat_gelu = weight split + projection + factor rows + lse + sweep + grad
+    # + projection backward (+ slab reduction); add_tanh = weight convert + lse + sweep + (weight
+    # convert +) grad
+    launches = {"concat_gelu": 7 + int(det), "add_tanh": 5 if gemm == "bf16" else 3}[mode]
     line = {
         "metric": METRIC, "value": total_cells * args.steps / (total_ms * 1e-3), "unit": UNIT,
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -510,15 +511,18 @@ def per_kernel(lib, st, mode, gemm, det, B, T, U1, V, H, cells, flush_buf, iters
             else:
                 bench("torch_projections(gelu+linear x2, library)", proj,
                       4 * (enc.numel() + dec.numel() + w.numel()) + io, ours=False)
+            fac_bytes = lib.rnntb200_joint_cg_factors_bytes(B, T, U1, V)
+            fac = torch.empty(max(fac_bytes, 16), dtype=torch.uint8, device=dev)
+            # factor-rows kernel + cell kernel (two launches, timed together)
             bench("cg_lse_kernel", lambda: _lib.check(lib.rnntb200_joint_cg_logprobs(
-                p(penc), p(pdec), p(lab), p(al), p(ll), B, T, U1, V, 0, p(lp2), p(lse), stream)),
-                12 * cells + io)
+                p(penc), p(pdec), p(lab), p(al), p(ll), B, T, U1, V, 0, p(lp2), p(lse),
+                p(fac) if fac_bytes else None, fac_bytes, stream)), 12 * cells + io)
             bench("lattice_sweep_kernel", lambda: _lib.check(lib.rnntb200_lattice_sweep(
                 p(lp2), p(al), p(ll), B, T, U1, p(alpha), p(beta), p(costs), None, stream)), 24 * cells)
             bench("cg_grad_kernel", lambda: _lib.check(lib.rnntb200_joint_cg_bwd(
                 p(penc), p(pdec), p(lab), p(al), p(ll), B, T, U1, V, 0, p(lse), p(alpha), p(beta),
-                p(gcosts), p(d_penc), p(d_pdec), int(det), p(ws), ws_bytes, stream)),
-                12 * cells + 2 * io)
+                p(gcosts), p(d_penc), p(d_pdec), int(det), p(ws), ws_bytes,
+                p(fac) if fac_bytes else None, fac_bytes, stream)), 12 * cells + 2 * io)
             bws_bytes = lib.rnntb200_joint_cg_project_bwd_workspace_bytes(V, He, dec.shape[-1])
             if bws_bytes:
                 bws = torch.empty(bws_bytes, dtype=torch.uint8, device=dev)

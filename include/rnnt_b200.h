@@ -147,10 +147,18 @@ RNNTB200_API int rnntb200_joint_cg_project_bwd(const float* enc, const float* de
                                   float* d_bias, void* workspace, size_t workspace_bytes,
                                   int workspace_holds_split, void* stream);
 
+/* `factors` (rnntb200_joint_cg_factors_bytes, 16-byte aligned; the query returns 0 and NULL is
+ * accepted for V > 128) receives the factor planes of this step -- 2^((P - rowmax) log2 e) of both
+ * projections plus per-row scalars, computed once instead of per frame tile.  The forward (or
+ * rnntb200_joint_cg_logprobs) writes them; rnntb200_joint_cg_bwd for the same penc / pdec reads
+ * them: like lse / alpha / beta they are state saved between the two passes, owned by the caller. */
+RNNTB200_API size_t rnntb200_joint_cg_factors_bytes(int B, int T, int U1, int V);
+
 RNNTB200_API int rnntb200_joint_cg_fwd(const float* penc, const float* pdec, const int32_t* labels,
                           const int32_t* act_lens, const int32_t* label_lens, int B, int T, int U1,
                           int V, int blank, float* costs, void* lp2, float* lse,
-                          rnntb200_e16m16_t* alpha, rnntb200_e16m16_t* beta, void* stream);
+                          rnntb200_e16m16_t* alpha, rnntb200_e16m16_t* beta, void* factors,
+                          size_t factors_bytes, void* stream);
 
 RNNTB200_API size_t rnntb200_joint_cg_bwd_workspace_bytes(int B, int T, int U1, int V, int deterministic);
 
@@ -159,7 +167,7 @@ RNNTB200_API int rnntb200_joint_cg_bwd(const float* penc, const float* pdec, con
                           int V, int blank, const float* lse, const rnntb200_e16m16_t* alpha,
                           const rnntb200_e16m16_t* beta, const float* grad_costs, float* d_penc,
                           float* d_pdec, int deterministic, void* workspace, size_t workspace_bytes,
-                          void* stream);
+                          const void* factors, size_t factors_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Fused joint + loss, ADD_TANH mode: logits(t,u,:) = tanh(enc_t + dec_u) W^T + bias, the one
@@ -197,7 +205,8 @@ RNNTB200_API int rnntb200_dense_logprobs(const void* logits, int dtype, const in
 
 RNNTB200_API int rnntb200_joint_cg_logprobs(const float* penc, const float* pdec, const int32_t* labels,
                                const int32_t* act_lens, const int32_t* label_lens, int B, int T,
-                               int U1, int V, int blank, void* lp2, float* lse, void* stream);
+                               int U1, int V, int blank, void* lp2, float* lse, void* factors,
+                               size_t factors_bytes, void* stream);
 
 RNNTB200_API int rnntb200_joint_at_logprobs(const float* enc, const float* dec, const float* weight,
                                const float* bias, int gemm, const int32_t* labels,

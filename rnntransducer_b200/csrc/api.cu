@@ -111,17 +111,23 @@ RNNTB200_API int rnntb200_joint_cg_project_bwd(const float* enc, const float* de
 RNNTB200_API int rnntb200_joint_cg_fwd(const float* penc, const float* pdec, const int32_t* labels,
                           const int32_t* act_lens, const int32_t* label_lens, int B, int T, int U1,
                           int V, int blank, float* costs, void* lp2, float* lse,
-                          rnntb200_e16m16_t* alpha, rnntb200_e16m16_t* beta, void* stream) {
+                          rnntb200_e16m16_t* alpha, rnntb200_e16m16_t* beta, void* factors,
+                          size_t factors_bytes, void* stream) {
     if (bad_shape(B, T, U1, V, blank)) return RNNTB200_STATUS_INVALID_VALUE;
     if (B > 0 && (!penc || !pdec || !act_lens || !label_lens || !costs || !lp2 || !lse || !alpha || !beta))
         return RNNTB200_STATUS_INVALID_VALUE;
     if (B > 0 && U1 > 1 && !labels) return RNNTB200_STATUS_INVALID_VALUE;
     cudaStream_t s = (cudaStream_t)stream;
     int st = launch_cg_lse(penc, pdec, labels, act_lens, label_lens, B, T, U1, V, blank, (float2*)lp2,
-                           lse, s);
+                           lse, factors, factors_bytes, s);
     if (st != RNNTB200_STATUS_SUCCESS) return st;
     return launch_lattice_sweep((const float2*)lp2, act_lens, label_lens, B, T, U1, alpha, beta,
                                 costs, nullptr, s);
+}
+
+RNNTB200_API size_t rnntb200_joint_cg_factors_bytes(int B, int T, int U1, int V) {
+    if (B <= 0 || T <= 0 || U1 <= 0 || V <= 0) return 0;
+    return cg_factors_bytes(B, T, U1, V);
 }
 
 RNNTB200_API size_t rnntb200_joint_cg_bwd_workspace_bytes(int B, int T, int U1, int V, int deterministic) {
@@ -134,7 +140,7 @@ RNNTB200_API int rnntb200_joint_cg_bwd(const float* penc, const float* pdec, con
                           int V, int blank, const float* lse, const rnntb200_e16m16_t* alpha,
                           const rnntb200_e16m16_t* beta, const float* grad_costs, float* d_penc,
                           float* d_pdec, int deterministic, void* workspace, size_t workspace_bytes,
-                          void* stream) {
+                          const void* factors, size_t factors_bytes, void* stream) {
     if (bad_shape(B, T, U1, V, blank)) return RNNTB200_STATUS_INVALID_VALUE;
     if (B > 0 && (!penc || !pdec || !act_lens || !label_lens || !lse || !alpha || !beta ||
                   !grad_costs || !d_penc || !d_pdec))
@@ -142,7 +148,7 @@ RNNTB200_API int rnntb200_joint_cg_bwd(const float* penc, const float* pdec, con
     if (B > 0 && U1 > 1 && !labels) return RNNTB200_STATUS_INVALID_VALUE;
     return launch_cg_grad(penc, pdec, labels, act_lens, label_lens, B, T, U1, V, blank, lse, alpha,
                           beta, grad_costs, d_penc, d_pdec, deterministic, workspace,
-                          workspace_bytes, (cudaStream_t)stream);
+                          workspace_bytes, factors, factors_bytes, (cudaStream_t)stream);
 }
 
 RNNTB200_API size_t rnntb200_joint_at_workspace_bytes(int V, int H, int gemm) {
@@ -198,12 +204,13 @@ RNNTB200_API int rnntb200_dense_logprobs(const void* logits, int dtype, const in
 
 RNNTB200_API int rnntb200_joint_cg_logprobs(const float* penc, const float* pdec, const int32_t* labels,
                                const int32_t* act_lens, const int32_t* label_lens, int B, int T,
-                               int U1, int V, int blank, void* lp2, float* lse, void* stream) {
+                               int U1, int V, int blank, void* lp2, float* lse, void* factors,
+                               size_t factors_bytes, void* stream) {
     if (bad_shape(B, T, U1, V, blank)) return RNNTB200_STATUS_INVALID_VALUE;
     if (B > 0 && (!penc || !pdec || !act_lens || !label_lens || !lp2 || !lse)) return RNNTB200_STATUS_INVALID_VALUE;
     if (B > 0 && U1 > 1 && !labels) return RNNTB200_STATUS_INVALID_VALUE;
     return launch_cg_lse(penc, pdec, labels, act_lens, label_lens, B, T, U1, V, blank, (float2*)lp2,
-                         lse, (cudaStream_t)stream);
+                         lse, factors, factors_bytes, (cudaStream_t)stream);
 }
 
 RNNTB200_API int rnntb200_joint_at_logprobs(const float* enc, const float* dec, const float* weight,

@@ -26,6 +26,12 @@ __device__ __forceinline__ float fast_lg2(float x) {
     return y;
 }
 
+__device__ __forceinline__ float fast_rcp(float x) {  // MUFU.RCP, <= 1 ulp; x normal and finite
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // log2(2^a + 2^b), base-2 log domain: 1 MUFU.EX2 + 1 MUFU.LG2 on the dependent chain.
 __device__ __forceinline__ float logaddexp2(float a, float b) {
     const float m = fmaxf(a, b);
@@ -68,7 +74,7 @@ __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { retu
 __device__ __forceinline__ float e16m16_mant(int q) { return __int_as_float(0x3f800000 | ((q & 0xFFFF) << 7)); }
 __device__ __forceinline__ float e16m16_log2_ratio(int aq, int bq, int llq) {
     const int e = (aq >> 16) + (bq >> 16) - (llq >> 16);
-    const float m = e16m16_mant(aq) * e16m16_mant(bq) * __frcp_rn(e16m16_mant(llq));
+    const float m = e16m16_mant(aq) * e16m16_mant(bq) * fast_rcp(e16m16_mant(llq));
     return (float)e + fast_lg2(m);
 }
 
@@ -95,14 +101,29 @@ int launch_dense_grad(const void* logits, int dtype, const int32_t* labels, cons
                       const float* lse, const int32_t* alpha, const int32_t* beta,
                       const float* grad_costs, void* grad_logits, cudaStream_t stream);
 
+// Factor planes of the factorised concat-GELU joint (joint_cg_mm.cu), V <= 128: written once per
+// step by the forward into caller memory (cg_factors_bytes), read by the cell kernels of both passes.
+struct CgFactors {
+    float* Ea;   // [B*T][Vk]   2^((P_enc - rowmax) log2e), pad columns zero
+    float* Eb;   // [B*U1][Vk]  same for P_dec
+    float* mA;   // [B*T]   row maxima, base 2
+    float* lAb;  // [B*T]   log2 Ea[.][blank] (exact: not taken from the possibly underflowed Ea)
+    float* mB;   // [B*U1]
+    float* lBb;  // [B*U1]
+    float* lBy;  // [B*U1]  log2 Eb[u][y_u], 0 for u >= U_b
+    int Vk;      // V rounded up to a multiple of 8
+};
+size_t cg_factors_bytes(int B, int T, int U1, int V);  // 0: V > 128, the generic kernels need no factors
+
+// factors == nullptr is allowed only when cg_factors_bytes(...) == 0
 int launch_cg_lse(const float* penc, const float* pdec, const int32_t* labels, const int32_t* act_lens,
                   const int32_t* label_lens, int B, int T, int U1, int V, int blank, float2* lp2,
-                  float* lse, cudaStream_t stream);
+                  float* lse, void* factors, size_t factors_bytes, cudaStream_t stream);
 int launch_cg_grad(const float* penc, const float* pdec, const int32_t* labels, const int32_t* act_lens,
                    const int32_t* label_lens, int B, int T, int U1, int V, int blank, const float* lse,
                    const int32_t* alpha, const int32_t* beta, const float* grad_costs,
                    float* d_penc, float* d_pdec, int deterministic, void* workspace,
-                   size_t workspace_bytes, cudaStream_t stream);
+                   size_t workspace_bytes, const void* factors, size_t factors_bytes, cudaStream_t stream);
 size_t cg_grad_workspace_bytes(int B, int T, int U1, int V, int deterministic);
 
 int launch_at_lse(const float* enc, const float* dec, const float* weight, const float* bias, int gemm,

@@ -16,13 +16,16 @@ namespace rnntb200 {
 // joint_cg_mm.cu: the factorised (exp(a+b) = exp(a) exp(b)) kernels used for V <= 128
 bool cg_mm_supported(int V);
 int cg_mm_tile_rows();
-int launch_cg_lse_mm(const float* penc, const float* pdec, const int32_t* labels, const int32_t* act_lens,
-                     const int32_t* label_lens, int B, int T, int U1, int V, int blank, float2* lp2,
-                     float* lse, cudaStream_t stream);
-int launch_cg_grad_mm(const float* penc, const float* pdec, const int32_t* labels, const int32_t* act_lens,
-                      const int32_t* label_lens, int B, int T, int U1, int V, int blank, const float* lse,
-                      const int32_t* alpha, const int32_t* beta, const float* grad_costs, float* d_penc,
-                      float* d_pdec, float* partial, cudaStream_t stream);
+CgFactors cg_factors_layout(void* mem, int B, int T, int U1, int V);
+int launch_cg_factor_rows(const float* penc, const float* pdec, const int32_t* labels, const int32_t* label_lens,
+                          int B, int T, int U1, int V, int blank, const CgFactors& F, cudaStream_t stream);
+int launch_cg_lse_mm(const float* penc, const float* pdec, const CgFactors& F, const int32_t* labels,
+                     const int32_t* act_lens, const int32_t* label_lens, int B, int T, int U1, int V, int blank,
+                     float2* lp2, float* lse, cudaStream_t stream);
+int launch_cg_grad_mm(const float* penc, const float* pdec, const CgFactors& F, const int32_t* labels,
+                      const int32_t* act_lens, const int32_t* label_lens, int B, int T, int U1, int V, int blank,
+                      const float* lse, const int32_t* alpha, const int32_t* beta, const float* grad_costs,
+                      float* d_penc, float* d_pdec, float* partial, cudaStream_t stream);
 
 namespace {
 
@@ -215,10 +218,16 @@ __global__ void cg_reduce_slabs_kernel(const float* __restrict__ partial, int n_
 
 int launch_cg_lse(const float* penc, const float* pdec, const int32_t* labels, const int32_t* act_lens,
                   const int32_t* label_lens, int B, int T, int U1, int V, int blank, float2* lp2,
-                  float* lse, cudaStream_t stream) {
+                  float* lse, void* factors, size_t factors_bytes, cudaStream_t stream) {
     if ((long long)B * T * U1 == 0) return RNNTB200_STATUS_SUCCESS;
-    if (cg_mm_supported(V))
-        return launch_cg_lse_mm(penc, pdec, labels, act_lens, label_lens, B, T, U1, V, blank, lp2, lse, stream);
+    if (cg_mm_supported(V)) {
+        if (!factors || factors_bytes < cg_factors_bytes(B, T, U1, V) || ((uintptr_t)factors & 15))
+            return RNNTB200_STATUS_INVALID_VALUE;
+        const CgFactors F = cg_factors_layout(factors, B, T, U1, V);
+        const int st = launch_cg_factor_rows(penc, pdec, labels, label_lens, B, T, U1, V, blank, F, stream);
+        if (st != RNNTB200_STATUS_SUCCESS) return st;
+        return launch_cg_lse_mm(penc, pdec, F, labels, act_lens, label_lens, B, T, U1, V, blank, lp2, lse, stream);
+    }
     const int Vs = V | 1;  // odd row stride: lanes reading different rows hit different banks
     const size_t smem = (size_t)(kTT + kUU) * Vs * sizeof(float);
     if (smem > 227 * 1024) return RNNTB200_STATUS_INVALID_VALUE;
@@ -243,9 +252,11 @@ int launch_cg_grad(const float* penc, const float* pdec, const int32_t* labels, 
                    const int32_t* label_lens, int B, int T, int U1, int V, int blank, const float* lse,
                    const int32_t* alpha, const int32_t* beta, const float* grad_costs,
                    float* d_penc, float* d_pdec, int deterministic, void* workspace,
-                   size_t workspace_bytes, cudaStream_t stream) {
+                   size_t workspace_bytes, const void* factors, size_t factors_bytes, cudaStream_t stream) {
     if ((long long)B * T * U1 == 0) return RNNTB200_STATUS_SUCCESS;
     const bool mm = cg_mm_supported(V);
+    if (mm && (!factors || factors_bytes < cg_factors_bytes(B, T, U1, V) || ((uintptr_t)factors & 15)))
+        return RNNTB200_STATUS_INVALID_VALUE;
     const int rows = mm ? cg_mm_tile_rows() : kGT;
     const int n_tiles = (T + rows - 1) / rows;
     float* partial = nullptr;
@@ -259,7 +270,9 @@ int launch_cg_grad(const float* penc, const float* pdec, const int32_t* labels, 
     }
     int st;
     if (mm) {
-        st = launch_cg_grad_mm(penc, pdec, labels, act_lens, label_lens, B, T, U1, V, blank, lse, alpha, beta,
+        // the forward of this step filled the factor planes for the same penc / pdec
+        const CgFactors F = cg_factors_layout(const_cast<void*>(factors), B, T, U1, V);
+        st = launch_cg_grad_mm(penc, pdec, F, labels, act_lens, label_lens, B, T, U1, V, blank, lse, alpha, beta,
                                grad_costs, d_penc, d_pdec, partial, stream);
     } else {
         const int threads = min(256, ((V + 31) / 32) * 32);

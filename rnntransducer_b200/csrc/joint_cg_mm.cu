@@ -10,14 +10,19 @@
 // with C[t,u] = grad_cost * occupancy(t,u) / S[t,u] (one exp per CELL, not per cell x vocabulary)
 // and the corrections touching only the blank column and the label column of each cell.
 // The C*V exponentials of the straightforward evaluation (76 M at B=32,T=400,U=80,V=73 -- the MUFU
-// floor of cg_lse_kernel / cg_grad_kernel) become FFMAs of three small batched GEMMs.
+// floor of cg_lse_kernel / cg_grad_kernel) become three small batched GEMMs.
+//
+// The GEMMs are per-CTA products of shared-memory tiles (32 x 64 x V, 32 x V x 48, 48 x V x 32):
+// they run as warp-level tensor-core MMAs (mma.sync m16n8k8, TF32 operands, fp32 accumulate) on
+// operands split into hi + lo TF32 halves, hi*hi + hi*lo + lo*hi (the dropped lo*lo term is 2^-22
+// relative), i.e. at fp32 accuracy.  One warp instruction replaces 1024 FFMA lanes; tcgen05 would
+// add a TMEM round trip per 32-frame tile for products this small (K = V <= 128).
 //
 // Range: A, B are in (0,1].  If the peaks of the two rows do not line up, S can be tiny; cells
 // with S < 2^-66 (logit ranges beyond ~45 nats in BOTH rows, never seen with real activations) take
 // an exact per-cell path instead (log-sum-exp with the true maximum / explicit V-wide gradient).
 //
-// Used for V <= 128 (thread tiles keep 16*NC vocabulary columns in registers); larger vocabularies
-// run the generic kernels of joint_cg.cu.
+// Used for V <= 128; larger vocabularies run the generic kernels of joint_cg.cu.
 #include "common.cuh"
 
 namespace rnntb200 {
@@ -26,120 +31,210 @@ namespace {
 
 constexpr float kTinyLog2 = -66.f;  // log2 of the partition threshold below which a cell goes exact
 
+// x = hi + lo with hi, lo representable in TF32 (round-to-nearest both times: no one-sided bias)
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+    const float r = x - __uint_as_float(hi);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+
+// D += A B, A 16x8 (row), B 8x8 (col), fp32 accumulate.  Lane (g = lane/4, q = lane%4) holds
+//   a0 = A[g][q]  a1 = A[g+8][q]  a2 = A[g][q+4]  a3 = A[g+8][q+4];  b0 = B[q][g]  b1 = B[q+4][g];
+//   d0 = D[g][2q]  d1 = D[g][2q+1]  d2 = D[g+8][2q]  d3 = D[g+8][2q+1]
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+// Factor planes (CgFactors, common.cuh): cg_factor_rows_kernel turns every row of P_enc / P_dec into
+// E = 2^((x - rowmax) log2e) (row stride Vk = V rounded up to 8, pad columns zero) ONCE per step,
+// together with the per-row scalars the cell kernels need: the row maximum (base 2), the
+// normalised base-2 log at the blank column and, for predictor rows, at the row's label (those can
+// underflow in E although they are representable -- and may lie on the best path).  The cell
+// kernels then stage tiles of E with 16-byte cp.async; no CTA repeats the exponentials (every
+// utterance's P_dec used to be re-exponentiated by each of its T/32 frame tiles).
+// One warp per row.
+__global__ void __launch_bounds__(256)
+cg_factor_rows_kernel(const float* __restrict__ penc, const float* __restrict__ pdec,
+                      const int32_t* __restrict__ labels, const int32_t* __restrict__ label_lens, int rows_enc,
+                      int rows_dec, int U1, int V, int Vk, int blank, float* __restrict__ Ea,
+                      float* __restrict__ mA, float* __restrict__ lAb, float* __restrict__ Eb,
+                      float* __restrict__ mB, float* __restrict__ lBb, float* __restrict__ lBy) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows_enc + rows_dec) return;
+    const bool is_dec = row >= rows_enc;
+    const int r = is_dec ? row - rows_enc : row;
+    const float* x = (is_dec ? pdec : penc) + (size_t)r * V;
+    float* e = (is_dec ? Eb : Ea) + (size_t)r * Vk;
+    float xv[4];  // V <= 128
+    float m = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int v = lane + 32 * i;
+        xv[i] = v < V ? __ldg(x + v) : -INFINITY;
+        m = fmaxf(m, xv[i]);
+    }
+    m = warp_max(m);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int v = lane + 32 * i;
+        if (v < Vk) e[v] = v < V ? fast_ex2((xv[i] - m) * kLog2e) : 0.f;
+    }
+    if (lane == 0) {
+        const float lb = (__ldg(x + blank) - m) * kLog2e;
+        if (!is_dec) {
+            mA[r] = m * kLog2e;
+            lAb[r] = lb;
+        } else {
+            mB[r] = m * kLog2e;
+            lBb[r] = lb;
+            const int b = r / U1, u = r - b * U1;
+            const int Ub = min(__ldg(label_lens + b), U1 - 1);
+            lBy[r] = u < Ub ? (__ldg(x + __ldg(labels + (size_t)b * (U1 - 1) + u)) - m) * kLog2e : 0.f;
+        }
+    }
+}
+
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gmem_src) : "memory");
+}
+// rows [0, n_copy) of a factor plane (row stride Vk floats) -> shared memory (row stride Vs), rows
+// [n_copy, n_rows) -> zeros.  Fire-and-forget; stage_wait + a block barrier make the tile visible.
+__device__ __forceinline__ void stage_tile(float* dst, const float* __restrict__ src, int n_copy, int n_rows, int Vk,
+                                           int Vs) {
+    const int cpr = Vk >> 2;  // 16-byte chunks per row (<= 32): one warp per row, one lane per chunk
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    if (lane < cpr) {
+        for (int r = warp; r < n_rows; r += n_warps) {
+            if (r < n_copy) cp_async_16(dst + r * Vs + 4 * lane, src + (size_t)r * Vk + 4 * lane);
+            else *reinterpret_cast<float4*>(dst + r * Vs + 4 * lane) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+// per-row scalars of the same rows (0 beyond n_copy); joins the cp.async group committed next
+__device__ __forceinline__ void stage_scalars(float* dst, const float* __restrict__ src, int n_copy, int n_rows) {
+    for (int i = threadIdx.x; i < n_rows; i += blockDim.x) {
+        if (i < n_copy) {
+            const unsigned d = (unsigned)__cvta_generic_to_shared(dst + i);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src + i) : "memory");
+        } else {
+            dst[i] = 0.f;
+        }
+    }
+}
+
 // =================================================================================================
-// forward: CTA = (utterance, 32 frames); 4 warps; warp item = 16 t x 16 u, thread = 4 t x 2 u cells
+// forward: CTA = (utterance, 32 frames), 8 warps; per 64-position chunk warp w owns the 16-frame
+// row tile (w & 1) x two 8-position column tiles (w >> 1): S = A B^T on tensor cores.
+constexpr int kFThreads = 256;
 constexpr int kFT = 32;    // frames per CTA
 constexpr int kFUC = 64;   // label positions per staged chunk
 
-__device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gmem_src) {
-    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(gmem_src) : "memory");
-}
-
-// Stage n_rows rows of src ([.., V] row-major) as E = 2^((x - rowmax) log2e).  The raw rows go to
-// shared memory with cp.async (fire-and-forget: every load of the tile is in flight at once, no
-// register dependency), then one warp per row takes the row maximum and exponentiates in place.
-// Rows >= n_valid become zeros.  Optionally records the normalised base-2 log at column `col` of
-// every row (the blank column) and at a per-row column cols[r] (the row's label): those can
-// underflow in E although they are representable -- and may lie on the best path.
-// Contains two block barriers.
-__device__ __forceinline__ void stage_rows_exp(float* dst, float* rowmax, float* log_at_col, int col,
-                                               const float* __restrict__ src, int n_rows, int n_valid,
-                                               int V, int Vs, float* log_at_cols = nullptr,
-                                               const int* cols = nullptr) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-    for (int r = warp; r < n_valid; r += n_warps)
-        for (int v = lane; v < V; v += 32) cp_async_4(dst + r * Vs + v, src + (size_t)r * V + v);
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    for (int r = n_valid + warp; r < n_rows; r += n_warps) {
-        for (int v = lane; v < V; v += 32) dst[r * Vs + v] = 0.f;
-        if (lane == 0) {
-            rowmax[r] = 0.f;
-            if (log_at_col) log_at_col[r] = 0.f;
-            if (log_at_cols) log_at_cols[r] = 0.f;
-        }
-    }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
-    for (int r = warp; r < n_valid; r += n_warps) {
-        float* d = dst + r * Vs;
-        float m = -INFINITY;
-        for (int v = lane; v < V; v += 32) m = fmaxf(m, d[v]);
-        m = warp_max(m);
-        if (lane == 0) {
-            rowmax[r] = m * kLog2e;
-            if (log_at_col) log_at_col[r] = (d[col] - m) * kLog2e;
-            if (log_at_cols) log_at_cols[r] = cols[r] >= 0 ? (d[cols[r]] - m) * kLog2e : 0.f;
-        }
-        __syncwarp();
-        for (int v = lane; v < V; v += 32) d[v] = fast_ex2((d[v] - m) * kLog2e);
-    }
-    __syncthreads();
-}
-
-__global__ void __launch_bounds__(128)
-cg_lse_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec,
+__global__ void __launch_bounds__(kFThreads)
+cg_lse_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec, const CgFactors F,
                  const int32_t* __restrict__ labels, const int32_t* __restrict__ act_lens,
-                 const int32_t* __restrict__ label_lens, int T, int U1, int V, int Vs, int blank,
+                 const int32_t* __restrict__ label_lens, int T, int U1, int V, int Vk, int Vs, int blank,
                  float2* __restrict__ lp2, float* __restrict__ lse_out) {
     extern __shared__ float smem[];
-    float* As = smem;               // [kFT][Vs]
-    float* Bs = As + kFT * Vs;      // [kFUC][Vs]
-    float* mA = Bs + kFUC * Vs;     // [kFT]   row maxima, base 2
-    float* mB = mA + kFT;           // [kFUC]
-    float* lAb = mB + kFUC;         // [kFT]   log2 A[t][blank]
-    float* lBb = lAb + kFT;         // [kFUC]  log2 B[u][blank]
-    float* lBy = lBb + kFUC;        // [kFUC]  log2 B[u][y_u]
-    __shared__ int ys[kFUC];
+    float* As = smem;                   // [kFT][Vs]   (Vs = Vk + 4: conflict-free fragment loads)
+    float* Bs0 = As + kFT * Vs;         // [2][kFUC][Vs]: the next chunk's rows land while this one is used
+    float* mA = Bs0 + 2 * kFUC * Vs;    // [kFT]      row maxima, base 2
+    float* lAb = mA + kFT;              // [kFT]      log2 A[t][blank]
+    float* sc0 = lAb + kFT;             // [2][3][kFUC]  per chunk: row maxima, log2 B[u][blank], log2 B[u][y_u]
+    __shared__ int ys0[2][kFUC];
     const int b = blockIdx.y, t0 = blockIdx.x * kFT;
     const int Tb = min(__ldg(act_lens + b), T), Ub = min(__ldg(label_lens + b), U1 - 1);
     if (t0 >= Tb) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int ty = lane >> 3, tx = lane & 7;
+    const int g = lane >> 2, q = lane & 3;
+    const int mt = warp & 1, nq = warp >> 1;
 
-    stage_rows_exp(As, mA, lAb, blank, penc + ((size_t)b * T + t0) * V, kFT, min(kFT, Tb - t0), V, Vs);
-    for (int u0 = 0; u0 <= Ub; u0 += kFUC) {
-        if (u0 > 0) __syncthreads();  // every warp is done with the previous chunk
+    // everything chunk c needs travels as one cp.async group (+ plain stores of the labels) into
+    // buffer c & 1, issued one chunk ahead
+    auto issue_chunk = [&](int c) {
+        const int u0 = c * kFUC, n = min(kFUC, Ub + 1 - u0);
+        const size_t row = (size_t)b * U1 + u0;
+        float* sc = sc0 + (c & 1) * 3 * kFUC;
+        stage_scalars(sc, F.mB + row, n, kFUC);
+        stage_scalars(sc + kFUC, F.lBb + row, n, kFUC);
+        stage_scalars(sc + 2 * kFUC, F.lBy + row, n, kFUC);
         if (threadIdx.x < kFUC) {
             const int u = u0 + threadIdx.x;
-            ys[threadIdx.x] = u < Ub ? __ldg(labels + (size_t)b * (U1 - 1) + u) : -1;
+            ys0[c & 1][threadIdx.x] = u < Ub ? __ldg(labels + (size_t)b * (U1 - 1) + u) : -1;
         }
-        __syncthreads();
-        stage_rows_exp(Bs, mB, lBb, blank, pdec + ((size_t)b * U1 + u0) * V, kFUC, min(kFUC, Ub + 1 - u0), V, Vs,
-                       lBy, ys);
-        for (int item = warp; item < (kFT / 16) * (kFUC / 16); item += 4) {
-            const int rt = (item / (kFUC / 16)) * 16 + 4 * ty;  // first of this thread's 4 frames
-            const int ru = (item % (kFUC / 16)) * 16 + 2 * tx;  // first of its 2 label positions
-            if (t0 + (item / (kFUC / 16)) * 16 >= Tb || u0 + (item % (kFUC / 16)) * 16 > Ub) continue;
-            const float* a = As + rt * Vs;
-            const float* bb = Bs + ru * Vs;
-            float s[4][2];
+        stage_tile(Bs0 + (c & 1) * kFUC * Vs, F.Eb + row * Vk, n, kFUC, Vk, Vs);
+    };
+    {
+        const int n = min(kFT, Tb - t0);
+        const size_t row = (size_t)b * T + t0;
+        stage_scalars(mA, F.mA + row, n, kFT);
+        stage_scalars(lAb, F.lAb + row, n, kFT);
+        stage_tile(As, F.Ea + row * Vk, n, kFT, Vk, Vs);
+    }
+    issue_chunk(0);
+    int chunk = 0;
+    for (int u0 = 0; u0 <= Ub; u0 += kFUC, ++chunk) {
+        const float* Bs = Bs0 + (chunk & 1) * kFUC * Vs;
+        const float* mB = sc0 + (chunk & 1) * 3 * kFUC;
+        const float* lBb = mB + kFUC;
+        const float* lBy = lBb + kFUC;
+        const int* ys = ys0[chunk & 1];
+        stage_wait();
+        __syncthreads();  // this chunk has landed; every warp is done with the previous one
+        if (u0 + kFUC <= Ub) issue_chunk(chunk + 1);
+
+        const int un0 = nq * 16;  // first position (within the chunk) of this warp's column tiles
+        if (t0 + mt * 16 >= Tb || u0 + un0 > Ub) continue;  // warp-uniform
+        const bool n_on1 = u0 + un0 + 8 <= Ub;
+        float acc[2][4], acs[2][4];  // hi*hi / the two cross terms
 #pragma unroll
-            for (int i = 0; i < 4; ++i) s[i][0] = s[i][1] = 0.f;
-#pragma unroll 4
-            for (int v = 0; v < V; ++v) {
-                const float b0 = bb[v], b1 = bb[Vs + v];
+        for (int i = 0; i < 2; ++i)
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float av = a[i * Vs + v];
-                    s[i][0] = fmaf(av, b0, s[i][0]);
-                    s[i][1] = fmaf(av, b1, s[i][1]);
-                }
+            for (int k = 0; k < 4; ++k) acc[i][k] = acs[i][k] = 0.f;
+        const float* arow = As + (mt * 16 + g) * Vs + q;
+        const float* brow = Bs + (un0 + g) * Vs + q;
+#pragma unroll 2
+        for (int k0 = 0; k0 < Vk; k0 += 8) {
+            uint32_t ah[4], al[4];
+            split_tf32(arow[k0], ah[0], al[0]);
+            split_tf32(arow[k0 + 8 * Vs], ah[1], al[1]);
+            split_tf32(arow[k0 + 4], ah[2], al[2]);
+            split_tf32(arow[k0 + 8 * Vs + 4], ah[3], al[3]);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                if (i == 1 && !n_on1) continue;
+                uint32_t bh[2], bl[2];
+                split_tf32(brow[i * 8 * Vs + k0], bh[0], bl[0]);
+                split_tf32(brow[i * 8 * Vs + k0 + 4], bh[1], bl[1]);
+                mma_tf32(acc[i], ah, bh);
+                mma_tf32(acs[i], ah, bl);
+                mma_tf32(acs[i], al, bh);
             }
+        }
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 2; ++i) {
+            if (i == 1 && !n_on1) continue;
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {
-                    const int t = t0 + rt + i, u = u0 + ru + k;
+                    const int r = mt * 16 + g + 8 * h, uu = un0 + 8 * i + 2 * q + k;
+                    const int t = t0 + r, u = u0 + uu;
                     if (t >= Tb || u > Ub) continue;
-                    const float mm = mA[rt + i] + mB[ru + k];
+                    const float mm = mA[r] + mB[uu];
                     const float* pe = penc + ((size_t)b * T + t) * V;
-                    const float* pd = pdec + ((size_t)b * U1 + u) * V;
-                    float lgs = fast_lg2(s[i][k]);
-                    const int y = u < Ub ? ys[ru + k] : blank;
+                    float lgs = fast_lg2(acc[i][2 * h + k] + acs[i][2 * h + k]);
+                    const int y = u < Ub ? ys[uu] : blank;
                     float lb2, ll2;
                     if (lgs < kTinyLog2) {
                         // exact path: the row peaks do not line up, redo this cell in the log domain
+                        const float* pd = pdec + ((size_t)b * U1 + u) * V;
                         float mx = -INFINITY;
                         for (int v = 0; v < V; ++v) mx = fmaxf(mx, (pe[v] + pd[v]) * kLog2e);
                         float se = 0.f;
@@ -148,10 +243,10 @@ cg_lse_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec,
                     }
                     // blank / label log-probs straight in the log domain (A * B would underflow
                     // below 2^-126 although such steps are representable -- and may be on the path)
-                    lb2 = lAb[rt + i] + lBb[ru + k] - lgs;
-                    const float ay = a[i * Vs + y];  // A[t][y]: its log unless it underflowed
-                    const float lay = ay > 1e-30f ? fast_lg2(ay) : __ldg(pe + y) * kLog2e - mA[rt + i];
-                    ll2 = lay + lBy[ru + k] - lgs;
+                    lb2 = lAb[r] + lBb[uu] - lgs;
+                    const float ay = As[r * Vs + y];  // A[t][y]: its log unless it underflowed
+                    const float lay = ay > 1e-30f ? fast_lg2(ay) : __ldg(pe + y) * kLog2e - mA[r];
+                    ll2 = lay + lBy[uu] - lgs;
                     const size_t c = ((size_t)b * T + t) * U1 + u;
                     lp2[c] = make_float2(fmaxf(lb2 * kLn2, kNegInf), u < Ub ? fmaxf(ll2 * kLn2, kNegInf) : 0.f);
                     lse_out[c] = (mm + lgs) * kLn2;
@@ -161,83 +256,111 @@ cg_lse_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec,
 }
 
 // =================================================================================================
-// backward: CTA = (utterance, 32 frames), 128 threads as 8 (ty) x 16 (tx); thread tile for
-// E = C B: frames 4ty..4ty+3 x columns tx + 16c; for D = C^T A: positions ty + 8i x the same columns.
-// The blank / label corrections ride along as rank-1 style terms with a fixed summation order, so
-// the only order-dependent arithmetic is the cross-tile accumulation of d_pdec (fp32 atomics, or
-// per-tile slabs + a fixed-order reduction in deterministic mode) and the cold exact path.
+// backward: CTA = (utterance, 32 frames), 8 warps.  Per 48-position chunk: the per-cell scalars
+// (C and the blank / label corrections) go to shared memory, then on tensor cores
+//   E += C B     (32 x Vk, K = 48 positions; warp w: row tile w & 1, column quarter w >> 1; the
+//                 accumulators stay in registers across the chunks)
+//   D  = C^T A   (48 x Vk, K = 32 frames; warp w: its column quarter, row tiles 0, 2 or 1)
+// and d_pdec += B .* D - corrections.  The corrections ride along as rank-1 style terms with a fixed
+// summation order, so the only order-dependent arithmetic is the cross-tile accumulation of d_pdec
+// (fp32 atomics, or per-tile slabs + a fixed-order reduction in deterministic mode) and the cold
+// exact path.
 constexpr int kGT2 = 32;   // frames per CTA
-constexpr int kGUC2 = 48;  // label positions per chunk (6 per thread row group)
-constexpr int kCs = kGUC2 + 1;
-constexpr int kCellsPerThread = kGT2 * kGUC2 / 128;  // 12
-constexpr int kBatch = 4;  // cells whose global loads are in flight together
+constexpr int kGUC2 = 48;  // label positions per chunk
+constexpr int kGThreads = 256;
+constexpr int kCs = 52;    // row stride of the C plane (4 mod 8: conflict-free A fragments of C B)
+constexpr int kCc = 49;    // row stride of the two correction planes (odd: column walks are conflict-free)
+constexpr int kCellsPerThread = kGT2 * kGUC2 / kGThreads;  // 6
+constexpr int kBatch = 3;  // cells whose global loads are in flight together
 
-template <int NC>
-__global__ void __launch_bounds__(128)
-cg_grad_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec,
+template <int NTW>  // 8-column tiles per warp: ceil(Vk / 32)
+__global__ void __launch_bounds__(kGThreads, 3)
+cg_grad_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec, const CgFactors F,
                   const int32_t* __restrict__ labels, const int32_t* __restrict__ act_lens,
-                  const int32_t* __restrict__ label_lens, int T, int U1, int V, int Vs, int blank,
+                  const int32_t* __restrict__ label_lens, int T, int U1, int V, int Vk, int Vs, int blank,
                   const float* __restrict__ lse, const int32_t* __restrict__ alpha,
                   const int32_t* __restrict__ beta, const float* __restrict__ grad_costs,
                   float* __restrict__ d_penc, float* __restrict__ d_pdec,
                   float* __restrict__ partial /* deterministic slabs or null */) {
     extern __shared__ float smem[];
-    float* As = smem;                  // [32][Vs]  A = 2^(P_enc - max)
-    float* Bs = As + kGT2 * Vs;        // [48][Vs]  B chunk
-    float* Xs = Bs + kGUC2 * Vs;       // [32][Vs]  corrections of d_penc: -(blank, label terms) (+ exact path)
-    float* Cs = Xs + kGT2 * Vs;        // [32][49]  C chunk
+    float* As = smem;                  // [32][Vs]  A = 2^(P_enc - max)   (Vs = 8 mod 16: conflict-free B fragments)
+    float* Bs0 = As + kGT2 * Vs;       // [2][48][Vs]  B chunk, double-buffered (next chunk lands during this one)
+    float* Xs = Bs0 + 2 * kGUC2 * Vs;  // [32][Vk]  corrections of d_penc: -(blank, label terms) (+ exact path)
+    float* Cs = Xs + kGT2 * Vk;        // [32][52]  C chunk
     float* CBs = Cs + kGT2 * kCs;      // [32][49]  blank corrections
-    float* CLs = CBs + kGT2 * kCs;     // [32][49]  label corrections
-    float* mA = CLs + kGT2 * kCs;      // [32] row maxima (base 2)
-    float* mB = mA + kGT2;             // [48]
-    float* lAb = mB + kGUC2;           // [32] log2 A[t][blank]
-    float* lBb = lAb + kGT2;           // [48] log2 B[u][blank]
-    float* ub = lBb + kGUC2;           // [48] sum_t corr_blank
+    float* CLs = CBs + kGT2 * kCc;     // [32][49]  label corrections
+    float* mA = CLs + kGT2 * kCc;      // [32] row maxima (base 2)
+    float* lAb = mA + kGT2;            // [32] log2 A[t][blank]
+    float* sc0 = lAb + kGT2;           // [2][3][48] per chunk: row maxima, log2 B[u][blank], log2 B[u][y_u]
+    float* ub = sc0 + 6 * kGUC2;       // [48] sum_t corr_blank
     float* ul = ub + kGUC2;            // [48] sum_t corr_label
-    float* rb = ul + kGUC2;            // [32] sum_u corr_blank (all chunks)
-    float* lBy = rb + kGT2;            // [48] log2 B[u][y_u]
-    __shared__ int ys[kGUC2];
+    __shared__ int ys0[2][kGUC2];
     __shared__ int n_exact;
 
     const int b = blockIdx.y, tile = blockIdx.x, t0 = tile * kGT2;
     const int Tb = min(__ldg(act_lens + b), T), Ub = min(__ldg(label_lens + b), U1 - 1);
     const int n_tiles = gridDim.x;
     float* slab = partial ? partial + ((size_t)b * n_tiles + tile) * U1 * V : nullptr;
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    const int mt = warp & 1;                 // 16-frame row tile of E
+    const int nt0 = (warp >> 1) * NTW;       // first 8-column tile of this warp (column quarter)
+    const int n_nt = Vk >> 3;                // column tiles in use
 
     if (t0 >= Tb) {  // tile entirely in the padding: exact zeros
-        for (int i = tid; i < kGT2 * V; i += 128) {
+        for (int i = tid; i < kGT2 * V; i += kGThreads) {
             const int r = i / V, v = i - r * V;
             if (t0 + r < T) d_penc[((size_t)b * T + t0 + r) * V + v] = 0.f;
         }
         if (slab)
-            for (int i = tid; i < U1 * V; i += 128) slab[i] = 0.f;
+            for (int i = tid; i < U1 * V; i += kGThreads) slab[i] = 0.f;
         return;
     }
     const float gc = grad_costs[b];
     const int llq = beta[(size_t)b * T * U1];  // beta(0,0) = P(y|x), e16m16
     const int rows_t = min(kGT2, Tb - t0);
 
-    for (int i = tid; i < kGT2 * Vs; i += 128) Xs[i] = 0.f;
+    for (int i = tid; i < kGT2 * Vk; i += kGThreads) Xs[i] = 0.f;
     if (tid == 0) n_exact = 0;
-    stage_rows_exp(As, mA, lAb, blank, penc + ((size_t)b * T + t0) * V, kGT2, rows_t, V, Vs);
-
-    float E[4][NC];  // (C B)[t][v]
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int c = 0; c < NC; ++c) E[i][c] = 0.f;
-
-    for (int u0 = 0; u0 < U1; u0 += kGUC2) {
-        if (!slab && u0 > Ub) break;  // nothing left to add (slabs must be written in full)
-        const int rows_u = max(0, min(kGUC2, Ub + 1 - u0));
-        if (u0 > 0) __syncthreads();  // previous chunk fully consumed
+    auto issue_chunk = [&](int c) {  // everything chunk c needs, into buffer c & 1, one chunk ahead
+        const int u0 = c * kGUC2, n = max(0, min(kGUC2, Ub + 1 - u0));
+        const size_t row = (size_t)b * U1 + u0;
+        float* sc = sc0 + (c & 1) * 3 * kGUC2;
+        stage_scalars(sc, F.mB + row, n, kGUC2);
+        stage_scalars(sc + kGUC2, F.lBb + row, n, kGUC2);
+        stage_scalars(sc + 2 * kGUC2, F.lBy + row, n, kGUC2);
         if (tid < kGUC2) {
             const int u = u0 + tid;
-            ys[tid] = u < Ub ? __ldg(labels + (size_t)b * (U1 - 1) + u) : -1;
+            ys0[c & 1][tid] = u < Ub ? __ldg(labels + (size_t)b * (U1 - 1) + u) : -1;
         }
-        __syncthreads();  // ys visible to the staging warps
-        stage_rows_exp(Bs, mB, lBb, blank, pdec + ((size_t)b * U1 + u0) * V, kGUC2, rows_u, V, Vs, lBy, ys);
+        stage_tile(Bs0 + (c & 1) * kGUC2 * Vs, F.Eb + row * Vk, n, kGUC2, Vk, Vs);
+    };
+    {
+        const size_t row = (size_t)b * T + t0;
+        stage_scalars(mA, F.mA + row, rows_t, kGT2);
+        stage_scalars(lAb, F.lAb + row, rows_t, kGT2);
+        stage_tile(As, F.Ea + row * Vk, rows_t, kGT2, Vk, Vs);
+    }
+    issue_chunk(0);
+    int chunk = 0;
+
+    float E[NTW][4];  // (C B)[t][v] fragments
+#pragma unroll
+    for (int i = 0; i < NTW; ++i)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) E[i][k] = 0.f;
+
+    for (int u0 = 0; u0 < U1; u0 += kGUC2, ++chunk) {
+        if (!slab && u0 > Ub) break;  // nothing left to add (slabs must be written in full)
+        const int rows_u = max(0, min(kGUC2, Ub + 1 - u0));
+        const float* Bs = Bs0 + (chunk & 1) * kGUC2 * Vs;
+        const float* mB = sc0 + (chunk & 1) * 3 * kGUC2;
+        const float* lBb = mB + kGUC2;
+        const float* lBy = lBb + kGUC2;
+        const int* ys = ys0[chunk & 1];
+        stage_wait();
+        __syncthreads();  // this chunk has landed; the previous one is fully consumed
+        if (u0 + kGUC2 < U1 && (slab || u0 + kGUC2 <= Ub)) issue_chunk(chunk + 1);
 
         // per-cell scalars of the (32 x 48) block: C and the two corrections.  The global loads of
         // kBatch cells are issued together before any of them is used.
@@ -246,47 +369,47 @@ cg_grad_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec
             int aq[kBatch], bq[kBatch], bdn[kBatch], brt[kBatch];
             float z2[kBatch], pey[kBatch];
 #pragma unroll
-            for (int q = 0; q < kBatch; ++q) {
-                const int i = tid + 128 * (q0 + q), r = i / kGUC2, uu = i - r * kGUC2;
+            for (int qq = 0; qq < kBatch; ++qq) {
+                const int i = tid + kGThreads * (q0 + qq), r = i / kGUC2, uu = i - r * kGUC2;
                 const int t = t0 + r, u = u0 + uu;
-                aq[q] = bq[q] = bdn[q] = brt[q] = 0;
-                z2[q] = pey[q] = 0.f;
+                aq[qq] = bq[qq] = bdn[qq] = brt[qq] = 0;
+                z2[qq] = pey[qq] = 0.f;
                 if (t < Tb && u <= Ub) {
                     const size_t c = ((size_t)b * T + t) * U1 + u;
-                    aq[q] = alpha[c];
-                    bq[q] = beta[c];
-                    if (t < Tb - 1) bdn[q] = beta[c + U1];
+                    aq[qq] = alpha[c];
+                    bq[qq] = beta[c];
+                    if (t < Tb - 1) bdn[qq] = beta[c + U1];
                     if (u < Ub) {
-                        brt[q] = beta[c + 1];
+                        brt[qq] = beta[c + 1];
                         const float ay = As[r * Vs + ys[uu]];  // log2 A[t][y_u]; gather if it underflowed
-                        pey[q] = ay > 1e-30f ? fast_lg2(ay)
-                                             : __ldg(penc + ((size_t)b * T + t) * V + ys[uu]) * kLog2e - mA[r];
+                        pey[qq] = ay > 1e-30f ? fast_lg2(ay)
+                                              : __ldg(penc + ((size_t)b * T + t) * V + ys[uu]) * kLog2e - mA[r];
                     }
-                    z2[q] = lse[c] * kLog2e;
+                    z2[qq] = lse[c] * kLog2e;
                 }
             }
 #pragma unroll
-            for (int q = 0; q < kBatch; ++q) {
-                const int i = tid + 128 * (q0 + q), r = i / kGUC2, uu = i - r * kGUC2;
+            for (int qq = 0; qq < kBatch; ++qq) {
+                const int i = tid + kGThreads * (q0 + qq), r = i / kGUC2, uu = i - r * kGUC2;
                 const int t = t0 + r, u = u0 + uu;
                 float cval = 0.f, cb = 0.f, cl = 0.f;
                 if (t < Tb && u <= Ub) {
                     const float mm = mA[r] + mB[uu];
-                    const float shift = mm - z2[q];  // -log2 S(t,u)
+                    const float shift = mm - z2[qq];  // -log2 S(t,u)
                     if (shift > -kTinyLog2) atomicAdd(&n_exact, 1);  // C = 0: handled by the exact path
-                    else cval = gc * fast_ex2(e16m16_log2_ratio(aq[q], bq[q], llq) + shift);
+                    else cval = gc * fast_ex2(e16m16_log2_ratio(aq[qq], bq[qq], llq) + shift);
                     // log-domain p(blank), p(label): representable far below 2^-126
                     const float lb2 = lAb[r] + lBb[uu] + shift;
-                    if (t < Tb - 1) cb = gc * fast_ex2(e16m16_log2_ratio(aq[q], bdn[q], llq) + lb2);
-                    else if (u == Ub) cb = gc * fast_ex2(e16m16_log2_ratio(aq[q], 0, llq) + lb2);
+                    if (t < Tb - 1) cb = gc * fast_ex2(e16m16_log2_ratio(aq[qq], bdn[qq], llq) + lb2);
+                    else if (u == Ub) cb = gc * fast_ex2(e16m16_log2_ratio(aq[qq], 0, llq) + lb2);
                     if (u < Ub) {
-                        const float ll2 = pey[q] + lBy[uu] + shift;
-                        cl = gc * fast_ex2(e16m16_log2_ratio(aq[q], brt[q], llq) + ll2);
+                        const float ll2 = pey[qq] + lBy[uu] + shift;
+                        cl = gc * fast_ex2(e16m16_log2_ratio(aq[qq], brt[qq], llq) + ll2);
                     }
                 }
                 Cs[r * kCs + uu] = cval;
-                CBs[r * kCs + uu] = cb;
-                CLs[r * kCs + uu] = cl;
+                CBs[r * kCc + uu] = cb;
+                CLs[r * kCc + uu] = cl;
             }
         }
         __syncthreads();
@@ -294,73 +417,105 @@ cg_grad_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec
         // label column of every position: one thread per frame walks the positions sequentially
         // (two positions may share a label, so this must not be a parallel scatter).
         if (tid < kGT2) {
-            float* xr = Xs + tid * Vs;
+            float* xr = Xs + tid * Vk;
             float sb = 0.f;
             for (int uu = 0; uu < rows_u; ++uu) {
-                sb += CBs[tid * kCs + uu];
+                sb += CBs[tid * kCc + uu];
                 const int y = ys[uu];
-                if (y >= 0) xr[y] -= CLs[tid * kCs + uu];
+                if (y >= 0) xr[y] -= CLs[tid * kCc + uu];
             }
             xr[blank] -= sb;
         } else if (tid >= 64 && tid < 64 + kGUC2) {
             const int uu = tid - 64;
             float sb = 0.f, sl = 0.f;
-            for (int r = 0; r < kGT2; ++r) { sb += CBs[r * kCs + uu]; sl += CLs[r * kCs + uu]; }
+            for (int r = 0; r < kGT2; ++r) { sb += CBs[r * kCc + uu]; sl += CLs[r * kCc + uu]; }
             ub[uu] = sb;
             ul[uu] = sl;
         }
-        // E += C B   (K = label positions of the chunk)
-        for (int uu = 0; uu < rows_u; ++uu) {
-            float bv[NC];
+        // E += C B   (K = label positions of the chunk; rows of C / B beyond rows_u are zeros)
+        {
+            const float* crow = Cs + (mt * 16 + g) * kCs + q;
+#pragma unroll 2
+            for (int k0 = 0; k0 < kGUC2; k0 += 8) {
+                if (k0 >= rows_u) break;
+                uint32_t ah[4], al[4];
+                split_tf32(crow[k0], ah[0], al[0]);
+                split_tf32(crow[k0 + 8 * kCs], ah[1], al[1]);
+                split_tf32(crow[k0 + 4], ah[2], al[2]);
+                split_tf32(crow[k0 + 8 * kCs + 4], ah[3], al[3]);
+                const float* bcol = Bs + (k0 + q) * Vs + nt0 * 8 + g;
 #pragma unroll
-            for (int c = 0; c < NC; ++c) bv[c] = Bs[uu * Vs + tx + 16 * c];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float cv = Cs[(4 * ty + i) * kCs + uu];
-#pragma unroll
-                for (int c = 0; c < NC; ++c) E[i][c] = fmaf(cv, bv[c], E[i][c]);
-            }
-        }
-        // D = C^T A   (K = frames of the tile), then d_pdec partial = B .* D - corrections
-        float D[6][NC];
-#pragma unroll
-        for (int i = 0; i < 6; ++i)
-#pragma unroll
-            for (int c = 0; c < NC; ++c) D[i][c] = 0.f;
-        for (int r = 0; r < rows_t; ++r) {
-            float av[NC];
-#pragma unroll
-            for (int c = 0; c < NC; ++c) av[c] = As[r * Vs + tx + 16 * c];
-#pragma unroll
-            for (int i = 0; i < 6; ++i) {
-                const float cv = Cs[r * kCs + ty + 8 * i];
-#pragma unroll
-                for (int c = 0; c < NC; ++c) D[i][c] = fmaf(cv, av[c], D[i][c]);
+                for (int i = 0; i < NTW; ++i) {
+                    if (nt0 + i >= n_nt) continue;
+                    uint32_t bh[2], bl[2];
+                    split_tf32(bcol[8 * i], bh[0], bl[0]);
+                    split_tf32(bcol[8 * i + 4 * Vs], bh[1], bl[1]);
+                    mma_tf32(E[i], ah, bh);
+                    mma_tf32(E[i], ah, bl);
+                    mma_tf32(E[i], al, bh);
+                }
             }
         }
         __syncthreads();  // ub / ul are complete
+        // D = C^T A   (K = frames of the tile), then d_pdec partial = B .* D - corrections
+#pragma unroll 1
+        for (int m0 = mt * 16; m0 < kGUC2; m0 += 32) {  // row tiles 0, 2 (even warps) / 1 (odd warps)
+            if (!slab && m0 >= rows_u) break;
+            float D[NTW][4];
 #pragma unroll
-        for (int i = 0; i < 6; ++i) {
-            const int uu = ty + 8 * i, u = u0 + uu;
-            if (u >= U1) continue;
+            for (int i = 0; i < NTW; ++i)
 #pragma unroll
-            for (int c = 0; c < NC; ++c) {
-                const int v = tx + 16 * c;
-                if (v >= V) continue;
-                float g = 0.f;
-                if (uu < rows_u) {
-                    g = Bs[uu * Vs + v] * D[i][c];
-                    if (v == blank) g -= ub[uu];
-                    if (v == ys[uu]) g -= ul[uu];
+                for (int k = 0; k < 4; ++k) D[i][k] = 0.f;
+            if (m0 < rows_u) {
+#pragma unroll 2
+                for (int k0 = 0; k0 < kGT2; k0 += 8) {
+                    if (k0 >= rows_t) break;
+                    const float* ccol = Cs + (k0 + q) * kCs + m0 + g;  // (C^T)[u][t] = C[t][u]
+                    uint32_t ah[4], al[4];
+                    split_tf32(ccol[0], ah[0], al[0]);
+                    split_tf32(ccol[8], ah[1], al[1]);
+                    split_tf32(ccol[4 * kCs], ah[2], al[2]);
+                    split_tf32(ccol[4 * kCs + 8], ah[3], al[3]);
+                    const float* acol = As + (k0 + q) * Vs + nt0 * 8 + g;
+#pragma unroll
+                    for (int i = 0; i < NTW; ++i) {
+                        if (nt0 + i >= n_nt) continue;
+                        uint32_t bh[2], bl[2];
+                        split_tf32(acol[8 * i], bh[0], bl[0]);
+                        split_tf32(acol[8 * i + 4 * Vs], bh[1], bl[1]);
+                        mma_tf32(D[i], ah, bh);
+                        mma_tf32(D[i], ah, bl);
+                        mma_tf32(D[i], al, bh);
+                    }
                 }
-                if (slab) slab[(size_t)u * V + v] = g;  // exact-path cells are added below
-                else if (uu < rows_u) atomicAdd(d_pdec + ((size_t)b * U1 + u) * V + v, g);
+            }
+#pragma unroll
+            for (int i = 0; i < NTW; ++i) {
+                if (nt0 + i >= n_nt) continue;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int uu = m0 + g + 8 * h, u = u0 + uu;
+                    if (u >= U1) continue;
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        const int v = (nt0 + i) * 8 + 2 * q + k;
+                        if (v >= V) continue;
+                        float gv = 0.f;
+                        if (uu < rows_u) {
+                            gv = Bs[uu * Vs + v] * D[i][2 * h + k];
+                            if (v == blank) gv -= ub[uu];
+                            if (v == ys[uu]) gv -= ul[uu];
+                        }
+                        if (slab) slab[(size_t)u * V + v] = gv;  // exact-path cells are added below
+                        else if (uu < rows_u) atomicAdd(d_pdec + ((size_t)b * U1 + u) * V + v, gv);
+                    }
+                }
             }
         }
         // exact path (cold): cells whose partition underflows the factorised form
         if (n_exact > 0) {  // uniform: n_exact was final at the barrier above
             __syncthreads();  // slab writes of this chunk are complete
-            for (int i = tid; i < kGT2 * kGUC2; i += 128) {
+            for (int i = tid; i < kGT2 * kGUC2; i += kGThreads) {
                 const int r = i / kGUC2, uu = i - r * kGUC2;
                 const int t = t0 + r, u = u0 + uu;
                 if (t >= Tb || u > Ub) continue;
@@ -371,10 +526,10 @@ cg_grad_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec
                 const float* pe = penc + ((size_t)b * T + t) * V;
                 const float* pd = pdec + ((size_t)b * U1 + u) * V;
                 for (int v = 0; v < V; ++v) {
-                    const float g = gc * fast_ex2((pe[v] + pd[v]) * kLog2e + occ);
-                    atomicAdd(Xs + r * Vs + v, g);
-                    if (slab) atomicAdd(slab + (size_t)u * V + v, g);
-                    else atomicAdd(d_pdec + ((size_t)b * U1 + u) * V + v, g);
+                    const float gg = gc * fast_ex2((pe[v] + pd[v]) * kLog2e + occ);
+                    atomicAdd(Xs + r * Vk + v, gg);
+                    if (slab) atomicAdd(slab + (size_t)u * V + v, gg);
+                    else atomicAdd(d_pdec + ((size_t)b * U1 + u) * V + v, gg);
                 }
             }
         }
@@ -382,30 +537,37 @@ cg_grad_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec
     __syncthreads();
     // d_penc = A .* E + corrections (+ exact-path cells); padded rows come out as zeros
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int r = 4 * ty + i;
-        if (t0 + r >= T) continue;
+    for (int i = 0; i < NTW; ++i) {
+        if (nt0 + i >= n_nt) continue;
 #pragma unroll
-        for (int c = 0; c < NC; ++c) {
-            const int v = tx + 16 * c;
-            if (v >= V) continue;
-            d_penc[((size_t)b * T + t0 + r) * V + v] = fmaf(As[r * Vs + v], E[i][c], Xs[r * Vs + v]);
+        for (int h = 0; h < 2; ++h) {
+            const int r = mt * 16 + g + 8 * h;
+            if (t0 + r >= T) continue;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int v = (nt0 + i) * 8 + 2 * q + k;
+                if (v >= V) continue;
+                d_penc[((size_t)b * T + t0 + r) * V + v] = fmaf(As[r * Vs + v], E[i][2 * h + k], Xs[r * Vk + v]);
+            }
         }
     }
 }
 
-template <int NC>
-int launch_grad_mm(const float* penc, const float* pdec, const int32_t* labels, const int32_t* act_lens,
-                   const int32_t* label_lens, int B, int T, int U1, int V, int blank, const float* lse,
-                   const int32_t* alpha, const int32_t* beta, const float* grad_costs, float* d_penc,
-                   float* d_pdec, float* partial, cudaStream_t stream) {
-    const int Vs = V | 1;
-    const size_t smem = ((size_t)(2 * kGT2 + kGUC2) * Vs + 3 * kGT2 * kCs + 3 * kGT2 + 5 * kGUC2) * sizeof(float);
-    cudaError_t e = cudaFuncSetAttribute(cg_grad_mm_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+inline int grad_row_stride(int Vk) { return (Vk & 15) == 8 ? Vk : Vk + 8; }  // 8 mod 16
+
+template <int NTW>
+int launch_grad_mm(const float* penc, const float* pdec, const CgFactors& F, const int32_t* labels,
+                   const int32_t* act_lens, const int32_t* label_lens, int B, int T, int U1, int V, int blank,
+                   const float* lse, const int32_t* alpha, const int32_t* beta, const float* grad_costs,
+                   float* d_penc, float* d_pdec, float* partial, cudaStream_t stream) {
+    const int Vk = F.Vk, Vs = grad_row_stride(Vk);
+    const size_t smem = ((size_t)(kGT2 + 2 * kGUC2) * Vs + kGT2 * Vk + kGT2 * (kCs + 2 * kCc) + 2 * kGT2 + 8 * kGUC2) *
+                        sizeof(float);  // 74.5 KiB at V = 73: three CTAs per SM, the whole cfg-2 grid in one wave
+    cudaError_t e = cudaFuncSetAttribute(cg_grad_mm_kernel<NTW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return status_from_cuda(e);
     dim3 grid((T + kGT2 - 1) / kGT2, B);
-    cg_grad_mm_kernel<NC><<<grid, 128, smem, stream>>>(penc, pdec, labels, act_lens, label_lens, T, U1, V, Vs,
-                                                      blank, lse, alpha, beta, grad_costs, d_penc, d_pdec, partial);
+    cg_grad_mm_kernel<NTW><<<grid, kGThreads, smem, stream>>>(penc, pdec, F, labels, act_lens, label_lens, T, U1, V, Vk, Vs,
+                                                       blank, lse, alpha, beta, grad_costs, d_penc, d_pdec, partial);
     return launch_status();
 }
 
@@ -414,31 +576,60 @@ int launch_grad_mm(const float* penc, const float* pdec, const int32_t* labels, 
 bool cg_mm_supported(int V) { return V <= 128; }
 int cg_mm_tile_rows() { return kGT2; }
 
-int launch_cg_lse_mm(const float* penc, const float* pdec, const int32_t* labels, const int32_t* act_lens,
-                     const int32_t* label_lens, int B, int T, int U1, int V, int blank, float2* lp2,
-                     float* lse, cudaStream_t stream) {
-    const int Vs = V | 1;
-    const size_t smem = ((size_t)(kFT + kFUC) * Vs + 2 * kFT + 3 * kFUC) * sizeof(float);
+// factor planes: E_enc [B*T][Vk], E_dec [B*U1][Vk], then the per-row scalars
+size_t cg_factors_bytes(int B, int T, int U1, int V) {
+    if (!cg_mm_supported(V)) return 0;
+    const size_t Vk = (V + 7) & ~7, re = (size_t)B * T, rd = (size_t)B * U1;
+    return ((re + rd) * Vk + 2 * re + 3 * rd) * sizeof(float);
+}
+
+CgFactors cg_factors_layout(void* mem, int B, int T, int U1, int V) {
+    const size_t Vk = (V + 7) & ~7, re = (size_t)B * T, rd = (size_t)B * U1;
+    float* p = static_cast<float*>(mem);
+    CgFactors F;
+    F.Vk = (int)Vk;
+    F.Ea = p;
+    F.Eb = p + re * Vk;
+    F.mA = F.Eb + rd * Vk;
+    F.lAb = F.mA + re;
+    F.mB = F.lAb + re;
+    F.lBb = F.mB + rd;
+    F.lBy = F.lBb + rd;
+    return F;
+}
+
+int launch_cg_factor_rows(const float* penc, const float* pdec, const int32_t* labels, const int32_t* label_lens,
+                          int B, int T, int U1, int V, int blank, const CgFactors& F, cudaStream_t stream) {
+    const int rows = B * (T + U1);
+    if (rows == 0) return RNNTB200_STATUS_SUCCESS;
+    cg_factor_rows_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(penc, pdec, labels, label_lens, B * T, B * U1, U1, V,
+                                                             F.Vk, blank, F.Ea, F.mA, F.lAb, F.Eb, F.mB, F.lBb, F.lBy);
+    return launch_status();
+}
+
+int launch_cg_lse_mm(const float* penc, const float* pdec, const CgFactors& F, const int32_t* labels,
+                     const int32_t* act_lens, const int32_t* label_lens, int B, int T, int U1, int V, int blank,
+                     float2* lp2, float* lse, cudaStream_t stream) {
+    const int Vk = F.Vk, Vs = Vk + 4;
+    const size_t smem = ((size_t)(kFT + 2 * kFUC) * Vs + 2 * kFT + 6 * kFUC) * sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(cg_lse_mm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return status_from_cuda(e);
     dim3 grid((T + kFT - 1) / kFT, B);
-    cg_lse_mm_kernel<<<grid, 128, smem, stream>>>(penc, pdec, labels, act_lens, label_lens, T, U1, V, Vs, blank,
+    cg_lse_mm_kernel<<<grid, kFThreads, smem, stream>>>(penc, pdec, F, labels, act_lens, label_lens, T, U1, V, Vk, Vs, blank,
                                                   lp2, lse);
     return launch_status();
 }
 
-int launch_cg_grad_mm(const float* penc, const float* pdec, const int32_t* labels, const int32_t* act_lens,
-                      const int32_t* label_lens, int B, int T, int U1, int V, int blank, const float* lse,
-                      const int32_t* alpha, const int32_t* beta, const float* grad_costs, float* d_penc,
-                      float* d_pdec, float* partial, cudaStream_t stream) {
-#define RNNT_MM(NC)                                                                                      \
-    return launch_grad_mm<NC>(penc, pdec, labels, act_lens, label_lens, B, T, U1, V, blank, lse, alpha,  \
-                              beta, grad_costs, d_penc, d_pdec, partial, stream)
-    if (V <= 16) RNNT_MM(1);
-    if (V <= 32) RNNT_MM(2);
-    if (V <= 48) RNNT_MM(3);
-    if (V <= 80) RNNT_MM(5);
-    RNNT_MM(8);
+int launch_cg_grad_mm(const float* penc, const float* pdec, const CgFactors& F, const int32_t* labels,
+                      const int32_t* act_lens, const int32_t* label_lens, int B, int T, int U1, int V, int blank,
+                      const float* lse, const int32_t* alpha, const int32_t* beta, const float* grad_costs,
+                      float* d_penc, float* d_pdec, float* partial, cudaStream_t stream) {
+#define RNNT_MM(NTW)                                                                                         \
+    return launch_grad_mm<NTW>(penc, pdec, F, labels, act_lens, label_lens, B, T, U1, V, blank, lse, alpha, \
+                               beta, grad_costs, d_penc, d_pdec, partial, stream)
+    if (V <= 32) RNNT_MM(1);
+    if (V <= 96) RNNT_MM(3);
+    RNNT_MM(4);
 #undef RNNT_MM
 }
 

@@ -51,8 +51,9 @@ __host__ __device__ inline SmemP smem_layout_p(int NB) {
 
 __device__ __forceinline__ float gelu_tanh(float x) {
     // 0.5 x (1 + tanh(y)) = x * sigmoid(2y),  y = sqrt(2/pi) (x + 0.044715 x^3)
-    const float y2 = 1.5957691216057308f * fmaf(0.044715f * x * x, x, x);  // 2y
-    return x * __frcp_rn(1.f + fast_ex2(-y2 * kLog2e));
+    // -2y log2(e) = x (c0 + c1 x^2); ex2 overflows to +inf for very negative x and the reciprocal is then 0
+    const float a = x * fmaf(-0.10294324f, x * x, -2.3022082f);
+    return x * fast_rcp(1.f + fast_ex2(a));
 }
 
 __device__ __forceinline__ void split_store(float a, float b, uint32_t& hi, uint32_t& lo) {

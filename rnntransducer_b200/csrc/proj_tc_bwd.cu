@@ -58,8 +58,8 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
 
 // sigmoid(2y), y = sqrt(2/pi)(x + 0.044715 x^3):  gelu = x s,  gelu' = s + x s (1 - s) d(2y)/dx
 __device__ __forceinline__ float gelu_sig(float x) {
-    const float y2 = 1.5957691216057308f * fmaf(0.044715f * x * x, x, x);
-    return __frcp_rn(1.f + fast_ex2(-y2 * kLog2e));
+    const float a = x * fmaf(-0.10294324f, x * x, -2.3022082f);  // -2y log2(e)
+    return fast_rcp(1.f + fast_ex2(a));
 }
 __device__ __forceinline__ float gelu_val(float x) { return x * gelu_sig(x); }
 __device__ __forceinline__ float gelu_grad(float x) {

@@ -121,21 +121,26 @@ class _ConcatGeluRNNT(torch.autograd.Function):
         lse = torch.empty(B, T, U1, **f32)
         alpha, beta = (torch.empty(B, T, U1, device=penc.device, dtype=torch.int32) for _ in range(2))
         lib = _lib.load()
+        # factor planes (exp of the projections, once per step): written here, read again by the backward
+        fac_bytes = lib.rnntb200_joint_cg_factors_bytes(B, T, U1, V)
+        factors = torch.empty(fac_bytes, dtype=torch.uint8, device=penc.device)
         with torch.cuda.device(penc.device):
             _lib.check(lib.rnntb200_joint_cg_fwd(
                 _ptr(penc), _ptr(pdec), _ptr(labels), _ptr(act_lens), _ptr(label_lens), B, T, U1, V,
-                blank, _ptr(costs), _ptr(lp2), _ptr(lse), _ptr(alpha), _ptr(beta), _stream()),
+                blank, _ptr(costs), _ptr(lp2), _ptr(lse), _ptr(alpha), _ptr(beta),
+                _ptr(factors) if fac_bytes else None, fac_bytes, _stream()),
                 "rnntb200_joint_cg_fwd")
-        ctx.save_for_backward(penc, pdec, labels, act_lens, label_lens, lse, alpha, beta)
+        ctx.save_for_backward(penc, pdec, labels, act_lens, label_lens, lse, alpha, beta, factors)
         ctx.blank, ctx.deterministic = blank, bool(deterministic)
         return costs
 
     @staticmethod
     def backward(ctx, grad_costs):
-        penc, pdec, labels, act_lens, label_lens, lse, alpha, beta = ctx.saved_tensors
+        penc, pdec, labels, act_lens, label_lens, lse, alpha, beta, factors = ctx.saved_tensors
         B, T, V = penc.shape
         U1 = pdec.shape[1]
         grad_costs = grad_costs.contiguous().to(torch.float32)
+        fac_bytes = factors.numel()
         d_penc = torch.empty_like(penc)
         d_pdec = torch.empty_like(pdec)
         lib = _lib.load()
@@ -146,7 +151,8 @@ class _ConcatGeluRNNT(torch.autograd.Function):
             _lib.check(lib.rnntb200_joint_cg_bwd(
                 _ptr(penc), _ptr(pdec), _ptr(labels), _ptr(act_lens), _ptr(label_lens), B, T, U1, V,
                 ctx.blank, _ptr(lse), _ptr(alpha), _ptr(beta), _ptr(grad_costs),
-                _ptr(d_penc), _ptr(d_pdec), det, _ptr(ws), ws_bytes, _stream()),
+                _ptr(d_penc), _ptr(d_pdec), det, _ptr(ws), ws_bytes,
+                _ptr(factors) if fac_bytes else None, fac_bytes, _stream()),
                 "rnntb200_joint_cg_bwd")
         return d_penc, d_pdec, None, None, None, None, None
 
