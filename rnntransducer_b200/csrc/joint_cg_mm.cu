@@ -261,15 +261,15 @@ cg_lse_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec,
 //   E += C B     (32 x Vk, K = 48 positions; warp w: row tile w & 1, column quarter w >> 1; the
 //                 accumulators stay in registers across the chunks)
 //   D  = C^T A   (48 x Vk, K = 32 frames; warp w: its column quarter, row tiles 0, 2 or 1)
-// and d_pdec += B .* D - corrections.  The corrections ride along as rank-1 style terms with a fixed
-// summation order, so the only order-dependent arithmetic is the cross-tile accumulation of d_pdec
-// (fp32 atomics, or per-tile slabs + a fixed-order reduction in deterministic mode) and the cold
-// exact path.
+// and d_pdec += B .* D - corrections.  The d_penc corrections (row t loses cb at the blank column and
+// cl at the label column of every position) are a fourth product, CL Y + CB Y_blank with one-hot
+// columns generated in registers; the d_pdec ones are column sums.  All of it has a fixed summation
+// order, so the only order-dependent arithmetic is the cross-tile accumulation of d_pdec (fp32
+// atomics, or per-tile slabs + a fixed-order reduction in deterministic mode) and the cold exact path.
 constexpr int kGT2 = 32;   // frames per CTA
 constexpr int kGUC2 = 48;  // label positions per chunk
 constexpr int kGThreads = 256;
-constexpr int kCs = 52;    // row stride of the C plane (4 mod 8: conflict-free A fragments of C B)
-constexpr int kCc = 49;    // row stride of the two correction planes (odd: column walks are conflict-free)
+constexpr int kCs = 52;    // row stride of the C planes (4 mod 8: conflict-free A fragments of C B)
 constexpr int kCellsPerThread = kGT2 * kGUC2 / kGThreads;  // 6
 constexpr int kBatch = 3;  // cells whose global loads are in flight together
 
@@ -285,11 +285,10 @@ cg_grad_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec
     extern __shared__ float smem[];
     float* As = smem;                  // [32][Vs]  A = 2^(P_enc - max)   (Vs = 8 mod 16: conflict-free B fragments)
     float* Bs0 = As + kGT2 * Vs;       // [2][48][Vs]  B chunk, double-buffered (next chunk lands during this one)
-    float* Xs = Bs0 + 2 * kGUC2 * Vs;  // [32][Vk]  corrections of d_penc: -(blank, label terms) (+ exact path)
-    float* Cs = Xs + kGT2 * Vk;        // [32][52]  C chunk
-    float* CBs = Cs + kGT2 * kCs;      // [32][49]  blank corrections
-    float* CLs = CBs + kGT2 * kCc;     // [32][49]  label corrections
-    float* mA = CLs + kGT2 * kCc;      // [32] row maxima (base 2)
+    float* Cs = Bs0 + 2 * kGUC2 * Vs;  // [32][52]  C chunk
+    float* CBs = Cs + kGT2 * kCs;      // [32][52]  blank corrections
+    float* CLs = CBs + kGT2 * kCs;     // [32][52]  label corrections
+    float* mA = CLs + kGT2 * kCs;      // [32] row maxima (base 2)
     float* lAb = mA + kGT2;            // [32] log2 A[t][blank]
     float* sc0 = lAb + kGT2;           // [2][3][48] per chunk: row maxima, log2 B[u][blank], log2 B[u][y_u]
     float* ub = sc0 + 6 * kGUC2;       // [48] sum_t corr_blank
@@ -306,6 +305,7 @@ cg_grad_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec
     const int mt = warp & 1;                 // 16-frame row tile of E
     const int nt0 = (warp >> 1) * NTW;       // first 8-column tile of this warp (column quarter)
     const int n_nt = Vk >> 3;                // column tiles in use
+    constexpr uint32_t kOne = 0x3f800000u;   // 1.0f: exact in TF32
 
     if (t0 >= Tb) {  // tile entirely in the padding: exact zeros
         for (int i = tid; i < kGT2 * V; i += kGThreads) {
@@ -320,7 +320,6 @@ cg_grad_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec
     const int llq = beta[(size_t)b * T * U1];  // beta(0,0) = P(y|x), e16m16
     const int rows_t = min(kGT2, Tb - t0);
 
-    for (int i = tid; i < kGT2 * Vk; i += kGThreads) Xs[i] = 0.f;
     if (tid == 0) n_exact = 0;
     auto issue_chunk = [&](int c) {  // everything chunk c needs, into buffer c & 1, one chunk ahead
         const int u0 = c * kGUC2, n = max(0, min(kGUC2, Ub + 1 - u0));
@@ -344,11 +343,13 @@ cg_grad_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec
     issue_chunk(0);
     int chunk = 0;
 
-    float E[NTW][4];  // (C B)[t][v] fragments
+    // fragments of (C B)[t][v] and of the d_penc corrections X[t][v] = sum_u cl(t,u) [v = y_u] + cb(t,u) [v = blank]
+    // (a product with one-hot columns generated in registers: exact, fixed order, no scatter)
+    float E[NTW][4], X[NTW][4];
 #pragma unroll
     for (int i = 0; i < NTW; ++i)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) E[i][k] = 0.f;
+        for (int k = 0; k < 4; ++k) E[i][k] = X[i][k] = 0.f;
 
     for (int u0 = 0; u0 < U1; u0 += kGUC2, ++chunk) {
         if (!slab && u0 > Ub) break;  // nothing left to add (slabs must be written in full)
@@ -408,41 +409,40 @@ cg_grad_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec
                     }
                 }
                 Cs[r * kCs + uu] = cval;
-                CBs[r * kCc + uu] = cb;
-                CLs[r * kCc + uu] = cl;
+                CBs[r * kCs + uu] = cb;
+                CLs[r * kCs + uu] = cl;
             }
         }
         __syncthreads();
-        // corrections, in a fixed order.  Row r of d_penc loses cb at the blank column and cl at the
-        // label column of every position: one thread per frame walks the positions sequentially
-        // (two positions may share a label, so this must not be a parallel scatter).
-        if (tid < kGT2) {
-            float* xr = Xs + tid * Vk;
-            float sb = 0.f;
-            for (int uu = 0; uu < rows_u; ++uu) {
-                sb += CBs[tid * kCc + uu];
-                const int y = ys[uu];
-                if (y >= 0) xr[y] -= CLs[tid * kCc + uu];
-            }
-            xr[blank] -= sb;
-        } else if (tid >= 64 && tid < 64 + kGUC2) {
+        // column sums of the two correction planes (what d_pdec loses at the blank / label column)
+        if (tid >= 64 && tid < 64 + kGUC2) {
             const int uu = tid - 64;
             float sb = 0.f, sl = 0.f;
-            for (int r = 0; r < kGT2; ++r) { sb += CBs[r * kCc + uu]; sl += CLs[r * kCc + uu]; }
+            for (int r = 0; r < kGT2; ++r) { sb += CBs[r * kCs + uu]; sl += CLs[r * kCs + uu]; }
             ub[uu] = sb;
             ul[uu] = sl;
         }
-        // E += C B   (K = label positions of the chunk; rows of C / B beyond rows_u are zeros)
+        // E += C B, X += CL Y + CB Y_blank  (K = label positions of the chunk; rows beyond rows_u are zeros)
         {
             const float* crow = Cs + (mt * 16 + g) * kCs + q;
+            const int off_b = CBs - Cs, off_l = CLs - Cs;
 #pragma unroll 2
             for (int k0 = 0; k0 < kGUC2; k0 += 8) {
                 if (k0 >= rows_u) break;
-                uint32_t ah[4], al[4];
+                uint32_t ah[4], al[4], lh[4], ll[4], bh4[4], bl4[4];
                 split_tf32(crow[k0], ah[0], al[0]);
                 split_tf32(crow[k0 + 8 * kCs], ah[1], al[1]);
                 split_tf32(crow[k0 + 4], ah[2], al[2]);
                 split_tf32(crow[k0 + 8 * kCs + 4], ah[3], al[3]);
+                split_tf32(crow[off_l + k0], lh[0], ll[0]);
+                split_tf32(crow[off_l + k0 + 8 * kCs], lh[1], ll[1]);
+                split_tf32(crow[off_l + k0 + 4], lh[2], ll[2]);
+                split_tf32(crow[off_l + k0 + 8 * kCs + 4], lh[3], ll[3]);
+                split_tf32(crow[off_b + k0], bh4[0], bl4[0]);
+                split_tf32(crow[off_b + k0 + 8 * kCs], bh4[1], bl4[1]);
+                split_tf32(crow[off_b + k0 + 4], bh4[2], bl4[2]);
+                split_tf32(crow[off_b + k0 + 8 * kCs + 4], bh4[3], bl4[3]);
+                const int y0 = ys[k0 + q], y1 = ys[k0 + q + 4];  // -1: no label, matches no column
                 const float* bcol = Bs + (k0 + q) * Vs + nt0 * 8 + g;
 #pragma unroll
                 for (int i = 0; i < NTW; ++i) {
@@ -453,11 +453,20 @@ cg_grad_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec
                     mma_tf32(E[i], ah, bh);
                     mma_tf32(E[i], ah, bl);
                     mma_tf32(E[i], al, bh);
+                    const int col = (nt0 + i) * 8 + g;
+                    const uint32_t yh[2] = {y0 == col ? kOne : 0u, y1 == col ? kOne : 0u};
+                    mma_tf32(X[i], lh, yh);
+                    mma_tf32(X[i], ll, yh);
+                    if ((blank >> 3) == nt0 + i) {  // warp-uniform
+                        const uint32_t yb[2] = {col == blank ? kOne : 0u, col == blank ? kOne : 0u};
+                        mma_tf32(X[i], bh4, yb);
+                        mma_tf32(X[i], bl4, yb);
+                    }
                 }
             }
         }
-        __syncthreads();  // ub / ul are complete
         // D = C^T A   (K = frames of the tile), then d_pdec partial = B .* D - corrections
+        bool synced = false;
 #pragma unroll 1
         for (int m0 = mt * 16; m0 < kGUC2; m0 += 32) {  // row tiles 0, 2 (even warps) / 1 (odd warps)
             if (!slab && m0 >= rows_u) break;
@@ -489,6 +498,10 @@ cg_grad_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec
                     }
                 }
             }
+            if (!synced) {  // ub / ul are complete (the barrier is reached by every warp exactly once per chunk:
+                synced = true;  // see below for the warps that skip this loop)
+                __syncthreads();
+            }
 #pragma unroll
             for (int i = 0; i < NTW; ++i) {
                 if (nt0 + i >= n_nt) continue;
@@ -506,36 +519,15 @@ cg_grad_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec
                             if (v == blank) gv -= ub[uu];
                             if (v == ys[uu]) gv -= ul[uu];
                         }
-                        if (slab) slab[(size_t)u * V + v] = gv;  // exact-path cells are added below
+                        if (slab) slab[(size_t)u * V + v] = gv;  // exact-path cells are added at the end
                         else if (uu < rows_u) atomicAdd(d_pdec + ((size_t)b * U1 + u) * V + v, gv);
                     }
                 }
             }
         }
-        // exact path (cold): cells whose partition underflows the factorised form
-        if (n_exact > 0) {  // uniform: n_exact was final at the barrier above
-            __syncthreads();  // slab writes of this chunk are complete
-            for (int i = tid; i < kGT2 * kGUC2; i += kGThreads) {
-                const int r = i / kGUC2, uu = i - r * kGUC2;
-                const int t = t0 + r, u = u0 + uu;
-                if (t >= Tb || u > Ub) continue;
-                const size_t c = ((size_t)b * T + t) * U1 + u;
-                const float zz = lse[c] * kLog2e;
-                if (!(mA[r] + mB[uu] - zz > -kTinyLog2)) continue;
-                const float occ = e16m16_log2_ratio(alpha[c], beta[c], llq) - zz;
-                const float* pe = penc + ((size_t)b * T + t) * V;
-                const float* pd = pdec + ((size_t)b * U1 + u) * V;
-                for (int v = 0; v < V; ++v) {
-                    const float gg = gc * fast_ex2((pe[v] + pd[v]) * kLog2e + occ);
-                    atomicAdd(Xs + r * Vk + v, gg);
-                    if (slab) atomicAdd(slab + (size_t)u * V + v, gg);
-                    else atomicAdd(d_pdec + ((size_t)b * U1 + u) * V + v, gg);
-                }
-            }
-        }
+        if (!synced) __syncthreads();  // warps without a row tile in this chunk
     }
-    __syncthreads();
-    // d_penc = A .* E + corrections (+ exact-path cells); padded rows come out as zeros
+    // d_penc = A .* E - corrections; padded rows come out as zeros
 #pragma unroll
     for (int i = 0; i < NTW; ++i) {
         if (nt0 + i >= n_nt) continue;
@@ -547,7 +539,29 @@ cg_grad_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec
             for (int k = 0; k < 2; ++k) {
                 const int v = (nt0 + i) * 8 + 2 * q + k;
                 if (v >= V) continue;
-                d_penc[((size_t)b * T + t0 + r) * V + v] = fmaf(As[r * Vs + v], E[i][2 * h + k], Xs[r * Vk + v]);
+                d_penc[((size_t)b * T + t0 + r) * V + v] = fmaf(As[r * Vs + v], E[i][2 * h + k], -X[i][2 * h + k]);
+            }
+        }
+    }
+    // exact path (cold): cells whose partition underflows the factorised form contributed C = 0
+    // above; their full V-wide gradient is added here (this CTA owns these d_penc rows / this slab)
+    __syncthreads();
+    if (n_exact > 0) {
+        for (int i = tid; i < kGT2 * (Ub + 1); i += kGThreads) {
+            const int r = i / (Ub + 1), u = i - r * (Ub + 1);
+            const int t = t0 + r;
+            if (t >= Tb) continue;
+            const size_t c = ((size_t)b * T + t) * U1 + u;
+            const float zz = lse[c] * kLog2e;
+            if (!(mA[r] + __ldg(F.mB + (size_t)b * U1 + u) - zz > -kTinyLog2)) continue;
+            const float occ = e16m16_log2_ratio(alpha[c], beta[c], llq) - zz;
+            const float* pe = penc + ((size_t)b * T + t) * V;
+            const float* pd = pdec + ((size_t)b * U1 + u) * V;
+            for (int v = 0; v < V; ++v) {
+                const float gg = gc * fast_ex2((pe[v] + pd[v]) * kLog2e + occ);
+                atomicAdd(d_penc + ((size_t)b * T + t) * V + v, gg);
+                if (slab) atomicAdd(slab + (size_t)u * V + v, gg);
+                else atomicAdd(d_pdec + ((size_t)b * U1 + u) * V + v, gg);
             }
         }
     }
@@ -561,8 +575,8 @@ int launch_grad_mm(const float* penc, const float* pdec, const CgFactors& F, con
                    const float* lse, const int32_t* alpha, const int32_t* beta, const float* grad_costs,
                    float* d_penc, float* d_pdec, float* partial, cudaStream_t stream) {
     const int Vk = F.Vk, Vs = grad_row_stride(Vk);
-    const size_t smem = ((size_t)(kGT2 + 2 * kGUC2) * Vs + kGT2 * Vk + kGT2 * (kCs + 2 * kCc) + 2 * kGT2 + 8 * kGUC2) *
-                        sizeof(float);  // 74.5 KiB at V = 73: three CTAs per SM, the whole cfg-2 grid in one wave
+    const size_t smem = ((size_t)(kGT2 + 2 * kGUC2) * Vs + 3 * kGT2 * kCs + 2 * kGT2 + 8 * kGUC2) *
+                        sizeof(float);  // 65 KiB at V = 73: three CTAs per SM, the whole cfg-2 grid in one wave
     cudaError_t e = cudaFuncSetAttribute(cg_grad_mm_kernel<NTW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return status_from_cuda(e);
     dim3 grid((T + kGT2 - 1) / kGT2, B);

@@ -128,7 +128,10 @@ proj_tc_kernel(const __grid_constant__ CUtensorMap w0_hi, const __grid_constant_
 
     if (warp < kProducerWarps) {
         // ===== A producers: thread = (row r, K chunks kc0 and kc0+4 of each block) =====
-        const int r = threadIdx.x & 127, kc0 = threadIdx.x >> 7;
+        // a warp covers 8 rows x 4 chunks: one load instruction touches 8 rows x 128 contiguous bytes
+        // (8 cache lines; a lane-per-row mapping touches 32 and is bound by L1 tag look-ups), and a
+        // quarter warp still stores 8 rows x 16 B = one 128-byte core-matrix column, conflict-free
+        const int r = warp * 8 + (lane & 7), kc0 = lane >> 3;
         const int row = min(row0 + r, P.rows - 1);  // rows past the end are computed but never stored
         const float4* xrow = reinterpret_cast<const float4*>(P.x + (size_t)row * P.K);
         // three register buffers take turns (K loop unrolled by three, compile-time roles, no copy
@@ -214,20 +217,34 @@ proj_tc_kernel(const __grid_constant__ CUtensorMap w0_hi, const __grid_constant_
             umma_commit(acc_full);
         }
     } else {
-        // ===== epilogue: one output row per thread =====
+        // ===== epilogue: one output row per thread (= TMEM lane) -> shared-memory tile -> coalesced copy
+        // The [rows, V] tile is one contiguous span of the output; a thread-per-row store would touch
+        // 32 cache lines per instruction.  The A stages are free once the accumulator is complete.
         const int q = warp & 3, r = q * 32 + lane;
-        const int row = row0 + r;
+        float* stile = reinterpret_cast<float*>(smem + L.a);  // [128][Vp], odd row stride: conflict-free
+        const int Vp = V | 1;
         mbar_wait(acc_full, 0);
         tc_fence_after();
         for (int pc = 0; pc < NB / 16; ++pc) {
             float v[16];
             tmem_ld16(tmem + pc * 16 + ((uint32_t)(q * 32) << 16), v);
-            if (row < P.rows) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int col = pc * 16 + i;
-                    if (col < V) P.out[(size_t)row * V + col] = v[i] + (P.bias ? __ldg(P.bias + col) : 0.f);
-                }
+            for (int i = 0; i < 16; ++i) {
+                const int col = pc * 16 + i;
+                if (col < V) stile[r * Vp + col] = v[i] + (P.bias ? __ldg(P.bias + col) : 0.f);
+            }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps
+        const int n_rows = min(128, P.rows - row0);
+        const int n = n_rows * V, t = threadIdx.x - (kThreads - 128);
+        float* gout = P.out + (size_t)row0 * V;
+        if (Vp == V && (n & 3) == 0 && ((uintptr_t)gout & 15) == 0) {  // the tile is flat in both memories
+            for (int i = t; i < n / 4; i += 128)
+                reinterpret_cast<float4*>(gout)[i] = reinterpret_cast<const float4*>(stile)[i];
+        } else {
+            for (int i = t; i < n; i += 128) {
+                const int rr = i / V;
+                gout[i] = stile[rr * Vp + (i - rr * V)];
             }
         }
     }

@@ -127,54 +127,66 @@ proj_tc_bwd_kernel(const __grid_constant__ CUtensorMap w0_hi, const __grid_const
 
     if (warp < 8) {
         // ===== producers =====
-        const int r = threadIdx.x & 127, half = threadIdx.x >> 7;
-        const int row = row0 + r;
-        const bool row_ok = row < P.rows;
+        // A warp covers 16 rows; lane = (row within 8, one of 4 adjacent 16-byte-output groups): every
+        // global load instruction touches 8 rows x 128 contiguous bytes (8 cache lines -- one row per
+        // lane would touch 32 and is bound by L1 tag look-ups), and a quarter warp stores 8 rows x 16 B
+        // = one 128-byte core-matrix column, conflict-free.
+        const int r8 = warp * 16 + (lane & 7), c4 = lane >> 3;
         // (1) dP tile -> (hi, lo), [v-group][row][8 v]
-        const float* dprow = P.dp + (size_t)min(row, P.rows - 1) * V;
-        for (int gi = half; gi < NB / 8; gi += 2) {
-            float v[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int col = gi * 8 + j;
-                v[j] = (row_ok && col < V) ? __ldg(dprow + col) : 0.f;
+        for (int i1 = 0; i1 < 2; ++i1) {
+            const int r = r8 + 8 * i1, row = row0 + r;
+            const bool row_ok = row < P.rows;
+            const float* dprow = P.dp + (size_t)min(row, P.rows - 1) * V;
+            for (int gi = c4; gi < NB / 8; gi += 4) {
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int col = gi * 8 + j;
+                    v[j] = (row_ok && col < V) ? __ldg(dprow + col) : 0.f;
+                }
+                uint4 hi, lo;
+                split2(v[0], v[1], hi.x, lo.x);
+                split2(v[2], v[3], hi.y, lo.y);
+                split2(v[4], v[5], hi.z, lo.z);
+                split2(v[6], v[7], hi.w, lo.w);
+                *reinterpret_cast<uint4*>(smem + L.dp + gi * kGroup + r * 16) = hi;
+                *reinterpret_cast<uint4*>(smem + L.dp + L.dp_half + gi * kGroup + r * 16) = lo;
             }
-            uint4 hi, lo;
-            split2(v[0], v[1], hi.x, lo.x);
-            split2(v[2], v[3], hi.y, lo.y);
-            split2(v[4], v[5], hi.z, lo.z);
-            split2(v[6], v[7], hi.w, lo.w);
-            *reinterpret_cast<uint4*>(smem + L.dp + gi * kGroup + r * 16) = hi;
-            *reinterpret_cast<uint4*>(smem + L.dp + L.dp_half + gi * kGroup + r * 16) = lo;
         }
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(dp_full);
         // (2) gelu(x) in 128-column blocks -> (hi, lo), [h-group][row][8 h]
-        const float4* xrow = reinterpret_cast<const float4*>(P.x + (size_t)min(row, P.rows - 1) * P.K);
+        const bool row_ok0 = row0 + r8 < P.rows, row_ok1 = row0 + r8 + 8 < P.rows;
+        const float4* xrow0 = reinterpret_cast<const float4*>(P.x + (size_t)min(row0 + r8, P.rows - 1) * P.K);
+        const float4* xrow1 = reinterpret_cast<const float4*>(P.x + (size_t)min(row0 + r8 + 8, P.rows - 1) * P.K);
         // each 128-column block is produced as two 64-column halves from two register buffers that
-        // alternate: the loads of the next half are in flight while the current one is computed
+        // alternate: the loads of the next half are in flight while the current one is computed.
+        // Item i of a half: row r8 + 8 (i & 1), h-group 8 hf + c4 + 4 (i >> 1).
         float4 xa[8], xb[8];
-        auto load_half = [&](float4(&dst)[8], int blk, int hf) {  // h-groups 8*hf + half + 2i
+        auto load_half = [&](float4(&dst)[8], int blk, int hf) {
             if (blk < n_blk) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    dst[2 * i] = __ldg(xrow + blk * 32 + (8 * hf + half + 2 * i) * 2);
-                    dst[2 * i + 1] = __ldg(xrow + blk * 32 + (8 * hf + half + 2 * i) * 2 + 1);
+                    const float4* xr = (i & 1) ? xrow1 : xrow0;
+                    const int kc = 8 * hf + c4 + 4 * (i >> 1);
+                    dst[2 * i] = __ldg(xr + blk * 32 + kc * 2);
+                    dst[2 * i + 1] = __ldg(xr + blk * 32 + kc * 2 + 1);
                 }
             }
         };
         auto do_half = [&](const float4(&x)[8], int st, int hf) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int kc = 8 * hf + half + 2 * i;
+                const int kc = 8 * hf + c4 + 4 * (i >> 1), r = r8 + 8 * (i & 1);
                 const float4 x0 = x[2 * i], x1 = x[2 * i + 1];
                 uint4 hi, lo;
                 split2(gelu_val(x0.x), gelu_val(x0.y), hi.x, lo.x);
                 split2(gelu_val(x0.z), gelu_val(x0.w), hi.y, lo.y);
                 split2(gelu_val(x1.x), gelu_val(x1.y), hi.z, lo.z);
                 split2(gelu_val(x1.z), gelu_val(x1.w), hi.w, lo.w);
-                if (!row_ok) hi = lo = make_uint4(0, 0, 0, 0);  // rows past the end must not reach d_W
+                if (!((i & 1) ? row_ok1 : row_ok0)) hi = lo = make_uint4(0, 0, 0, 0);  // rows past the end must not reach d_W
                 unsigned char* dst = smem + L.gx + st * 2 * kGxHalf + kc * kGroup + r * 16;
                 *reinterpret_cast<uint4*>(dst) = hi;
                 *reinterpret_cast<uint4*>(dst + kGxHalf) = lo;

@@ -27,3 +27,16 @@ tot, tots = sum(d[0] for d in data), sum(d[1] for d in data)
 print(f"total warp instructions {tot}, samples {tots}")
 for d in sorted(data, reverse=True)[:top]:
     print(f"{d[0]:>10} {100 * d[0] / tot:5.1f}%  smp {100 * d[1] / max(tots, 1):5.1f}%  {d[2]}:{d[3]:<4} {d[4]}")
+
+# optional: totals per line range of the main file, e.g. ranges=300-360,361-420
+import os
+rng = os.environ.get("RANGES")
+if rng:
+    main = max(set(d[2] for d in data), key=lambda f: sum(d[0] for d in data if d[2] == f))
+    for part in rng.split(","):
+        lo, hi = map(int, part.split("-"))
+        n = sum(d[0] for d in data if d[2] == main and lo <= d[3] <= hi)
+        sm = sum(d[1] for d in data if d[2] == main and lo <= d[3] <= hi)
+        print(f"{main}:{lo}-{hi}: {n} ({100 * n / tot:.1f}%), samples {100 * sm / max(tots, 1):.1f}%")
+    other = sum(d[0] for d in data if d[2] != main)
+    print(f"other files (inlined helpers): {other} ({100 * other / tot:.1f}%)")
