@@ -106,6 +106,8 @@ int launch_dense_grad(const void* logits, int dtype, const int32_t* labels, cons
 struct CgFactors {
     float* Ea;   // [B*T][Vk]   2^((P_enc - rowmax) log2e), pad columns zero
     float* Eb;   // [B*U1][Vk]  same for P_dec
+    uint32_t* Ea2;  // the same two planes as packed (bf16 hi | bf16 lo << 16) pairs, hi + lo = value to
+    uint32_t* Eb2;  // 2^-18: the gradient kernel's tensor-core operands (no splitting in its loops)
     float* mA;   // [B*T]   row maxima, base 2
     float* lAb;  // [B*T]   log2 Ea[.][blank] (exact: not taken from the possibly underflowed Ea)
     float* mB;   // [B*U1]

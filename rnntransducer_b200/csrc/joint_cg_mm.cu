@@ -12,11 +12,15 @@
 // The C*V exponentials of the straightforward evaluation (76 M at B=32,T=400,U=80,V=73 -- the MUFU
 // floor of cg_lse_kernel / cg_grad_kernel) become three small batched GEMMs.
 //
-// The GEMMs are per-CTA products of shared-memory tiles (32 x 64 x V, 32 x V x 48, 48 x V x 32):
-// they run as warp-level tensor-core MMAs (mma.sync m16n8k8, TF32 operands, fp32 accumulate) on
-// operands split into hi + lo TF32 halves, hi*hi + hi*lo + lo*hi (the dropped lo*lo term is 2^-22
-// relative), i.e. at fp32 accuracy.  One warp instruction replaces 1024 FFMA lanes; tcgen05 would
-// add a TMEM round trip per 32-frame tile for products this small (K = V <= 128).
+// The GEMMs are per-CTA products of shared-memory tiles (32 x 64 x V, 32 x V x 48, 48 x V x 32) and
+// run as warp-level tensor-core MMAs on split operands, hi*hi + hi*lo + lo*hi:
+//   forward (the partition feeds every log-probability of the lattice): mma.sync m16n8k8, TF32
+//     halves split in the loop, dropped term 2^-22 relative, i.e. fp32 accuracy;
+//   backward: mma.sync m16n8k16 on operands stored as packed (bf16 hi | bf16 lo) pairs -- the pair
+//     rides in the instruction's k dimension, so the loops contain no conversions at all; 2^-17
+//     relative, far inside the 1e-4 gradient tolerance.
+// One warp instruction replaces 1024-2048 FFMA lanes; tcgen05 would add a TMEM round trip per
+// 32-frame tile for products this small (K = V <= 128).
 //
 // Range: A, B are in (0,1].  If the peaks of the two rows do not line up, S can be tiny; cells
 // with S < 2^-66 (logit ranges beyond ~45 nats in BOTH rows, never seen with real activations) take
@@ -36,6 +40,37 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
     const float r = x - __uint_as_float(hi);
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+
+// x -> (bf16 hi | bf16 lo << 16) with hi + lo = x to 2^-18 relative; and back
+__device__ __forceinline__ uint32_t pack_hilo(float x) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    const float hf = __bfloat162float(h);
+    const __nv_bfloat162 p = __floats2bfloat162_rn(hf, x - hf);  // .x (low half) = hi exactly, .y = lo
+    return *reinterpret_cast<const uint32_t*>(&p);
+}
+__device__ __forceinline__ float unpack_hilo(uint32_t p) {
+    return __uint_as_float(p << 16) + __uint_as_float(p & 0xffff0000u);
+}
+
+// D += A B with bf16 operands, m16n8k16, fp32 accumulate.  Register r of a fragment holds the two
+// CONSECUTIVE k indices (2q', 2q'+1).  The kernels below feed it packed (hi, lo) pairs, i.e. the
+// instruction's k index runs over (element, half): lane (g, q) then holds for A the elements
+// [g][q], [g+8][q], [g][q+4], [g+8][q+4] and for B [q][g], [q+4][g] -- the same addressing as the
+// TF32 fragments -- and one instruction covers 8 elements of the real K dimension.
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// (a_hi + a_lo)(b_hi + b_lo) ~ a_hi b_hi + a_lo b_hi + a_hi b_lo from packed operands: A as stored;
+// B once as (hi, hi) and once as (lo, 0) -- a byte permute and a shift instead of any conversion
+__device__ __forceinline__ void mma_hilo(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    const uint32_t hh[2] = {__byte_perm(b0, b0, 0x1010), __byte_perm(b1, b1, 0x1010)};
+    const uint32_t l0[2] = {b0 >> 16, b1 >> 16};
+    mma_bf16(d, a, hh);
+    mma_bf16(d, a, l0);
 }
 
 // D += A B, A 16x8 (row), B 8x8 (col), fp32 accumulate.  Lane (g = lane/4, q = lane%4) holds
@@ -61,7 +96,8 @@ cg_factor_rows_kernel(const float* __restrict__ penc, const float* __restrict__ 
                       const int32_t* __restrict__ labels, const int32_t* __restrict__ label_lens, int rows_enc,
                       int rows_dec, int U1, int V, int Vk, int blank, float* __restrict__ Ea,
                       float* __restrict__ mA, float* __restrict__ lAb, float* __restrict__ Eb,
-                      float* __restrict__ mB, float* __restrict__ lBb, float* __restrict__ lBy) {
+                      float* __restrict__ mB, float* __restrict__ lBb, float* __restrict__ lBy,
+                      uint32_t* __restrict__ Ea2, uint32_t* __restrict__ Eb2) {
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows_enc + rows_dec) return;
@@ -69,6 +105,7 @@ cg_factor_rows_kernel(const float* __restrict__ penc, const float* __restrict__ 
     const int r = is_dec ? row - rows_enc : row;
     const float* x = (is_dec ? pdec : penc) + (size_t)r * V;
     float* e = (is_dec ? Eb : Ea) + (size_t)r * Vk;
+    uint32_t* e2 = (is_dec ? Eb2 : Ea2) + (size_t)r * Vk;
     float xv[4];  // V <= 128
     float m = -INFINITY;
 #pragma unroll
@@ -81,7 +118,11 @@ cg_factor_rows_kernel(const float* __restrict__ penc, const float* __restrict__ 
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int v = lane + 32 * i;
-        if (v < Vk) e[v] = v < V ? fast_ex2((xv[i] - m) * kLog2e) : 0.f;
+        if (v < Vk) {
+            const float ev = v < V ? fast_ex2((xv[i] - m) * kLog2e) : 0.f;
+            e[v] = ev;
+            e2[v] = pack_hilo(ev);
+        }
     }
     if (lane == 0) {
         const float lb = (__ldg(x + blank) - m) * kLog2e;
@@ -282,13 +323,15 @@ cg_grad_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec
                   const int32_t* __restrict__ beta, const float* __restrict__ grad_costs,
                   float* __restrict__ d_penc, float* __restrict__ d_pdec,
                   float* __restrict__ partial /* deterministic slabs or null */) {
+    // operand planes hold packed (bf16 hi | bf16 lo << 16) pairs (pack_hilo): A / B arrive that way
+    // from the factor planes, the per-cell scalars are packed when they are stored
     extern __shared__ float smem[];
-    float* As = smem;                  // [32][Vs]  A = 2^(P_enc - max)   (Vs = 8 mod 16: conflict-free B fragments)
-    float* Bs0 = As + kGT2 * Vs;       // [2][48][Vs]  B chunk, double-buffered (next chunk lands during this one)
-    float* Cs = Bs0 + 2 * kGUC2 * Vs;  // [32][52]  C chunk
-    float* CBs = Cs + kGT2 * kCs;      // [32][52]  blank corrections
-    float* CLs = CBs + kGT2 * kCs;     // [32][52]  label corrections
-    float* mA = CLs + kGT2 * kCs;      // [32] row maxima (base 2)
+    uint32_t* As = reinterpret_cast<uint32_t*>(smem);  // [32][Vs]  A = 2^(P_enc - max)   (Vs = 8 mod 16: conflict-free B fragments)
+    uint32_t* Bs0 = As + kGT2 * Vs;       // [2][48][Vs]  B chunk, double-buffered (next chunk lands during this one)
+    uint32_t* Cs = Bs0 + 2 * kGUC2 * Vs;  // [32][52]  C chunk
+    uint32_t* CBs = Cs + kGT2 * kCs;      // [32][52]  blank corrections
+    uint32_t* CLs = CBs + kGT2 * kCs;     // [32][52]  label corrections
+    float* mA = reinterpret_cast<float*>(CLs + kGT2 * kCs);  // [32] row maxima (base 2)
     float* lAb = mA + kGT2;            // [32] log2 A[t][blank]
     float* sc0 = lAb + kGT2;           // [2][3][48] per chunk: row maxima, log2 B[u][blank], log2 B[u][y_u]
     float* ub = sc0 + 6 * kGUC2;       // [48] sum_t corr_blank
@@ -305,7 +348,7 @@ cg_grad_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec
     const int mt = warp & 1;                 // 16-frame row tile of E
     const int nt0 = (warp >> 1) * NTW;       // first 8-column tile of this warp (column quarter)
     const int n_nt = Vk >> 3;                // column tiles in use
-    constexpr uint32_t kOne = 0x3f800000u;   // 1.0f: exact in TF32
+    constexpr uint32_t kOnes = 0x3f803f80u;  // (1.0, 1.0) in bf16: selects hi + lo of a packed operand
 
     if (t0 >= Tb) {  // tile entirely in the padding: exact zeros
         for (int i = tid; i < kGT2 * V; i += kGThreads) {
@@ -332,13 +375,14 @@ cg_grad_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec
             const int u = u0 + tid;
             ys0[c & 1][tid] = u < Ub ? __ldg(labels + (size_t)b * (U1 - 1) + u) : -1;
         }
-        stage_tile(Bs0 + (c & 1) * kGUC2 * Vs, F.Eb + row * Vk, n, kGUC2, Vk, Vs);
+        stage_tile(reinterpret_cast<float*>(Bs0 + (c & 1) * kGUC2 * Vs), reinterpret_cast<const float*>(F.Eb2 + row * Vk),
+                   n, kGUC2, Vk, Vs);
     };
     {
         const size_t row = (size_t)b * T + t0;
         stage_scalars(mA, F.mA + row, rows_t, kGT2);
         stage_scalars(lAb, F.lAb + row, rows_t, kGT2);
-        stage_tile(As, F.Ea + row * Vk, rows_t, kGT2, Vk, Vs);
+        stage_tile(reinterpret_cast<float*>(As), reinterpret_cast<const float*>(F.Ea2 + row * Vk), rows_t, kGT2, Vk, Vs);
     }
     issue_chunk(0);
     int chunk = 0;
@@ -354,7 +398,7 @@ cg_grad_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec
     for (int u0 = 0; u0 < U1; u0 += kGUC2, ++chunk) {
         if (!slab && u0 > Ub) break;  // nothing left to add (slabs must be written in full)
         const int rows_u = max(0, min(kGUC2, Ub + 1 - u0));
-        const float* Bs = Bs0 + (chunk & 1) * kGUC2 * Vs;
+        const uint32_t* Bs = Bs0 + (chunk & 1) * kGUC2 * Vs;
         const float* mB = sc0 + (chunk & 1) * 3 * kGUC2;
         const float* lBb = mB + kGUC2;
         const float* lBy = lBb + kGUC2;
@@ -382,7 +426,7 @@ cg_grad_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec
                     if (t < Tb - 1) bdn[qq] = beta[c + U1];
                     if (u < Ub) {
                         brt[qq] = beta[c + 1];
-                        const float ay = As[r * Vs + ys[uu]];  // log2 A[t][y_u]; gather if it underflowed
+                        const float ay = unpack_hilo(As[r * Vs + ys[uu]]);  // log2 A[t][y_u]; gather if it underflowed
                         pey[qq] = ay > 1e-30f ? fast_lg2(ay)
                                               : __ldg(penc + ((size_t)b * T + t) * V + ys[uu]) * kLog2e - mA[r];
                     }
@@ -408,9 +452,9 @@ cg_grad_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec
                         cl = gc * fast_ex2(e16m16_log2_ratio(aq[qq], brt[qq], llq) + ll2);
                     }
                 }
-                Cs[r * kCs + uu] = cval;
-                CBs[r * kCs + uu] = cb;
-                CLs[r * kCs + uu] = cl;
+                Cs[r * kCs + uu] = pack_hilo(cval);
+                CBs[r * kCs + uu] = pack_hilo(cb);
+                CLs[r * kCs + uu] = pack_hilo(cl);
             }
         }
         __syncthreads();
@@ -418,49 +462,37 @@ cg_grad_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec
         if (tid >= 64 && tid < 64 + kGUC2) {
             const int uu = tid - 64;
             float sb = 0.f, sl = 0.f;
-            for (int r = 0; r < kGT2; ++r) { sb += CBs[r * kCs + uu]; sl += CLs[r * kCs + uu]; }
+            for (int r = 0; r < kGT2; ++r) {
+                sb += unpack_hilo(CBs[r * kCs + uu]);
+                sl += unpack_hilo(CLs[r * kCs + uu]);
+            }
             ub[uu] = sb;
             ul[uu] = sl;
         }
         // E += C B, X += CL Y + CB Y_blank  (K = label positions of the chunk; rows beyond rows_u are zeros)
         {
-            const float* crow = Cs + (mt * 16 + g) * kCs + q;
+            const uint32_t* crow = Cs + (mt * 16 + g) * kCs + q;
             const int off_b = CBs - Cs, off_l = CLs - Cs;
 #pragma unroll 2
             for (int k0 = 0; k0 < kGUC2; k0 += 8) {
                 if (k0 >= rows_u) break;
-                uint32_t ah[4], al[4], lh[4], ll[4], bh4[4], bl4[4];
-                split_tf32(crow[k0], ah[0], al[0]);
-                split_tf32(crow[k0 + 8 * kCs], ah[1], al[1]);
-                split_tf32(crow[k0 + 4], ah[2], al[2]);
-                split_tf32(crow[k0 + 8 * kCs + 4], ah[3], al[3]);
-                split_tf32(crow[off_l + k0], lh[0], ll[0]);
-                split_tf32(crow[off_l + k0 + 8 * kCs], lh[1], ll[1]);
-                split_tf32(crow[off_l + k0 + 4], lh[2], ll[2]);
-                split_tf32(crow[off_l + k0 + 8 * kCs + 4], lh[3], ll[3]);
-                split_tf32(crow[off_b + k0], bh4[0], bl4[0]);
-                split_tf32(crow[off_b + k0 + 8 * kCs], bh4[1], bl4[1]);
-                split_tf32(crow[off_b + k0 + 4], bh4[2], bl4[2]);
-                split_tf32(crow[off_b + k0 + 8 * kCs + 4], bh4[3], bl4[3]);
+                const uint32_t ca[4] = {crow[k0], crow[k0 + 8 * kCs], crow[k0 + 4], crow[k0 + 8 * kCs + 4]};
+                const uint32_t la[4] = {crow[off_l + k0], crow[off_l + k0 + 8 * kCs], crow[off_l + k0 + 4],
+                                        crow[off_l + k0 + 8 * kCs + 4]};
+                const uint32_t ba[4] = {crow[off_b + k0], crow[off_b + k0 + 8 * kCs], crow[off_b + k0 + 4],
+                                        crow[off_b + k0 + 8 * kCs + 4]};
                 const int y0 = ys[k0 + q], y1 = ys[k0 + q + 4];  // -1: no label, matches no column
-                const float* bcol = Bs + (k0 + q) * Vs + nt0 * 8 + g;
+                const uint32_t* bcol = Bs + (k0 + q) * Vs + nt0 * 8 + g;
 #pragma unroll
                 for (int i = 0; i < NTW; ++i) {
                     if (nt0 + i >= n_nt) continue;
-                    uint32_t bh[2], bl[2];
-                    split_tf32(bcol[8 * i], bh[0], bl[0]);
-                    split_tf32(bcol[8 * i + 4 * Vs], bh[1], bl[1]);
-                    mma_tf32(E[i], ah, bh);
-                    mma_tf32(E[i], ah, bl);
-                    mma_tf32(E[i], al, bh);
+                    mma_hilo(E[i], ca, bcol[8 * i], bcol[8 * i + 4 * Vs]);
                     const int col = (nt0 + i) * 8 + g;
-                    const uint32_t yh[2] = {y0 == col ? kOne : 0u, y1 == col ? kOne : 0u};
-                    mma_tf32(X[i], lh, yh);
-                    mma_tf32(X[i], ll, yh);
+                    const uint32_t yh[2] = {y0 == col ? kOnes : 0u, y1 == col ? kOnes : 0u};
+                    mma_bf16(X[i], la, yh);
                     if ((blank >> 3) == nt0 + i) {  // warp-uniform
-                        const uint32_t yb[2] = {col == blank ? kOne : 0u, col == blank ? kOne : 0u};
-                        mma_tf32(X[i], bh4, yb);
-                        mma_tf32(X[i], bl4, yb);
+                        const uint32_t yb[2] = {col == blank ? kOnes : 0u, col == blank ? kOnes : 0u};
+                        mma_bf16(X[i], ba, yb);
                     }
                 }
             }
@@ -479,22 +511,13 @@ cg_grad_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec
 #pragma unroll 2
                 for (int k0 = 0; k0 < kGT2; k0 += 8) {
                     if (k0 >= rows_t) break;
-                    const float* ccol = Cs + (k0 + q) * kCs + m0 + g;  // (C^T)[u][t] = C[t][u]
-                    uint32_t ah[4], al[4];
-                    split_tf32(ccol[0], ah[0], al[0]);
-                    split_tf32(ccol[8], ah[1], al[1]);
-                    split_tf32(ccol[4 * kCs], ah[2], al[2]);
-                    split_tf32(ccol[4 * kCs + 8], ah[3], al[3]);
-                    const float* acol = As + (k0 + q) * Vs + nt0 * 8 + g;
+                    const uint32_t* ccol = Cs + (k0 + q) * kCs + m0 + g;  // (C^T)[u][t] = C[t][u]
+                    const uint32_t ca[4] = {ccol[0], ccol[8], ccol[4 * kCs], ccol[4 * kCs + 8]};
+                    const uint32_t* acol = As + (k0 + q) * Vs + nt0 * 8 + g;
 #pragma unroll
                     for (int i = 0; i < NTW; ++i) {
                         if (nt0 + i >= n_nt) continue;
-                        uint32_t bh[2], bl[2];
-                        split_tf32(acol[8 * i], bh[0], bl[0]);
-                        split_tf32(acol[8 * i + 4 * Vs], bh[1], bl[1]);
-                        mma_tf32(D[i], ah, bh);
-                        mma_tf32(D[i], ah, bl);
-                        mma_tf32(D[i], al, bh);
+                        mma_hilo(D[i], ca, acol[8 * i], acol[8 * i + 4 * Vs]);
                     }
                 }
             }
@@ -515,7 +538,7 @@ cg_grad_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec
                         if (v >= V) continue;
                         float gv = 0.f;
                         if (uu < rows_u) {
-                            gv = Bs[uu * Vs + v] * D[i][2 * h + k];
+                            gv = unpack_hilo(Bs[uu * Vs + v]) * D[i][2 * h + k];
                             if (v == blank) gv -= ub[uu];
                             if (v == ys[uu]) gv -= ul[uu];
                         }
@@ -539,7 +562,8 @@ cg_grad_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec
             for (int k = 0; k < 2; ++k) {
                 const int v = (nt0 + i) * 8 + 2 * q + k;
                 if (v >= V) continue;
-                d_penc[((size_t)b * T + t0 + r) * V + v] = fmaf(As[r * Vs + v], E[i][2 * h + k], -X[i][2 * h + k]);
+                d_penc[((size_t)b * T + t0 + r) * V + v] =
+                    fmaf(unpack_hilo(As[r * Vs + v]), E[i][2 * h + k], -X[i][2 * h + k]);
             }
         }
     }
@@ -594,7 +618,7 @@ int cg_mm_tile_rows() { return kGT2; }
 size_t cg_factors_bytes(int B, int T, int U1, int V) {
     if (!cg_mm_supported(V)) return 0;
     const size_t Vk = (V + 7) & ~7, re = (size_t)B * T, rd = (size_t)B * U1;
-    return ((re + rd) * Vk + 2 * re + 3 * rd) * sizeof(float);
+    return (2 * (re + rd) * Vk + 2 * re + 3 * rd) * sizeof(float);
 }
 
 CgFactors cg_factors_layout(void* mem, int B, int T, int U1, int V) {
@@ -602,9 +626,11 @@ CgFactors cg_factors_layout(void* mem, int B, int T, int U1, int V) {
     float* p = static_cast<float*>(mem);
     CgFactors F;
     F.Vk = (int)Vk;
-    F.Ea = p;
+    F.Ea = p;  // the four planes first: each starts 32-byte aligned (rows * Vk floats, Vk a multiple of 8)
     F.Eb = p + re * Vk;
-    F.mA = F.Eb + rd * Vk;
+    F.Ea2 = reinterpret_cast<uint32_t*>(F.Eb + rd * Vk);
+    F.Eb2 = F.Ea2 + re * Vk;
+    F.mA = reinterpret_cast<float*>(F.Eb2 + rd * Vk);
     F.lAb = F.mA + re;
     F.mB = F.lAb + re;
     F.lBb = F.mB + rd;
@@ -617,7 +643,8 @@ int launch_cg_factor_rows(const float* penc, const float* pdec, const int32_t* l
     const int rows = B * (T + U1);
     if (rows == 0) return RNNTB200_STATUS_SUCCESS;
     cg_factor_rows_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(penc, pdec, labels, label_lens, B * T, B * U1, U1, V,
-                                                             F.Vk, blank, F.Ea, F.mA, F.lAb, F.Eb, F.mB, F.lBb, F.lBy);
+                                                             F.Vk, blank, F.Ea, F.mA, F.lAb, F.Eb, F.mB, F.lBb, F.lBy,
+                                                             F.Ea2, F.Eb2);
     return launch_status();
 }
 
