@@ -311,8 +311,7 @@ constexpr int kGT2 = 32;   // frames per CTA
 constexpr int kGUC2 = 48;  // label positions per chunk
 constexpr int kGThreads = 256;
 constexpr int kCs = 52;    // row stride of the C planes (4 mod 8: conflict-free A fragments of C B)
-constexpr int kCellsPerThread = kGT2 * kGUC2 / kGThreads;  // 6
-constexpr int kBatch = 3;  // cells whose global loads are in flight together
+static_assert(kGT2 * kGUC2 == 6 * kGThreads, "thread (rr, cc) owns 2 rows x 3 columns of the cell block");
 
 template <int NTW>  // 8-column tiles per warp: ceil(Vk / 32)
 __global__ void __launch_bounds__(kGThreads, 3)
@@ -407,54 +406,64 @@ cg_grad_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec
         __syncthreads();  // this chunk has landed; the previous one is fully consumed
         if (u0 + kGUC2 < U1 && (slab || u0 + kGUC2 <= Ub)) issue_chunk(chunk + 1);
 
-        // per-cell scalars of the (32 x 48) block: C and the two corrections.  The global loads of
-        // kBatch cells are issued together before any of them is used.
+        // per-cell scalars of the (32 x 48) block: the two corrections
+        //   cb = grad_cost alpha(t,u) beta(t+1,u) p(blank) / P,   cl = grad_cost alpha(t,u) beta(t,u+1) p(label) / P
+        // and C = grad_cost occupancy / S.  The beta recursion itself says occupancy = (cb + cl) /
+        // grad_cost, so beta(t,u) is not read.  Ratios are formed from the e16m16 planes with integer
+        // exponents: value = mantissa product * 2^(exponent sum + log2 p).  Thread (rr, cc) owns rows
+        // 2 rr + {0,1} x columns cc + 16 {0,1,2}; the global loads of a row's 3 cells go out together.
+        {
+            const int rr = tid >> 4, cc = tid & 15;
+            const int e_ll = llq >> 16;
+            const float k_ll = gc * fast_rcp(e16m16_mant(llq));
 #pragma unroll 1
-        for (int q0 = 0; q0 < kCellsPerThread; q0 += kBatch) {
-            int aq[kBatch], bq[kBatch], bdn[kBatch], brt[kBatch];
-            float z2[kBatch], pey[kBatch];
+            for (int i = 0; i < 2; ++i) {
+                const int r = 2 * rr + i, t = t0 + r;
+                const bool t_ok = t < Tb;
+                const size_t cbase = ((size_t)b * T + min(t, T - 1)) * U1 + u0;
+                int aq[3], bdn[3], brt[3];
+                float z2[3], pey[3];
 #pragma unroll
-            for (int qq = 0; qq < kBatch; ++qq) {
-                const int i = tid + kGThreads * (q0 + qq), r = i / kGUC2, uu = i - r * kGUC2;
-                const int t = t0 + r, u = u0 + uu;
-                aq[qq] = bq[qq] = bdn[qq] = brt[qq] = 0;
-                z2[qq] = pey[qq] = 0.f;
-                if (t < Tb && u <= Ub) {
-                    const size_t c = ((size_t)b * T + t) * U1 + u;
-                    aq[qq] = alpha[c];
-                    bq[qq] = beta[c];
-                    if (t < Tb - 1) bdn[qq] = beta[c + U1];
-                    if (u < Ub) {
-                        brt[qq] = beta[c + 1];
-                        const float ay = unpack_hilo(As[r * Vs + ys[uu]]);  // log2 A[t][y_u]; gather if it underflowed
-                        pey[qq] = ay > 1e-30f ? fast_lg2(ay)
-                                              : __ldg(penc + ((size_t)b * T + t) * V + ys[uu]) * kLog2e - mA[r];
-                    }
-                    z2[qq] = lse[c] * kLog2e;
-                }
-            }
-#pragma unroll
-            for (int qq = 0; qq < kBatch; ++qq) {
-                const int i = tid + kGThreads * (q0 + qq), r = i / kGUC2, uu = i - r * kGUC2;
-                const int t = t0 + r, u = u0 + uu;
-                float cval = 0.f, cb = 0.f, cl = 0.f;
-                if (t < Tb && u <= Ub) {
-                    const float mm = mA[r] + mB[uu];
-                    const float shift = mm - z2[qq];  // -log2 S(t,u)
-                    if (shift > -kTinyLog2) atomicAdd(&n_exact, 1);  // C = 0: handled by the exact path
-                    else cval = gc * fast_ex2(e16m16_log2_ratio(aq[qq], bq[qq], llq) + shift);
-                    // log-domain p(blank), p(label): representable far below 2^-126
-                    const float lb2 = lAb[r] + lBb[uu] + shift;
-                    if (t < Tb - 1) cb = gc * fast_ex2(e16m16_log2_ratio(aq[qq], bdn[qq], llq) + lb2);
-                    else if (u == Ub) cb = gc * fast_ex2(e16m16_log2_ratio(aq[qq], 0, llq) + lb2);
-                    if (u < Ub) {
-                        const float ll2 = pey[qq] + lBy[uu] + shift;
-                        cl = gc * fast_ex2(e16m16_log2_ratio(aq[qq], brt[qq], llq) + ll2);
+                for (int k = 0; k < 3; ++k) {
+                    const int uu = cc + 16 * k, u = u0 + uu;
+                    aq[k] = bdn[k] = brt[k] = 0;
+                    z2[k] = pey[k] = 0.f;
+                    if (t_ok && u <= Ub) {
+                        const size_t c = cbase + uu;
+                        aq[k] = alpha[c];
+                        if (t < Tb - 1) bdn[k] = beta[c + U1];
+                        if (u < Ub) {
+                            brt[k] = beta[c + 1];
+                            const float ay = unpack_hilo(As[r * Vs + ys[uu]]);  // log2 A[t][y_u]; gather if it underflowed
+                            pey[k] = ay > 1e-30f ? fast_lg2(ay)
+                                                 : __ldg(penc + ((size_t)b * T + t) * V + ys[uu]) * kLog2e - mA[r];
+                        }
+                        z2[k] = lse[c] * kLog2e;
                     }
                 }
-                Cs[r * kCs + uu] = pack_hilo(cval);
-                CBs[r * kCs + uu] = pack_hilo(cb);
-                CLs[r * kCs + uu] = pack_hilo(cl);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const int uu = cc + 16 * k, u = u0 + uu;
+                    float cval = 0.f, cb = 0.f, cl = 0.f;
+                    if (t_ok && u <= Ub) {
+                        const float shift = mA[r] + mB[uu] - z2[k];  // -log2 S(t,u)
+                        const int e_a = (aq[k] >> 16) - e_ll;
+                        const float m_a = k_ll * e16m16_mant(aq[k]);
+                        // log-domain p(blank), p(label): representable far below 2^-126
+                        const float lb2 = lAb[r] + lBb[uu] + shift;
+                        if (t < Tb - 1) cb = m_a * e16m16_mant(bdn[k]) * fast_ex2((float)(e_a + (bdn[k] >> 16)) + lb2);
+                        else if (u == Ub) cb = m_a * fast_ex2((float)e_a + lb2);
+                        if (u < Ub) {
+                            const float ll2 = pey[k] + lBy[uu] + shift;
+                            cl = m_a * e16m16_mant(brt[k]) * fast_ex2((float)(e_a + (brt[k] >> 16)) + ll2);
+                        }
+                        if (shift > -kTinyLog2) atomicAdd(&n_exact, 1);  // C = 0: handled by the exact path
+                        else cval = (cb + cl) * fast_ex2(shift);
+                    }
+                    Cs[r * kCs + uu] = pack_hilo(cval);
+                    CBs[r * kCs + uu] = pack_hilo(cb);
+                    CLs[r * kCs + uu] = pack_hilo(cl);
+                }
             }
         }
         __syncthreads();
