@@ -22,6 +22,8 @@ constexpr int kThreads = 18 * 32;  // 8 producer warps, TMA, MMA, 2 x 4 epilogue
 constexpr int kGroup = 2048;              // 128 rows x 16 B
 constexpr int kGxHalf = 16 * kGroup;      // 128 columns of gelu(x), hi (lo follows): 32 KiB
 constexpr int kRBytes = 16 * 256;         // ones selector, K-major [16 rows][128]
+constexpr int kStageBytes = 8 * 2048;     // epilogue transposition buffers: [32 rows][16 floats] per warp
+static_assert(kStageBytes >= kRBytes, "the staging area starts on top of the ones selector");
 constexpr int kColDX = 320, kColDB = 448;
 constexpr int kTmemCols = 512;
 
@@ -42,9 +44,9 @@ __host__ __device__ inline SmemPB smem_layout_pb(int NB) {
     s.gx = 2 * s.dp_half;
     s.w = s.gx + 2 * 2 * kGxHalf;
     s.w_half = NB * kKB * 2;
-    s.r = s.w + 2 * 2 * s.w_half;
-    s.bars = s.r + kRBytes;
-    s.total = s.bars + 24 * 8 + 16;
+    s.bars = s.w + 2 * 2 * s.w_half;
+    s.r = s.bars + 24 * 8 + 16;  // the ones selector; its 4 KiB are also the head of the epilogue staging
+    s.total = s.r + kStageBytes; // area (the d_b products that read it are complete long before)
     return s;
 }
 
@@ -264,35 +266,54 @@ proj_tc_bwd_kernel(const __grid_constant__ CUtensorMap w0_hi, const __grid_const
             umma_commit(done);
         }
     } else {
-        // ===== epilogue: one row per thread; group g (warps 10-13 / 14-17) owns dX buffer g, i.e. the
-        // even / odd 64-column pieces, and half of the final d_W flush =====
+        // ===== epilogue: one row per thread (= TMEM lane); group g (warps 10-13 / 14-17) owns dX buffer
+        // g, i.e. the even / odd 64-column pieces, and half of the final d_W flush.
+        // Global memory is touched through a per-warp transposition buffer ([32 rows][16 floats], XOR
+        // swizzled): 8 rows x 64 contiguous bytes per instruction instead of 32 rows x 16 bytes (a
+        // thread-per-row access costs 32 L1 tag look-ups per instruction and starves the producers).
         const int grp = (warp - 10) >> 2;
         const int q = warp & 3, r = q * 32 + lane;
-        const int row = row0 + r;
-        const bool row_ok = row < P.rows;
         const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
-        const float4* xrow = reinterpret_cast<const float4*>(P.x + (size_t)min(row, P.rows - 1) * P.K);
-        float4* dxrow = reinterpret_cast<float4*>(P.dx + (size_t)min(row, P.rows - 1) * P.K);
+        float* stg = reinterpret_cast<float*>(smem + L.r) + (warp - 10) * 512;
+        auto sw = [](int rowi, int chunk) { return rowi * 16 + ((chunk ^ ((rowi >> 1) & 3)) << 2); };
+        const int lr = lane >> 2, lc = lane & 3;  // transposed ownership: rows lr + 8 j, 16-byte chunk lc
         for (int kb = grp; kb < n_kb; kb += 2) {
             const int buf = grp;
-            float4 xv[16];
+            float4 xg[4][4];  // x of this 64-column piece, transposed ownership, requested before the wait
 #pragma unroll
-            for (int i = 0; i < 16; ++i) xv[i] = __ldg(xrow + kb * 16 + i);
+            for (int pc = 0; pc < 4; ++pc)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int grow = min(row0 + q * 32 + lr + 8 * j, P.rows - 1);
+                    xg[pc][j] = __ldg(reinterpret_cast<const float4*>(P.x + (size_t)grow * P.K + kb * kKB + pc * 16) + lc);
+                }
             mbar_wait(dx_full(buf), (kb >> 1) & 1);
             tc_fence_after();
 #pragma unroll
             for (int pc = 0; pc < 4; ++pc) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(stg + sw(lr + 8 * j, lc)) = xg[pc][j];
+                __syncwarp();
+                float4 xr[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) xr[c] = *reinterpret_cast<const float4*>(stg + sw(lane, c));
                 float v[16];
                 tmem_ld16(tmem + kColDX + buf * kKB + pc * 16 + lane_sel, v);
-                if (row_ok) {
+                __syncwarp();
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float4 x = xv[pc * 4 + i];
-                        dxrow[kb * 16 + pc * 4 + i] =
-                            make_float4(v[4 * i] * gelu_grad(x.x), v[4 * i + 1] * gelu_grad(x.y),
-                                        v[4 * i + 2] * gelu_grad(x.z), v[4 * i + 3] * gelu_grad(x.w));
-                    }
+                for (int c = 0; c < 4; ++c)
+                    *reinterpret_cast<float4*>(stg + sw(lane, c)) =
+                        make_float4(v[4 * c] * gelu_grad(xr[c].x), v[4 * c + 1] * gelu_grad(xr[c].y),
+                                    v[4 * c + 2] * gelu_grad(xr[c].z), v[4 * c + 3] * gelu_grad(xr[c].w));
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int grow = row0 + q * 32 + lr + 8 * j;
+                    if (grow < P.rows)
+                        reinterpret_cast<float4*>(P.dx + (size_t)grow * P.K + kb * kKB + pc * 16)[lc] =
+                            *reinterpret_cast<const float4*>(stg + sw(lr + 8 * j, lc));
                 }
+                __syncwarp();
             }
             tc_fence_before();
             __syncwarp();
