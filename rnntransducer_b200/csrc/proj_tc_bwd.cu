@@ -134,24 +134,30 @@ proj_tc_bwd_kernel(const __grid_constant__ CUtensorMap w0_hi, const __grid_const
         // lane would touch 32 and is bound by L1 tag look-ups), and a quarter warp stores 8 rows x 16 B
         // = one 128-byte core-matrix column, conflict-free.
         const int r8 = warp * 16 + (lane & 7), c4 = lane >> 3;
-        // (1) dP tile -> (hi, lo), [v-group][row][8 v]
+        // (1) dP tile -> (hi, lo), [v-group][row][8 v].  All loads of a row go out before the first
+        // conversion (the tile is the first thing every MMA of this CTA waits for).
 #pragma unroll
         for (int i1 = 0; i1 < 2; ++i1) {
             const int r = r8 + 8 * i1, row = row0 + r;
             const bool row_ok = row < P.rows;
             const float* dprow = P.dp + (size_t)min(row, P.rows - 1) * V;
-            for (int gi = c4; gi < NB / 8; gi += 4) {
-                float v[8];
+            float v[3][8];  // v-groups c4, c4 + 4, c4 + 8 (NB <= 80: at most ten groups)
+#pragma unroll
+            for (int i2 = 0; i2 < 3; ++i2)
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const int col = gi * 8 + j;
-                    v[j] = (row_ok && col < V) ? __ldg(dprow + col) : 0.f;
+                    const int col = (c4 + 4 * i2) * 8 + j;
+                    v[i2][j] = (row_ok && col < V) ? __ldg(dprow + col) : 0.f;
                 }
+#pragma unroll
+            for (int i2 = 0; i2 < 3; ++i2) {
+                const int gi = c4 + 4 * i2;
+                if (gi >= NB / 8) continue;
                 uint4 hi, lo;
-                split2(v[0], v[1], hi.x, lo.x);
-                split2(v[2], v[3], hi.y, lo.y);
-                split2(v[4], v[5], hi.z, lo.z);
-                split2(v[6], v[7], hi.w, lo.w);
+                split2(v[i2][0], v[i2][1], hi.x, lo.x);
+                split2(v[i2][2], v[i2][3], hi.y, lo.y);
+                split2(v[i2][4], v[i2][5], hi.z, lo.z);
+                split2(v[i2][6], v[i2][7], hi.w, lo.w);
                 *reinterpret_cast<uint4*>(smem + L.dp + gi * kGroup + r * 16) = hi;
                 *reinterpret_cast<uint4*>(smem + L.dp + L.dp_half + gi * kGroup + r * 16) = lo;
             }
