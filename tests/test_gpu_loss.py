@@ -191,6 +191,18 @@ def test_lattice_sweep_abi_alpha_beta(cuda_lib, oracle_lib):
         assert int(alpha[b, Tb:].abs().sum()) == 0 and int(beta[b, :, Ub + 1:].abs().sum()) == 0
 
 
+@pytest.mark.parametrize("U", [0, 1, 30, 31, 32, 62, 63, 64, 94, 95, 96, 126, 127, 128, 160])
+def test_sweep_warp_boundaries(cuda_lib, oracle_lib, U):
+    """Label lengths around every multiple of 32: one / two / three / four chain warps of the
+    warp-specialised sweep (U1 <= 128) and the first size of the cluster kernel (U1 > 128), with
+    T shorter and longer than the helpers' 64-row windows, ragged lengths included."""
+    for T in (3, 45, 150):
+        d = synthetic.make_dense_logits(3, T, U, 6, ragged=True, seed=100 + U + T)
+        r32, r64 = oracle_pair(oracle_lib, d)
+        costs, grads = run_dense(d["logits"], d["labels"], d["act_lens"], d["label_lens"])
+        check_against_oracles(costs, grads, r32, r64)
+
+
 def test_long_lattice_matches_oracle(cuda_lib, oracle_lib):
     """cfg-3-shaped deep sweep (T=1500, U=300; 1800 anti-diagonals) at small V."""
     d = synthetic.make_dense_logits(2, 1500, 300, 8, ragged=True, seed=33)
