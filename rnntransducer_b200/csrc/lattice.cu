@@ -287,33 +287,40 @@ lattice_sweep_kernel(const float2* __restrict__ lp2, const int32_t* __restrict__
 // At small batch sizes the sweep is bound by the latency of ONE warp walking T + U dependent steps,
 // and two thirds of that warp's instructions are not the recursion at all: fetching and splitting
 // the log-probabilities, packing and storing the result, address and predicate arithmetic.  Here
-// every chain warp has a helper warp (on another scheduler of the same SM):
-//   helper  cp.async ring -> (mantissa, exponent) factors of the next steps -> shared-memory ring;
-//           and, two blocks behind, lattice values from the chain's ring -> e16m16 -> global
+// every chain warp has four helper warps (see the roles below):
 //   chain   factors (one 16-byte load) -> hand-off -> add / normalise / multiply -> value (one 8-byte
-//           store); nothing else
+//           store); nothing else: 24 instructions, ~94 cycles per step when run alone
 // Rings are handed over in blocks of 8 steps through mbarriers (one elected arrival per warp after
 // a __syncwarp: 32 arrivals on one address serialise); the chain warps of one CTA keep the 8-step
 // skew and meet at a named barrier that the helpers never join.
+// Measured at cfg 2 (B=32, T=400, U=80): chain alone 29 us; + hand-shakes 35 us; + helper work 53 us.
 constexpr int kWsStages = 3;
-constexpr int kWin = 64;        // rows of the helper's two shared-memory windows (power of two)
-constexpr int kRowsAhead = 3;   // blocks of 8 rows in flight: 31 + 8 (kRowsAhead + 1) <= kWin - 1
+constexpr int kHalf = 8;        // steps whose loads / arithmetic / stores are batched for instruction-level parallelism
+constexpr int kWsEdgeRing = 64; // >= 2 * KB + 1 slots for warp-boundary values
+constexpr int kWin = 64;        // rows of the consumer's shared-memory window (power of two)
+constexpr int kRowBars = 16;    // ring of row-block barriers (> blocks the loader may run ahead)
 
-struct WsWarp {  // shared memory of one chain / helper pair
-    uint4 fac[kWsStages][kUnroll][32];        // (m_blank, e_blank, m_label, e_label) per step and lane
-    int2 val[kWsStages][kUnroll][32];         // normalised lattice value per step and lane
-    float2 raw[kWin * 32];                    // helper: window of lp2 rows (this warp's 32 columns), filled by cp.async
-    int32_t out[kWin * 32];                   // helper: window of packed output rows
+// KB = steps per hand-over block = skew between consecutive chain warps; RW = lattice rows in the
+// loader's window.
+template <int KB, int RW>
+struct WsWarp {  // shared memory of one chain warp and its helpers
+    uint4 fac[kWsStages][KB][32];             // (m_blank, e_blank, m_label, e_label) per step and lane
+    int2 val[kWsStages][KB][32];              // normalised lattice value per step and lane
+    float2 raw[RW * 32];                      // producer: window of RW lp2 rows (this warp's 32 columns), filled by cp.async
+    int32_t out[kWin * 32];                   // consumer: window of packed output rows
     unsigned long long bars[4 * kWsStages];   // full, empty (factors); vfull, vempty (values)
+    unsigned long long rows[kRowBars];        // "the lp2 rows of block b have landed" (loader -> converters)
+    int chain_done;                           // blocks the chain has finished (the loader's window-reuse throttle: a
+                                              // plain counter, because an mbarrier parity cannot name a phase that
+                                              // lies more than one completion back)
 };
-
-template <int DIR, bool kMulti>
-__device__ __forceinline__ void ws_chain(WsWarp& W, int2 (*edge)[33], int w, int nw, int lane, int n_blocks) {
+template <int DIR, bool kMulti, int KB, int RW>
+__device__ __forceinline__ void ws_chain(WsWarp<KB, RW>& W, int2 (*edge)[33], int w, int nw, int lane, int n_blocks) {
     const uint32_t bars = tc::smem_u32(W.bars);
     const int j = w * 32 + lane;
-    const int lag = kMulti ? w * kLag : 0;
+    const int lag = kMulti ? w * KB : 0;
     const int edge_col = (kMulti && w > 0) ? w - 1 : 32;
-    int es = (-lag - 1) & (kEdgeRing - 1);  // edge slot of diagonal d-1
+    int es = (-lag - 1) & (kWsEdgeRing - 1);  // edge slot of diagonal d-1
     ME own{1.f, j == 0 ? 0 : kZeroExp};
     ME share{1.f, kZeroExp};
 #pragma unroll 1
@@ -323,199 +330,269 @@ __device__ __forceinline__ void ws_chain(WsWarp& W, int2 (*edge)[33], int w, int
         if (kMulti) asm volatile("bar.sync 1, %0;" ::"r"(nw * 32) : "memory");  // chain warps only
         tc::mbar_wait(bars + 8 * st, ph);                        // factors of this block are there
         tc::mbar_wait(bars + 8 * (3 * kWsStages + st), ph ^ 1);  // the value slot has been drained
-        uint4 f = W.fac[st][0][lane];
-        // the previous warp is a whole block ahead: all eight boundary values of this block are
-        // already in the ring, fetch them off the dependent chain
-        int2 evs[kUnroll];
+#pragma unroll 1
+        for (int h = 0; h < KB; h += kHalf) {
+            uint4 f = W.fac[st][h][lane];
+            // the previous warp is a whole block ahead: the boundary values of this block are already
+            // in the ring, fetch them off the dependent chain
+            int2 evs[kHalf];
 #pragma unroll
-        for (int k = 0; k < kUnroll; ++k)
-            evs[k] = kMulti ? edge[(es + k) & (kEdgeRing - 1)][edge_col] : make_int2(0x3f800000, kZeroExp);
+            for (int k = 0; k < kHalf; ++k)
+                evs[k] = kMulti ? edge[(es + k) & (kWsEdgeRing - 1)][edge_col] : make_int2(0x3f800000, kZeroExp);
 #pragma unroll
-        for (int k = 0; k < kUnroll; ++k) {
-            const uint4 fn = W.fac[st][k + 1 < kUnroll ? k + 1 : k][lane];  // next step's factors, off the chain
-            ME in;
-            in.m = __shfl_up_sync(0xffffffffu, share.m, 1);
-            in.e = __shfl_up_sync(0xffffffffu, share.e, 1);
-            if (lane == 0) in = ME{__int_as_float(evs[k].x), evs[k].y};
-            const ME pb{__uint_as_float(f.x), (int)f.y}, pl{__uint_as_float(f.z), (int)f.w};
-            ME val;
-            if (DIR == 0) {
-                val = me_normalize(me_add(own, in));
-                own = me_mul(val, pb);
-                share = me_mul(val, pl);
-            } else {
-                val = me_normalize(me_add(me_mul(own, pb), me_mul(in, pl)));
-                own = val;
-                share = val;
+            for (int k = 0; k < kHalf; ++k) {
+                const uint4 fn = W.fac[st][h + (k + 1 < kHalf ? k + 1 : k)][lane];  // next step's factors, off the chain
+                ME in;
+                in.m = __shfl_up_sync(0xffffffffu, share.m, 1);
+                in.e = __shfl_up_sync(0xffffffffu, share.e, 1);
+                if (lane == 0) in = ME{__int_as_float(evs[k].x), evs[k].y};
+                const ME pb{__uint_as_float(f.x), (int)f.y}, pl{__uint_as_float(f.z), (int)f.w};
+                ME val;
+                if (DIR == 0) {
+                    val = me_normalize(me_add(own, in));
+                    own = me_mul(val, pb);
+                    share = me_mul(val, pl);
+                } else {
+                    val = me_normalize(me_add(me_mul(own, pb), me_mul(in, pl)));
+                    own = val;
+                    share = val;
+                }
+                W.val[st][h + k][lane] = make_int2(__float_as_int(val.m), val.e);
+                if (kMulti) {
+                    es = (es + 1) & (kWsEdgeRing - 1);  // now the slot of diagonal d
+                    if (lane == 31) edge[es][w] = make_int2(__float_as_int(share.m), share.e);
+                }
+                f = fn;
             }
-            W.val[st][k][lane] = make_int2(__float_as_int(val.m), val.e);
-            if (kMulti) {
-                es = (es + 1) & (kEdgeRing - 1);  // now the slot of diagonal d
-                if (lane == 31) edge[es][w] = make_int2(__float_as_int(share.m), share.e);
-            }
-            f = fn;
         }
         __syncwarp();  // orders every lane's shared-memory traffic before the one arrival below
         if (lane == 0) {
             tc::mbar_arrive(bars + 8 * (kWsStages + st));      // factor slot free
             tc::mbar_arrive(bars + 8 * (2 * kWsStages + st));  // values of this block are there
+            asm volatile("st.release.cta.shared::cta.s32 [%0], %1;" ::"r"(tc::smem_u32(&W.chain_done)), "r"(blk + 1) : "memory");
         }
     }
 }
 
-// ROLE 0: factor producer (global rows -> window -> split factors); ROLE 1: value consumer (values
-// -> e16m16 -> window -> global rows).  Two warps share the helper work of one chain warp: one alone
-// needs ~2000 cycles per block of 8 steps at a single warp's issue rate, the chain ~800.
-template <int DIR, bool kMulti, int ROLE>
-__device__ __forceinline__ void ws_helper(WsWarp& W, const float2* __restrict__ lp2, int Tb, int Ub, int T, int U1,
-                                          int b, int32_t* __restrict__ out, float* __restrict__ costs,
-                                          float* __restrict__ ll_alpha, int w, int lane, int n_blocks) {
-    const uint32_t bars = tc::smem_u32(W.bars);
-    const int j = w * 32 + lane;
-    const bool lane_on = j < Ub + 1;
-    const unsigned Tb_eff = lane_on ? Tb : 0;  // (unsigned)tau < Tb_eff  <=>  this thread has a cell
-    const int u = DIR == 0 ? j : Ub - j;
-    const int lag = kMulti ? w * kLag : 0;
-    const int stride = DIR == 0 ? U1 : -U1;
-    const size_t first = (size_t)b * T * U1 + (size_t)(DIR == 0 ? 0 : Tb - 1) * U1 + u;
-    const float2* src = lp2 + first;
-    int32_t* dst = out + first;
-    // Global memory is touched ROW-wise (all lanes of one instruction on one lattice row: 256
-    // contiguous bytes of lp2 / 128 of the output plane), the recursion needs the cells DIAGONAL-wise
-    // (lane j is 1 row behind lane j-1).  Both go through shared-memory windows of kWin rows in which
-    // lane j only ever touches column j -- its own copies, its own stores -- so the windows need no
-    // synchronisation at all.  (One lattice row per lane and instruction, as the single-warp sweep
-    // does, costs 32 L1 tag look-ups per instruction: that, not the arithmetic, bounded the sweep.)
-    const int tau0 = -lag - j;                 // this lane's progress at step 0
-    int tau_v = tau0;                          // ... at the step whose value is packed next
-    const int base = lag + 32 * w;             // lane 0 of this warp reaches row s - base at step s
-    int row_st = -base - 31;                   // next row to be stored (complete once lane 31 has passed it)
-    float2* rawc = W.raw + lane;               // column `lane` of the raw window, row stride 32
-    int32_t* outc = W.out + lane;              // column `lane` of the output window
-    const int t_last = (lane_on && j == Ub) ? Tb - 1 : -1;
-    ME last{1.f, kZeroExp};
-    int last_tau = 0;
-
-    auto prefetch_rows = [&](int pb) {  // the eight rows lane 0 reaches in block pb, one cp.async group
-        const int r0 = pb * kUnroll - base;
-#pragma unroll
-        for (int k = 0; k < kUnroll; ++k)
-            if ((unsigned)(r0 + k) < Tb_eff) cp_async_8(rawc + ((r0 + k) & (kWin - 1)) * 32, src + (long long)(r0 + k) * stride);
-        cp_async_commit();
-    };
-    auto store_row = [&](int r) {
-        if ((unsigned)r < Tb_eff) dst[(long long)r * stride] = outc[(r & (kWin - 1)) * 32];
-    };
-    if (ROLE == 0) {
-#pragma unroll
-        for (int pb = 0; pb < kRowsAhead; ++pb) prefetch_rows(pb);
+// Helper roles of one chain warp.  A single warp retires about one instruction every four cycles
+// whatever its instruction-level parallelism, so the ~95-cycle chain step tolerates ~20 helper
+// instructions per step and warp: the helper work is cut into four warps.
+//   loader     lp2 rows -> cp.async -> shared window; publishes "rows of block b landed"
+//   convert x2 one for p(blank), one for p(label): window (diagonal read) -> (mantissa, exponent) -> factor ring
+//   consumer   value ring -> e16m16 -> output window (diagonal write) -> global rows
+// Global memory is touched ROW-wise (all lanes of one instruction on one lattice row: 256 contiguous
+// bytes of lp2 / 128 of the output plane) although the recursion needs the cells DIAGONAL-wise (lane j
+// is 1 row behind lane j-1): both directions go through shared-memory windows in which lane j only
+// ever touches column j.  (One lattice row per lane and instruction, as the single-warp sweep does,
+// costs 32 L1 tag look-ups per instruction.)
+template <int DIR, bool kMulti, int KB>
+struct WsGeom {  // what every helper derives from (warp, lane, utterance)
+    int j, lag, base, tau0, stride;
+    unsigned Tb_eff;
+    size_t first;
+    __device__ WsGeom(int Tb, int Ub, int T, int U1, int b, int w, int lane) {
+        j = w * 32 + lane;
+        Tb_eff = j < Ub + 1 ? Tb : 0;  // (unsigned)tau < Tb_eff  <=>  this thread has a cell
+        const int u = DIR == 0 ? j : Ub - j;
+        lag = kMulti ? w * KB : 0;
+        base = lag + 32 * w;           // lane 0 of this warp reaches row s - base at step s
+        tau0 = -lag - j;               // this lane's progress at step 0
+        stride = DIR == 0 ? U1 : -U1;
+        first = (size_t)b * T * U1 + (size_t)(DIR == 0 ? 0 : Tb - 1) * U1 + u;
     }
+};
+
+template <int DIR, bool kMulti, int KB, int RW>
+__device__ __forceinline__ void ws_loader(WsWarp<KB, RW>& W, const float2* __restrict__ lp2, int Tb, int Ub, int T,
+                                          int U1, int b, int w, int lane, int n_blocks) {
+    constexpr int kRun = RW / KB - 5;             // blocks the loader may run ahead of the chain (window reuse)
+    constexpr int kFly = kRun > 5 ? 4 : kRun - 1; // cp.async groups in flight (~750 cycles each)
+    static_assert(kRun >= 2 && kRun + 1 < kRowBars, "window too small for this block size");
+    const WsGeom<DIR, kMulti, KB> G(Tb, Ub, T, U1, b, w, lane);
+    const uint32_t rows = tc::smem_u32(W.rows), progress = tc::smem_u32(&W.chain_done);
+    float2* rawc = W.raw + lane;                  // column `lane` of the window, row stride 32
+    const float2* p = lp2 + G.first + (long long)(-G.base) * G.stride;  // row -base: the first one block 0 needs
+    int r = -G.base;
 #pragma unroll 1
-    for (int blk = ROLE == 0 ? 0 : 2; blk < (ROLE == 0 ? n_blocks : n_blocks + 2); ++blk) {
-        if (ROLE == 0) {
-            const int st = blk % kWsStages;
-            prefetch_rows(blk + kRowsAhead);
-            cp_async_wait<kRowsAhead>();  // the rows of block blk (and everything older) have landed
-            tc::mbar_wait(bars + 8 * (kWsStages + st), ((blk / kWsStages) & 1) ^ 1);
-            const int tau = tau0 + blk * kUnroll;
-            // all loads, then all arithmetic, then all stores: eight independent streams in flight
-            // (a single warp issues one instruction every ~4 cycles when each depends on the last)
-            float2 lp[kUnroll];
-#pragma unroll
-            for (int k = 0; k < kUnroll; ++k) lp[k] = rawc[((tau + k) & (kWin - 1)) * 32];
-            uint4 fv[kUnroll];
-#pragma unroll
-            for (int k = 0; k < kUnroll; ++k) {
-                const bool on = (unsigned)(tau + k) < Tb_eff;  // no cell: factors 1
-                const ME pb = me_from_log(on ? lp[k].x : 0.f), pl = me_from_log(on ? lp[k].y : 0.f);
-                fv[k] = make_uint4(__float_as_uint(pb.m), (unsigned)pb.e, __float_as_uint(pl.m), (unsigned)pl.e);
+    for (int pb = 0; pb < n_blocks + kFly; ++pb) {
+        if (pb < n_blocks) {
+            // the chain (hence the converters) must have finished block pb - kRun before its rows are overwritten
+            if (pb >= kRun) {
+                int done;
+                for (;;) {
+                    asm volatile("ld.acquire.cta.shared::cta.s32 %0, [%1];" : "=r"(done) : "r"(progress) : "memory");
+                    if (done > pb - kRun) break;
+                    __nanosleep(64);
+                }
             }
 #pragma unroll
-            for (int k = 0; k < kUnroll; ++k) W.fac[st][k][lane] = fv[k];
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive(bars + 8 * st);
+            for (int k = 0; k < KB; ++k) {
+                if ((unsigned)r < G.Tb_eff) cp_async_8(rawc + (r & (RW - 1)) * 32, p);
+                ++r;
+                p += G.stride;
+            }
         }
-        if (ROLE == 1) {
-            const int vb = blk - 2, st = vb % kWsStages;
-            tc::mbar_wait(bars + 8 * (2 * kWsStages + st), (vb / kWsStages) & 1);
-            int2 v[kUnroll];
+        cp_async_commit();
+        cp_async_wait<kFly>();  // the rows of block pb - kFly (and everything older) have landed
+        const int done = pb - kFly;
+        if (done >= 0) {
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(rows + 8 * (done % kRowBars));
+        }
+    }
+}
+
+// COMP 0: p(blank) -> fac[..].xy; COMP 1: p(label) -> fac[..].zw
+template <int DIR, bool kMulti, int COMP, int KB, int RW>
+__device__ __forceinline__ void ws_convert(WsWarp<KB, RW>& W, int Tb, int Ub, int T, int U1, int b, int w, int lane,
+                                           int n_blocks) {
+    const WsGeom<DIR, kMulti, KB> G(Tb, Ub, T, U1, b, w, lane);
+    const uint32_t bars = tc::smem_u32(W.bars), rows = tc::smem_u32(W.rows);
+    const float* rawc = reinterpret_cast<const float*>(W.raw + lane) + COMP;
+#pragma unroll 1
+    for (int blk = 0; blk < n_blocks; ++blk) {
+        const int st = blk % kWsStages;
+        tc::mbar_wait(rows + 8 * (blk % kRowBars), (blk / kRowBars) & 1);                   // rows landed
+        tc::mbar_wait(bars + 8 * (kWsStages + st), ((blk / kWsStages) & 1) ^ 1);            // ring slot free
+#pragma unroll 1
+        for (int h = 0; h < KB; h += kHalf) {
+            const int tau = G.tau0 + blk * KB + h;
+            float lp[kHalf];  // all loads, then all arithmetic, then all stores
 #pragma unroll
-            for (int k = 0; k < kUnroll; ++k) v[k] = W.val[st][k][lane];
-            int pk[kUnroll];
+            for (int k = 0; k < kHalf; ++k) lp[k] = rawc[((tau + k) & (RW - 1)) * 64];
+            uint2 fv[kHalf];
 #pragma unroll
-            for (int k = 0; k < kUnroll; ++k) pk[k] = me_pack(ME{__int_as_float(v[k].x), v[k].y});
+            for (int k = 0; k < kHalf; ++k) {
+                const ME f = me_from_log((unsigned)(tau + k) < G.Tb_eff ? lp[k] : 0.f);  // no cell: factor 1
+                fv[k] = make_uint2(__float_as_uint(f.m), (unsigned)f.e);
+            }
 #pragma unroll
-            for (int k = 0; k < kUnroll; ++k) outc[((tau_v + k) & (kWin - 1)) * 32] = pk[k];
-            if ((unsigned)(t_last - tau_v) < (unsigned)kUnroll) {  // the terminal cell is in this block (one lane, once)
+            for (int k = 0; k < kHalf; ++k) reinterpret_cast<uint2*>(&W.fac[st][h + k][lane])[COMP] = fv[k];
+        }
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(bars + 8 * st);  // one of the two arrivals that complete "full"
+    }
+}
+
+template <int DIR, bool kMulti, int KB, int RW>
+__device__ __forceinline__ void ws_consumer(WsWarp<KB, RW>& W, const float2* __restrict__ lp2, int Tb, int Ub, int T,
+                                            int U1, int b, int32_t* __restrict__ out, float* __restrict__ costs,
+                                            float* __restrict__ ll_alpha, int w, int lane, int n_blocks) {
+    const WsGeom<DIR, kMulti, KB> G(Tb, Ub, T, U1, b, w, lane);
+    const uint32_t bars = tc::smem_u32(W.bars);
+    int32_t* outc = W.out + lane;              // column `lane` of the output window
+    int tau_v = G.tau0;                        // progress at the step whose value is packed next
+    int row_st = -G.base - 31;                 // next row to be stored (complete once lane 31 has passed it)
+    int32_t* pst = out + G.first + (long long)row_st * G.stride;
+    const int t_last = (G.Tb_eff != 0 && G.j == Ub) ? Tb - 1 : -1;
+    ME last{1.f, kZeroExp};
+#pragma unroll 1
+    for (int vb = 0; vb < n_blocks; ++vb) {
+        const int st = vb % kWsStages;
+        tc::mbar_wait(bars + 8 * (2 * kWsStages + st), (vb / kWsStages) & 1);
+#pragma unroll 1
+        for (int h = 0; h < KB; h += kHalf) {
+            int2 v[kHalf];
 #pragma unroll
-                for (int k = 0; k < kUnroll; ++k)
+            for (int k = 0; k < kHalf; ++k) v[k] = W.val[st][h + k][lane];
+            int pk[kHalf];
+#pragma unroll
+            for (int k = 0; k < kHalf; ++k) pk[k] = me_pack(ME{__int_as_float(v[k].x), v[k].y});
+#pragma unroll
+            for (int k = 0; k < kHalf; ++k) outc[((tau_v + k) & (kWin - 1)) * 32] = pk[k];
+            if ((unsigned)(t_last - tau_v) < (unsigned)kHalf) {  // the terminal cell is here (one lane, once)
+#pragma unroll
+                for (int k = 0; k < kHalf; ++k)
                     if (tau_v + k == t_last) last = ME{__int_as_float(v[k].x), v[k].y};
             }
-            tau_v += kUnroll;
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive(bars + 8 * (3 * kWsStages + st));
-            // lane 31 has now passed rows row_st .. row_st + 7
-            int ov[kUnroll];
+            tau_v += kHalf;
+        }
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(bars + 8 * (3 * kWsStages + st));
+        // lane 31 has now passed rows row_st .. row_st + KB - 1
+#pragma unroll 1
+        for (int h = 0; h < KB; h += kHalf) {
+            int ov[kHalf];
 #pragma unroll
-            for (int k = 0; k < kUnroll; ++k) ov[k] = outc[((row_st + k) & (kWin - 1)) * 32];
+            for (int k = 0; k < kHalf; ++k) ov[k] = outc[((row_st + k) & (kWin - 1)) * 32];
 #pragma unroll
-            for (int k = 0; k < kUnroll; ++k)
-                if ((unsigned)(row_st + k) < Tb_eff) dst[(long long)(row_st + k) * stride] = ov[k];
-            row_st += kUnroll;
+            for (int k = 0; k < kHalf; ++k) {
+                if ((unsigned)(row_st + k) < G.Tb_eff) *pst = ov[k];
+                pst += G.stride;
+            }
+            row_st += kHalf;
         }
     }
-    if (ROLE == 0) {
-        cp_async_wait<0>();
-        return;
-    }
-    for (; row_st < Tb; ++row_st) store_row(row_st);  // rows the last lanes finished in the final blocks
-    last_tau = t_last;
+    for (; row_st < Tb; ++row_st, pst += G.stride)  // rows the last lanes finished in the final blocks
+        if ((unsigned)row_st < G.Tb_eff) *pst = outc[(row_st & (kWin - 1)) * 32];
     if (t_last >= 0) {
         if (DIR == 0) {
-            if (ll_alpha) ll_alpha[b] = (float)me_ln(me_normalize(me_mul(last, me_from_log(src[(long long)last_tau * stride].x))));
+            if (ll_alpha) {
+                const float2* src = lp2 + G.first;
+                ll_alpha[b] = (float)me_ln(me_normalize(me_mul(last, me_from_log(src[(long long)t_last * G.stride].x))));
+            }
         } else {
             costs[b] = (float)(-me_ln(last));
         }
     }
 }
 
-template <bool kMulti>
-__global__ void __launch_bounds__(384, 1)
+template <bool kMulti, int KB, int RW>
+__global__ void __launch_bounds__(640, 1)
 lattice_sweep_ws_kernel(const float2* __restrict__ lp2, const int32_t* __restrict__ act_lens,
                         const int32_t* __restrict__ label_lens, int T, int U1, int32_t* __restrict__ alpha,
                         int32_t* __restrict__ beta, float* __restrict__ costs, float* __restrict__ ll_alpha) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    WsWarp* ws = reinterpret_cast<WsWarp*>(smem_raw);
-    __shared__ int2 edge[kEdgeRing][33];
-    const int nw = blockDim.x / 96;  // warps [0, nw): chains, [nw, 2 nw): factor producers, [2 nw, 3 nw): value consumers
+    WsWarp<KB, RW>* ws = reinterpret_cast<WsWarp<KB, RW>*>(smem_raw);
+    __shared__ int2 edge[kWsEdgeRing][33];
+    const int nw = blockDim.x / 160;  // warps [0, nw): chains, then nw loaders, 2 nw converters, nw consumers
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x;
     const int Tb = min(max(act_lens[b], 1), T);
     const int Ub = min(max(label_lens[b], 0), U1 - 1);
-    if ((int)threadIdx.x < nw)
-        for (int i = 0; i < 4 * kWsStages; ++i) tc::mbar_init(tc::smem_u32(ws[threadIdx.x].bars + i), 1);
+    if ((int)threadIdx.x < nw) {
+        WsWarp<KB, RW>& W = ws[threadIdx.x];
+        for (int i = 0; i < 4 * kWsStages; ++i) tc::mbar_init(tc::smem_u32(W.bars + i), i < kWsStages ? 2 : 1);
+        for (int i = 0; i < kRowBars; ++i) tc::mbar_init(tc::smem_u32(W.rows + i), 1);
+        W.chain_done = 0;
+    }
     tc::fence_barrier_init();
     if (kMulti)
-        for (int i = threadIdx.x; i < kEdgeRing * 33; i += blockDim.x) edge[i / 33][i % 33] = make_int2(0x3f800000, kZeroExp);
+        for (int i = threadIdx.x; i < kWsEdgeRing * 33; i += blockDim.x) edge[i / 33][i % 33] = make_int2(0x3f800000, kZeroExp);
     __syncthreads();
     // every warp runs the same number of steps (uniform barriers), rounded up to whole blocks
-    const int max_lag = kMulti ? ((Ub + 32) / 32 - 1) * kLag : 0;
-    const int n_blocks = (Tb + Ub + max_lag + kUnroll - 1) / kUnroll;
-    const int w = warp % nw;
-    if (warp < nw) {
-        if (blockIdx.y == 0) ws_chain<0, kMulti>(ws[w], edge, w, nw, lane, n_blocks);
-        else ws_chain<1, kMulti>(ws[w], edge, w, nw, lane, n_blocks);
-    } else if (warp < 2 * nw) {
-        if (blockIdx.y == 0)
-            ws_helper<0, kMulti, 0>(ws[w], lp2, Tb, Ub, T, U1, b, alpha, costs, ll_alpha, w, lane, n_blocks);
-        else
-            ws_helper<1, kMulti, 0>(ws[w], lp2, Tb, Ub, T, U1, b, beta, costs, ll_alpha, w, lane, n_blocks);
+    const int max_lag = kMulti ? ((Ub + 32) / 32 - 1) * KB : 0;
+    const int n_blocks = (Tb + Ub + max_lag + KB - 1) / KB;
+    const int w = warp % nw, role = warp / nw;
+    const bool fwd = blockIdx.y == 0;
+    int32_t* plane = fwd ? alpha : beta;
+    if (role == 0) {
+        if (fwd) ws_chain<0, kMulti, KB, RW>(ws[w], edge, w, nw, lane, n_blocks);
+        else ws_chain<1, kMulti, KB, RW>(ws[w], edge, w, nw, lane, n_blocks);
+    } else if (role == 1) {
+        if (fwd) ws_loader<0, kMulti, KB, RW>(ws[w], lp2, Tb, Ub, T, U1, b, w, lane, n_blocks);
+        else ws_loader<1, kMulti, KB, RW>(ws[w], lp2, Tb, Ub, T, U1, b, w, lane, n_blocks);
+    } else if (role == 2) {
+        if (fwd) ws_convert<0, kMulti, 0, KB, RW>(ws[w], Tb, Ub, T, U1, b, w, lane, n_blocks);
+        else ws_convert<1, kMulti, 0, KB, RW>(ws[w], Tb, Ub, T, U1, b, w, lane, n_blocks);
+    } else if (role == 3) {
+        if (fwd) ws_convert<0, kMulti, 1, KB, RW>(ws[w], Tb, Ub, T, U1, b, w, lane, n_blocks);
+        else ws_convert<1, kMulti, 1, KB, RW>(ws[w], Tb, Ub, T, U1, b, w, lane, n_blocks);
     } else {
-        if (blockIdx.y == 0)
-            ws_helper<0, kMulti, 1>(ws[w], lp2, Tb, Ub, T, U1, b, alpha, costs, ll_alpha, w, lane, n_blocks);
-        else
-            ws_helper<1, kMulti, 1>(ws[w], lp2, Tb, Ub, T, U1, b, beta, costs, ll_alpha, w, lane, n_blocks);
+        if (fwd) ws_consumer<0, kMulti, KB, RW>(ws[w], lp2, Tb, Ub, T, U1, b, plane, costs, ll_alpha, w, lane, n_blocks);
+        else ws_consumer<1, kMulti, KB, RW>(ws[w], lp2, Tb, Ub, T, U1, b, plane, costs, ll_alpha, w, lane, n_blocks);
     }
+}
+
+template <bool kMulti, int KB, int RW>
+int launch_ws(const float2* lp2, const int32_t* act_lens, const int32_t* label_lens, int B, int T, int U1,
+              int32_t* alpha, int32_t* beta, float* costs, float* ll_alpha, int warps, cudaStream_t stream) {
+    const size_t smem = (size_t)warps * sizeof(WsWarp<KB, RW>);
+    cudaError_t e = cudaFuncSetAttribute(lattice_sweep_ws_kernel<kMulti, KB, RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return status_from_cuda(e);
+    lattice_sweep_ws_kernel<kMulti, KB, RW><<<dim3(B, 2), warps * 160, smem, stream>>>(lp2, act_lens, label_lens, T, U1, alpha,
+                                                                                   beta, costs, ll_alpha);
+    return launch_status();
 }
 
 }  // namespace
@@ -527,21 +604,12 @@ int launch_lattice_sweep(const float2* lp2, const int32_t* act_lens, const int32
     if (U1 > 1024) return RNNTB200_STATUS_INVALID_VALUE;
     const int warps = (U1 + 31) / 32;
     static const bool legacy = getenv("RNNTB200_SWEEP_LEGACY") != nullptr;  // A/B timing of the one-warp-does-all sweep
-    if (warps <= 4 && !legacy) {  // chain warps + two helper warps each
-        const size_t smem = (size_t)warps * sizeof(WsWarp);
-        cudaError_t e;
-        if (warps == 1) {
-            e = cudaFuncSetAttribute(lattice_sweep_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return status_from_cuda(e);
-            lattice_sweep_ws_kernel<false><<<dim3(B, 2), 96, smem, stream>>>(lp2, act_lens, label_lens, T, U1, alpha,
-                                                                             beta, costs, ll_alpha);
-        } else {
-            e = cudaFuncSetAttribute(lattice_sweep_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return status_from_cuda(e);
-            lattice_sweep_ws_kernel<true><<<dim3(B, 2), warps * 96, smem, stream>>>(lp2, act_lens, label_lens, T, U1,
-                                                                                    alpha, beta, costs, ll_alpha);
-        }
-        return launch_status();
+    if (warps <= 4 && !legacy) {  // chain warps + four helper warps each
+        // 8-step blocks; the producer's window holds 128 lattice rows (88 requested ahead) where the shared
+        // memory allows it (up to three chain warps), 64 rows (24 ahead) for four
+        if (warps == 1) return launch_ws<false, 8, 128>(lp2, act_lens, label_lens, B, T, U1, alpha, beta, costs, ll_alpha, 1, stream);
+        if (warps <= 3) return launch_ws<true, 8, 128>(lp2, act_lens, label_lens, B, T, U1, alpha, beta, costs, ll_alpha, warps, stream);
+        return launch_ws<true, 8, 64>(lp2, act_lens, label_lens, B, T, U1, alpha, beta, costs, ll_alpha, warps, stream);
     }
     if (warps == 1) {
         const size_t smem = (size_t)kRingStride * 32 * sizeof(float2);
