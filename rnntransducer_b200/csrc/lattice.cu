@@ -28,6 +28,10 @@
 // Loads.  The (lp_blank, lp_label) pair of a cell is one 8-byte cp.async into a per-thread slot
 // of a shared-memory ring, issued kDepth-1 diagonals ahead (the loads do not depend on the
 // recursion), so HBM latency is off the dependent chain.
+//
+// Label sequences of up to 128 positions run the warp-specialised variant in the second half of
+// this file (chain warps that only do the recursion + helper warps for everything else); the
+// kernel described above serves longer sequences, spread over a thread-block cluster.
 #include <cstdlib>
 
 #include "tc_common.cuh"
