@@ -303,6 +303,19 @@ constexpr int kHalf = 8;        // steps whose loads / arithmetic / stores are b
 constexpr int kWsEdgeRing = 64; // >= 2 * KB + 1 slots for warp-boundary values
 constexpr int kWin = 64;        // rows of the consumer's shared-memory window (power of two)
 constexpr int kRowBars = 16;    // ring of row-block barriers (> blocks the loader may run ahead)
+constexpr int kBandSkew = 32;   // steps the first chain warp of a CTA trails the last one of the previous CTA (cluster)
+
+// Label sequences beyond four chain warps: the sweep is cut into BANDS of three chain warps, one CTA of a
+// thread-block cluster each.  The value crossing a band boundary is forwarded by the consumer helper
+// of the band's last chain warp straight into the next CTA's shared memory (st.shared::cluster into
+// `xedge`, one slot per step of the whole sweep: no ring, hence no back-pressure), followed by a
+// release store of the finished block count (`xdone`) that the receiving chain warp polls locally.
+struct WsBand {
+    int band, n_bands;   // this CTA's rank in the cluster
+    int xlag;            // extra skew of this band: band * (kBandSkew - KB)
+    int2* xedge;         // [n_blocks * KB] boundary values from the previous band (local shared memory)
+    int* xdone;          // blocks the previous band's last warp has forwarded (local shared memory)
+};
 
 // KB = steps per hand-over block = skew between consecutive chain warps; RW = lattice rows in the
 // loader's window.
@@ -319,11 +332,15 @@ struct WsWarp {  // shared memory of one chain warp and its helpers
                                               // lies more than one completion back)
 };
 template <int DIR, bool kMulti, int KB, int RW>
-__device__ __forceinline__ void ws_chain(WsWarp<KB, RW>& W, int2 (*edge)[33], int w, int nw, int lane, int n_blocks) {
+__device__ __forceinline__ void ws_chain(WsWarp<KB, RW>& W, int2 (*edge)[33], int w, int nw, int lane, int n_blocks,
+                                         const WsBand& X) {
     const uint32_t bars = tc::smem_u32(W.bars);
-    const int j = w * 32 + lane;
-    const int lag = kMulti ? w * KB : 0;
+    const int wg = X.band * nw + w;  // position of this warp in the whole sweep
+    const int j = wg * 32 + lane;
+    const int lag = kMulti ? wg * KB + X.xlag : 0;
     const int edge_col = (kMulti && w > 0) ? w - 1 : 32;
+    const bool from_band = kMulti && w == 0 && X.band > 0;  // lane 0's neighbour lives in the previous CTA
+    const uint32_t xdone = tc::smem_u32(X.xdone);
     int es = (-lag - 1) & (kWsEdgeRing - 1);  // edge slot of diagonal d-1
     ME own{1.f, j == 0 ? 0 : kZeroExp};
     ME share{1.f, kZeroExp};
@@ -334,6 +351,14 @@ __device__ __forceinline__ void ws_chain(WsWarp<KB, RW>& W, int2 (*edge)[33], in
         if (kMulti) asm volatile("bar.sync 1, %0;" ::"r"(nw * 32) : "memory");  // chain warps only
         tc::mbar_wait(bars + 8 * st, ph);                        // factors of this block are there
         tc::mbar_wait(bars + 8 * (3 * kWsStages + st), ph ^ 1);  // the value slot has been drained
+        if (from_band && blk >= kBandSkew / KB) {  // the previous band has forwarded what this block reads
+            int done;
+            for (;;) {
+                asm volatile("ld.acquire.cluster.shared::cta.s32 %0, [%1];" : "=r"(done) : "r"(xdone) : "memory");
+                if (done > blk - kBandSkew / KB) break;
+                __nanosleep(32);
+            }
+        }
 #pragma unroll 1
         for (int h = 0; h < KB; h += kHalf) {
             uint4 f = W.fac[st][h][lane];
@@ -341,8 +366,13 @@ __device__ __forceinline__ void ws_chain(WsWarp<KB, RW>& W, int2 (*edge)[33], in
             // in the ring, fetch them off the dependent chain
             int2 evs[kHalf];
 #pragma unroll
-            for (int k = 0; k < kHalf; ++k)
+            for (int k = 0; k < kHalf; ++k) {
                 evs[k] = kMulti ? edge[(es + k) & (kWsEdgeRing - 1)][edge_col] : make_int2(0x3f800000, kZeroExp);
+                if (from_band) {
+                    const int q = blk * KB + h + k - lag - 1;  // the previous band's step index of diagonal d-1
+                    evs[k] = q >= 0 ? X.xedge[q] : make_int2(0x3f800000, kZeroExp);
+                }
+            }
 #pragma unroll
             for (int k = 0; k < kHalf; ++k) {
                 const uint4 fn = W.fac[st][h + (k + 1 < kHalf ? k + 1 : k)][lane];  // next step's factors, off the chain
@@ -394,12 +424,12 @@ struct WsGeom {  // what every helper derives from (warp, lane, utterance)
     int j, lag, base, tau0, stride;
     unsigned Tb_eff;
     size_t first;
-    __device__ WsGeom(int Tb, int Ub, int T, int U1, int b, int w, int lane) {
-        j = w * 32 + lane;
+    __device__ WsGeom(int Tb, int Ub, int T, int U1, int b, int wg, int lane, int xlag) {  // wg: warp in the whole sweep
+        j = wg * 32 + lane;
         Tb_eff = j < Ub + 1 ? Tb : 0;  // (unsigned)tau < Tb_eff  <=>  this thread has a cell
         const int u = DIR == 0 ? j : Ub - j;
-        lag = kMulti ? w * KB : 0;
-        base = lag + 32 * w;           // lane 0 of this warp reaches row s - base at step s
+        lag = kMulti ? wg * KB + xlag : 0;
+        base = lag + 32 * wg;          // lane 0 of this warp reaches row s - base at step s
         tau0 = -lag - j;               // this lane's progress at step 0
         stride = DIR == 0 ? U1 : -U1;
         first = (size_t)b * T * U1 + (size_t)(DIR == 0 ? 0 : Tb - 1) * U1 + u;
@@ -408,11 +438,11 @@ struct WsGeom {  // what every helper derives from (warp, lane, utterance)
 
 template <int DIR, bool kMulti, int KB, int RW>
 __device__ __forceinline__ void ws_loader(WsWarp<KB, RW>& W, const float2* __restrict__ lp2, int Tb, int Ub, int T,
-                                          int U1, int b, int w, int lane, int n_blocks) {
+                                          int U1, int b, int wg, int lane, int n_blocks, int xlag) {
     constexpr int kRun = RW / KB - 5;             // blocks the loader may run ahead of the chain (window reuse)
     constexpr int kFly = kRun > 5 ? 4 : kRun - 1; // cp.async groups in flight (~750 cycles each)
     static_assert(kRun >= 2 && kRun + 1 < kRowBars, "window too small for this block size");
-    const WsGeom<DIR, kMulti, KB> G(Tb, Ub, T, U1, b, w, lane);
+    const WsGeom<DIR, kMulti, KB> G(Tb, Ub, T, U1, b, wg, lane, xlag);
     const uint32_t rows = tc::smem_u32(W.rows), progress = tc::smem_u32(&W.chain_done);
     float2* rawc = W.raw + lane;                  // column `lane` of the window, row stride 32
     const float2* p = lp2 + G.first + (long long)(-G.base) * G.stride;  // row -base: the first one block 0 needs
@@ -448,9 +478,9 @@ __device__ __forceinline__ void ws_loader(WsWarp<KB, RW>& W, const float2* __res
 
 // COMP 0: p(blank) -> fac[..].xy; COMP 1: p(label) -> fac[..].zw
 template <int DIR, bool kMulti, int COMP, int KB, int RW>
-__device__ __forceinline__ void ws_convert(WsWarp<KB, RW>& W, int Tb, int Ub, int T, int U1, int b, int w, int lane,
-                                           int n_blocks) {
-    const WsGeom<DIR, kMulti, KB> G(Tb, Ub, T, U1, b, w, lane);
+__device__ __forceinline__ void ws_convert(WsWarp<KB, RW>& W, int Tb, int Ub, int T, int U1, int b, int wg, int lane,
+                                           int n_blocks, int xlag) {
+    const WsGeom<DIR, kMulti, KB> G(Tb, Ub, T, U1, b, wg, lane, xlag);
     const uint32_t bars = tc::smem_u32(W.bars), rows = tc::smem_u32(W.rows);
     const float* rawc = reinterpret_cast<const float*>(W.raw + lane) + COMP;
 #pragma unroll 1
@@ -481,9 +511,17 @@ __device__ __forceinline__ void ws_convert(WsWarp<KB, RW>& W, int Tb, int Ub, in
 template <int DIR, bool kMulti, int KB, int RW>
 __device__ __forceinline__ void ws_consumer(WsWarp<KB, RW>& W, const float2* __restrict__ lp2, int Tb, int Ub, int T,
                                             int U1, int b, int32_t* __restrict__ out, float* __restrict__ costs,
-                                            float* __restrict__ ll_alpha, int w, int lane, int n_blocks) {
-    const WsGeom<DIR, kMulti, KB> G(Tb, Ub, T, U1, b, w, lane);
+                                            float* __restrict__ ll_alpha, int w, int nw, int lane, int n_blocks,
+                                            const WsBand& X, const int2 (*edge)[33]) {
+    const WsGeom<DIR, kMulti, KB> G(Tb, Ub, T, U1, b, X.band * nw + w, lane, X.xlag);
     const uint32_t bars = tc::smem_u32(W.bars);
+    // the last chain warp of a band forwards its boundary values to the next CTA of the cluster
+    const bool to_band = kMulti && w == nw - 1 && X.band + 1 < X.n_bands;
+    uint32_t r_xedge = 0, r_xdone = 0;
+    if (to_band) {
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r_xedge) : "r"(tc::smem_u32(X.xedge)), "r"(X.band + 1));
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r_xdone) : "r"(tc::smem_u32(X.xdone)), "r"(X.band + 1));
+    }
     int32_t* outc = W.out + lane;              // column `lane` of the output window
     int tau_v = G.tau0;                        // progress at the step whose value is packed next
     int row_st = -G.base - 31;                 // next row to be stored (complete once lane 31 has passed it)
@@ -510,6 +548,17 @@ __device__ __forceinline__ void ws_consumer(WsWarp<KB, RW>& W, const float2* __r
                     if (tau_v + k == t_last) last = ME{__int_as_float(v[k].x), v[k].y};
             }
             tau_v += kHalf;
+        }
+        if (to_band && lane == 0) {  // slot q of the receiver = this warp's step index minus its lag
+#pragma unroll
+            for (int k = 0; k < KB; ++k) {
+                const int q = vb * KB + k - G.lag;
+                if (q >= 0) {
+                    const int2 ev = edge[q & (kWsEdgeRing - 1)][w];
+                    asm volatile("st.shared::cluster.v2.u32 [%0], {%1, %2};" ::"r"(r_xedge + 8u * (unsigned)q), "r"(ev.x), "r"(ev.y) : "memory");
+                }
+            }
+            asm volatile("st.release.cluster.shared::cluster.s32 [%0], %1;" ::"r"(r_xdone), "r"(vb + 1) : "memory");
         }
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(bars + 8 * (3 * kWsStages + st));
@@ -541,17 +590,25 @@ __device__ __forceinline__ void ws_consumer(WsWarp<KB, RW>& W, const float2* __r
     }
 }
 
-template <bool kMulti, int KB, int RW>
+template <bool kMulti, int KB, int RW, bool kCluster>
 __global__ void __launch_bounds__(640, 1)
 lattice_sweep_ws_kernel(const float2* __restrict__ lp2, const int32_t* __restrict__ act_lens,
                         const int32_t* __restrict__ label_lens, int T, int U1, int32_t* __restrict__ alpha,
-                        int32_t* __restrict__ beta, float* __restrict__ costs, float* __restrict__ ll_alpha) {
+                        int32_t* __restrict__ beta, float* __restrict__ costs, float* __restrict__ ll_alpha,
+                        int xedge_slots) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WsWarp<KB, RW>* ws = reinterpret_cast<WsWarp<KB, RW>*>(smem_raw);
     __shared__ int2 edge[kWsEdgeRing][33];
+    __shared__ int xdone_slot;
     const int nw = blockDim.x / 160;  // warps [0, nw): chains, then nw loaders, 2 nw converters, nw consumers
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.x;
+    WsBand X;
+    X.band = kCluster ? (int)cluster_ctarank() : 0;
+    X.n_bands = kCluster ? (int)cluster_nctarank() : 1;
+    X.xlag = X.band * (kBandSkew - KB);
+    X.xedge = reinterpret_cast<int2*>(ws + nw);  // [xedge_slots], cluster launches only
+    X.xdone = &xdone_slot;
+    const int b = kCluster ? blockIdx.x / X.n_bands : blockIdx.x;
     const int Tb = min(max(act_lens[b], 1), T);
     const int Ub = min(max(label_lens[b], 0), U1 - 1);
     if ((int)threadIdx.x < nw) {
@@ -560,43 +617,83 @@ lattice_sweep_ws_kernel(const float2* __restrict__ lp2, const int32_t* __restric
         for (int i = 0; i < kRowBars; ++i) tc::mbar_init(tc::smem_u32(W.rows + i), 1);
         W.chain_done = 0;
     }
+    if (threadIdx.x == 0) xdone_slot = 0;
     tc::fence_barrier_init();
     if (kMulti)
         for (int i = threadIdx.x; i < kWsEdgeRing * 33; i += blockDim.x) edge[i / 33][i % 33] = make_int2(0x3f800000, kZeroExp);
     __syncthreads();
-    // every warp runs the same number of steps (uniform barriers), rounded up to whole blocks
-    const int max_lag = kMulti ? ((Ub + 32) / 32 - 1) * KB : 0;
-    const int n_blocks = (Tb + Ub + max_lag + KB - 1) / KB;
-    const int w = warp % nw, role = warp / nw;
+    if (kCluster) cluster_barrier();  // no CTA may be written to before it has initialised its shared memory
+    // every warp of every band runs the same number of steps (uniform barriers), rounded up to whole blocks
+    const int n_on = (Ub + 32) / 32;  // chain warps with cells
+    const int max_lag = kMulti ? (n_on - 1) * KB + ((n_on - 1) / nw) * (kBandSkew - KB) : 0;
+    int n_blocks = (Tb + Ub + max_lag + KB - 1) / KB;
+    if (kCluster) n_blocks = min(n_blocks, xedge_slots / KB);  // (the host sized xedge for the longest utterance)
+    const int w = warp % nw, role = warp / nw, wg = X.band * nw + w;
     const bool fwd = blockIdx.y == 0;
     int32_t* plane = fwd ? alpha : beta;
     if (role == 0) {
-        if (fwd) ws_chain<0, kMulti, KB, RW>(ws[w], edge, w, nw, lane, n_blocks);
-        else ws_chain<1, kMulti, KB, RW>(ws[w], edge, w, nw, lane, n_blocks);
+        if (fwd) ws_chain<0, kMulti, KB, RW>(ws[w], edge, w, nw, lane, n_blocks, X);
+        else ws_chain<1, kMulti, KB, RW>(ws[w], edge, w, nw, lane, n_blocks, X);
     } else if (role == 1) {
-        if (fwd) ws_loader<0, kMulti, KB, RW>(ws[w], lp2, Tb, Ub, T, U1, b, w, lane, n_blocks);
-        else ws_loader<1, kMulti, KB, RW>(ws[w], lp2, Tb, Ub, T, U1, b, w, lane, n_blocks);
+        if (fwd) ws_loader<0, kMulti, KB, RW>(ws[w], lp2, Tb, Ub, T, U1, b, wg, lane, n_blocks, X.xlag);
+        else ws_loader<1, kMulti, KB, RW>(ws[w], lp2, Tb, Ub, T, U1, b, wg, lane, n_blocks, X.xlag);
     } else if (role == 2) {
-        if (fwd) ws_convert<0, kMulti, 0, KB, RW>(ws[w], Tb, Ub, T, U1, b, w, lane, n_blocks);
-        else ws_convert<1, kMulti, 0, KB, RW>(ws[w], Tb, Ub, T, U1, b, w, lane, n_blocks);
+        if (fwd) ws_convert<0, kMulti, 0, KB, RW>(ws[w], Tb, Ub, T, U1, b, wg, lane, n_blocks, X.xlag);
+        else ws_convert<1, kMulti, 0, KB, RW>(ws[w], Tb, Ub, T, U1, b, wg, lane, n_blocks, X.xlag);
     } else if (role == 3) {
-        if (fwd) ws_convert<0, kMulti, 1, KB, RW>(ws[w], Tb, Ub, T, U1, b, w, lane, n_blocks);
-        else ws_convert<1, kMulti, 1, KB, RW>(ws[w], Tb, Ub, T, U1, b, w, lane, n_blocks);
+        if (fwd) ws_convert<0, kMulti, 1, KB, RW>(ws[w], Tb, Ub, T, U1, b, wg, lane, n_blocks, X.xlag);
+        else ws_convert<1, kMulti, 1, KB, RW>(ws[w], Tb, Ub, T, U1, b, wg, lane, n_blocks, X.xlag);
     } else {
-        if (fwd) ws_consumer<0, kMulti, KB, RW>(ws[w], lp2, Tb, Ub, T, U1, b, plane, costs, ll_alpha, w, lane, n_blocks);
-        else ws_consumer<1, kMulti, KB, RW>(ws[w], lp2, Tb, Ub, T, U1, b, plane, costs, ll_alpha, w, lane, n_blocks);
+        if (fwd)
+            ws_consumer<0, kMulti, KB, RW>(ws[w], lp2, Tb, Ub, T, U1, b, plane, costs, ll_alpha, w, nw, lane, n_blocks, X, edge);
+        else
+            ws_consumer<1, kMulti, KB, RW>(ws[w], lp2, Tb, Ub, T, U1, b, plane, costs, ll_alpha, w, nw, lane, n_blocks, X, edge);
     }
+    if (kCluster) cluster_barrier();  // no CTA may exit while a neighbour can still write into its shared memory
 }
 
 template <bool kMulti, int KB, int RW>
 int launch_ws(const float2* lp2, const int32_t* act_lens, const int32_t* label_lens, int B, int T, int U1,
               int32_t* alpha, int32_t* beta, float* costs, float* ll_alpha, int warps, cudaStream_t stream) {
     const size_t smem = (size_t)warps * sizeof(WsWarp<KB, RW>);
-    cudaError_t e = cudaFuncSetAttribute(lattice_sweep_ws_kernel<kMulti, KB, RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(lattice_sweep_ws_kernel<kMulti, KB, RW, false>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return status_from_cuda(e);
-    lattice_sweep_ws_kernel<kMulti, KB, RW><<<dim3(B, 2), warps * 160, smem, stream>>>(lp2, act_lens, label_lens, T, U1, alpha,
-                                                                                   beta, costs, ll_alpha);
+    lattice_sweep_ws_kernel<kMulti, KB, RW, false><<<dim3(B, 2), warps * 160, smem, stream>>>(
+        lp2, act_lens, label_lens, T, U1, alpha, beta, costs, ll_alpha, 0);
     return launch_status();
+}
+
+// More than four chain warps: bands of four in a thread-block cluster.  Returns -1 when the boundary
+// buffer of the longest possible sweep does not fit in shared memory (the caller falls back).
+int launch_ws_cluster(const float2* lp2, const int32_t* act_lens, const int32_t* label_lens, int B, int T, int U1,
+                      int32_t* alpha, int32_t* beta, float* costs, float* ll_alpha, int warps, int NW,
+                      cudaStream_t stream) {
+    constexpr int KB = 8, RW = 128;
+    const int n_bands = (warps + NW - 1) / NW;
+    if (n_bands > 8) return -1;
+    const int max_lag = (warps - 1) * KB + (n_bands - 1) * (kBandSkew - KB);
+    const int slots = (T + U1 + max_lag + KB - 1) / KB * KB;
+    const size_t smem = (size_t)NW * sizeof(WsWarp<KB, RW>) + (size_t)slots * sizeof(int2);
+    if (NW < 1 || NW > 3) return -1;
+    if (smem + sizeof(int2) * kWsEdgeRing * 33 + 64 > 227 * 1024) return -1;
+    auto kern = lattice_sweep_ws_kernel<true, KB, RW, true>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return status_from_cuda(e);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(B * n_bands), 2);
+    cfg.blockDim = dim3(NW * 160);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)n_bands;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, kern, lp2, act_lens, label_lens, T, U1, alpha, beta, costs, ll_alpha, slots);
+    return e == cudaSuccess ? launch_status() : status_from_cuda(e);
 }
 
 }  // namespace
@@ -608,12 +705,17 @@ int launch_lattice_sweep(const float2* lp2, const int32_t* act_lens, const int32
     if (U1 > 1024) return RNNTB200_STATUS_INVALID_VALUE;
     const int warps = (U1 + 31) / 32;
     static const bool legacy = getenv("RNNTB200_SWEEP_LEGACY") != nullptr;  // A/B timing of the one-warp-does-all sweep
-    if (warps <= 4 && !legacy) {  // chain warps + four helper warps each
-        // 8-step blocks; the producer's window holds 128 lattice rows (88 requested ahead) where the shared
-        // memory allows it (up to three chain warps), 64 rows (24 ahead) for four
+    // Measured (sweep alone, us):  U1 = 81 (3 warps): 53 warp-specialised in one CTA / 59 single-role;
+    // U1 = 101 (4 warps): 81 in one CTA (20 warps crowd the SM) / 74 as two bands / 68 single-role;
+    // U1 = 301 (10 warps): 245 as five bands of two / 274 as four bands of three / 360 single-role cluster.
+    if (!legacy) {
         if (warps == 1) return launch_ws<false, 8, 128>(lp2, act_lens, label_lens, B, T, U1, alpha, beta, costs, ll_alpha, 1, stream);
         if (warps <= 3) return launch_ws<true, 8, 128>(lp2, act_lens, label_lens, B, T, U1, alpha, beta, costs, ll_alpha, warps, stream);
-        return launch_ws<true, 8, 64>(lp2, act_lens, label_lens, B, T, U1, alpha, beta, costs, ll_alpha, warps, stream);
+        if (warps >= 5) {  // bands of two (up to 16 warps) or three chain warps in a thread-block cluster
+            const int st = launch_ws_cluster(lp2, act_lens, label_lens, B, T, U1, alpha, beta, costs, ll_alpha, warps,
+                                             warps <= 16 ? 2 : 3, stream);
+            if (st >= 0) return st;
+        }
     }
     if (warps == 1) {
         const size_t smem = (size_t)kRingStride * 32 * sizeof(float2);

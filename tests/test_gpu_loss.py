@@ -191,11 +191,12 @@ def test_lattice_sweep_abi_alpha_beta(cuda_lib, oracle_lib):
         assert int(alpha[b, Tb:].abs().sum()) == 0 and int(beta[b, :, Ub + 1:].abs().sum()) == 0
 
 
-@pytest.mark.parametrize("U", [0, 1, 30, 31, 32, 62, 63, 64, 94, 95, 96, 126, 127, 128, 160])
+@pytest.mark.parametrize("U", [0, 1, 30, 31, 32, 62, 63, 64, 94, 95, 96, 126, 127, 128, 160, 200, 520, 800])
 def test_sweep_warp_boundaries(cuda_lib, oracle_lib, U):
-    """Label lengths around every multiple of 32: one / two / three / four chain warps of the
-    warp-specialised sweep (U1 <= 128) and the first size of the cluster kernel (U1 > 128), with
-    T shorter and longer than the helpers' 64-row windows, ragged lengths included."""
+    """Label lengths around every multiple of 32 and in every regime of the sweep dispatch: one / two /
+    three chain warps of the warp-specialised kernel, four warps (single-role kernel), bands of two
+    (U1 <= 512) and of three chain warps in a thread-block cluster, and the single-role cluster kernel
+    beyond; T shorter and longer than the helpers' windows, ragged lengths included."""
     for T in (3, 45, 150):
         d = synthetic.make_dense_logits(3, T, U, 6, ragged=True, seed=100 + U + T)
         r32, r64 = oracle_pair(oracle_lib, d)
