@@ -595,12 +595,15 @@ __global__ void __launch_bounds__(640, 1)
 lattice_sweep_ws_kernel(const float2* __restrict__ lp2, const int32_t* __restrict__ act_lens,
                         const int32_t* __restrict__ label_lens, int T, int U1, int32_t* __restrict__ alpha,
                         int32_t* __restrict__ beta, float* __restrict__ costs, float* __restrict__ ll_alpha,
-                        int xedge_slots) {
+                        int xedge_slots, int nw, int spread) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WsWarp<KB, RW>* ws = reinterpret_cast<WsWarp<KB, RW>*>(smem_raw);
     __shared__ int2 edge[kWsEdgeRing][33];
     __shared__ int xdone_slot;
-    const int nw = blockDim.x / 160;  // warps [0, nw): chains, then nw loaders, 2 nw converters, nw consumers
+    // warps [0, nw): chains, then nw loaders, 2 nw converters, nw consumers -- or, `spread` (two chain
+    // warps): chains on warps 0, 1 and the helpers on warps 2, 3 mod 4 only, so that (warp id mod 4
+    // being the scheduler) no helper shares an issue port with a chain warp; warps 0, 1 mod 4 beyond the
+    // chains stay idle
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     WsBand X;
     X.band = kCluster ? (int)cluster_ctarank() : 0;
@@ -628,7 +631,12 @@ lattice_sweep_ws_kernel(const float2* __restrict__ lp2, const int32_t* __restric
     const int max_lag = kMulti ? (n_on - 1) * KB + ((n_on - 1) / nw) * (kBandSkew - KB) : 0;
     int n_blocks = (Tb + Ub + max_lag + KB - 1) / KB;
     if (kCluster) n_blocks = min(n_blocks, xedge_slots / KB);  // (the host sized xedge for the longest utterance)
-    const int w = warp % nw, role = warp / nw, wg = X.band * nw + w;
+    int w = warp % nw, role = warp / nw;
+    if (spread) {
+        w = warp & 1;
+        role = warp < 2 ? 0 : (warp & 2) ? 1 + (warp >> 2) : 5;  // 2,3 loaders; 6,7 / 10,11 converters; 14,15 consumers
+    }
+    const int wg = X.band * nw + w;
     const bool fwd = blockIdx.y == 0;
     int32_t* plane = fwd ? alpha : beta;
     if (role == 0) {
@@ -643,7 +651,7 @@ lattice_sweep_ws_kernel(const float2* __restrict__ lp2, const int32_t* __restric
     } else if (role == 3) {
         if (fwd) ws_convert<0, kMulti, 1, KB, RW>(ws[w], Tb, Ub, T, U1, b, wg, lane, n_blocks, X.xlag);
         else ws_convert<1, kMulti, 1, KB, RW>(ws[w], Tb, Ub, T, U1, b, wg, lane, n_blocks, X.xlag);
-    } else {
+    } else if (role == 4) {
         if (fwd)
             ws_consumer<0, kMulti, KB, RW>(ws[w], lp2, Tb, Ub, T, U1, b, plane, costs, ll_alpha, w, nw, lane, n_blocks, X, edge);
         else
@@ -660,7 +668,7 @@ int launch_ws(const float2* lp2, const int32_t* act_lens, const int32_t* label_l
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return status_from_cuda(e);
     lattice_sweep_ws_kernel<kMulti, KB, RW, false><<<dim3(B, 2), warps * 160, smem, stream>>>(
-        lp2, act_lens, label_lens, T, U1, alpha, beta, costs, ll_alpha, 0);
+        lp2, act_lens, label_lens, T, U1, alpha, beta, costs, ll_alpha, 0, warps, 0);
     return launch_status();
 }
 
@@ -682,7 +690,8 @@ int launch_ws_cluster(const float2* lp2, const int32_t* act_lens, const int32_t*
     if (e != cudaSuccess) return status_from_cuda(e);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(B * n_bands), 2);
-    cfg.blockDim = dim3(NW * 160);
+    const int spread = NW == 2;  // helpers on schedulers 2, 3 only (16 warps, six of them idle): 246 -> 236 us at cfg 3
+    cfg.blockDim = dim3(spread ? 512 : NW * 160);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -692,7 +701,7 @@ int launch_ws_cluster(const float2* lp2, const int32_t* act_lens, const int32_t*
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, kern, lp2, act_lens, label_lens, T, U1, alpha, beta, costs, ll_alpha, slots);
+    e = cudaLaunchKernelEx(&cfg, kern, lp2, act_lens, label_lens, T, U1, alpha, beta, costs, ll_alpha, slots, NW, spread);
     return e == cudaSuccess ? launch_status() : status_from_cuda(e);
 }
 
