@@ -62,3 +62,48 @@ def joint_loss_fwd_bwd(enc, dec, weight, bias, labels, act_lens, label_lens, bla
     return dict(costs=res["costs"], loss=warp_cpu.reduce_costs(res["costs"], reduction),
                 d_enc=enc_t.grad.numpy(), d_dec=dec_t.grad.numpy(), d_weight=w_t.grad.numpy(),
                 d_bias=b_t.grad.numpy(), logits=logits.detach().numpy(), threads=res["threads"])
+
+
+def joint_loss_fwd_bwd_chunked(enc, dec, weight, bias, labels, act_lens, label_lens, blank=0,
+                               reduction="mean", mode="concat_gelu", num_threads=0, dtype=torch.float64,
+                               frames_per_chunk=None, budget_bytes=1 << 30):
+    """The same CPU step as :func:`joint_loss_fwd_bwd` at BASELINE's FULL sizes (cfg 2/3/4).
+
+    The arithmetic is the reference's, cell by cell (``transducer.py:54-71``: repeat -> cat -> GELU ->
+    Linear, then the loss, then autograd); only the *evaluation order* differs: the ``[B,T,U1,2H]``
+    intermediates (45 GB at cfg 3 in fp32) are formed one (utterance, block of frames) at a time and
+    thrown away, the joint is re-evaluated per block for the backward (``logits_block.backward(
+    d_logits_block)`` accumulates into the same leaves autograd would reach in one piece).  The dense
+    logits ``[B,T,U1,V]`` and their gradient ARE held whole (the loss oracle wants them).
+    Returns numpy costs, loss, d_enc, d_dec, d_weight, d_bias (gradients of the REDUCED loss)."""
+    t = lambda a: torch.as_tensor(np.asarray(a)).to(dtype).clone().requires_grad_(True)
+    enc_t, dec_t, w_t, b_t = t(enc), t(dec), t(weight), t(bias)
+    B, T, _ = enc_t.shape
+    U1, V = dec_t.shape[1], w_t.shape[0]
+    K = w_t.shape[1]
+    if frames_per_chunk is None:  # ~4 live copies of the [tc, U1, K] intermediate under autograd
+        frames_per_chunk = max(1, int(budget_bytes // (4 * U1 * K * enc_t.element_size())))
+    np_dtype = np.float32 if dtype == torch.float32 else np.float64
+    logits = np.empty((B, T, U1, V), dtype=np_dtype)
+    joint = JOINTS[mode]
+    with torch.no_grad():
+        for b in range(B):
+            for t0 in range(0, T, frames_per_chunk):
+                t1 = min(T, t0 + frames_per_chunk)
+                logits[b, t0:t1] = joint(enc_t[b:b + 1, t0:t1], dec_t[b:b + 1], w_t, b_t)[0].numpy()
+    res = warp_cpu.rnnt_loss_cpu(logits, labels, act_lens, label_lens, blank, want_grad=True,
+                                 num_threads=num_threads, dtype=np_dtype)
+    del logits
+    scale = {"mean": 1.0 / B, "sum": 1.0, "none": 1.0}[reduction]
+    grads = res["grads"]
+    for b in range(B):
+        for t0 in range(0, T, frames_per_chunk):
+            t1 = min(T, t0 + frames_per_chunk)
+            g = torch.from_numpy(grads[b, t0:t1]).to(dtype)
+            if not bool(g.any()):
+                continue  # frames past the utterance's length: exactly zero gradient
+            out = joint(enc_t[b:b + 1, t0:t1], dec_t[b:b + 1], w_t, b_t)
+            out.backward((g * scale).unsqueeze(0))
+    z = lambda p: (p.grad if p.grad is not None else torch.zeros_like(p)).numpy()
+    return dict(costs=res["costs"], loss=warp_cpu.reduce_costs(res["costs"], reduction),
+                d_enc=z(enc_t), d_dec=z(dec_t), d_weight=z(w_t), d_bias=z(b_t), threads=res["threads"])

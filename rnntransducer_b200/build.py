@@ -36,21 +36,43 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > mt for d in deps)
 
 
+def _compile_one(nvcc, src, obj, hdr_mtime):
+    """One translation unit -> object file (skipped when the object is newer than source + headers)."""
+    if os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), hdr_mtime):
+        return src, 0, ""
+    cmd = [nvcc] + [f for f in NVCC_FLAGS if f != "-shared"] + ["-c", "-o", obj, src]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    return src, proc.returncode, " ".join(cmd) + "\n" + proc.stdout + proc.stderr
+
+
 def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: librnnt_b200.so must be built where the CUDA toolkit is")
+    from concurrent.futures import ThreadPoolExecutor
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    hdrs = glob.glob(os.path.join(CSRC, "*.cuh")) + [os.path.join(os.path.dirname(HERE), "include", "rnnt_b200.h"), __file__]
+    hdr_mtime = float("inf") if force else max(os.path.getmtime(h) for h in hdrs)
+    objs = [os.path.join(objdir, os.path.basename(s)[:-3] + ".o") for s in sources()]
+    with ThreadPoolExecutor(max_workers=min(len(objs), os.cpu_count() or 1)) as ex:
+        results = list(ex.map(lambda so: _compile_one(nvcc, so[0], so[1], hdr_mtime), zip(sources(), objs)))
+    log = "".join(r[2] for r in results)
     tmp = LIB + ".tmp"
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", tmp] + sources()
-    proc = subprocess.run(cmd, capture_output=True, text=True)
-    log = proc.stdout + proc.stderr
-    with open(os.path.join(HERE, "build.log"), "w") as f:
-        f.write(" ".join(cmd) + "\n" + log)
-    if proc.returncode != 0:
+    failed = [r[0] for r in results if r[1] != 0]
+    if not failed:
+        cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC", "-o", tmp] + objs
+        proc = subprocess.run(cmd, capture_output=True, text=True)
+        log += " ".join(cmd) + "\n" + proc.stdout + proc.stderr
+        if proc.returncode != 0:
+            failed = ["link"]
+    with open(os.path.join(HERE, "build.log"), "a" if not force else "w") as f:
+        f.write(log)
+    if failed:
         sys.stderr.write(log)
-        raise RuntimeError("nvcc failed building librnnt_b200.so")
+        raise RuntimeError(f"nvcc failed building librnnt_b200.so ({failed})")
     os.replace(tmp, LIB)
     if verbose:
         print(log)

@@ -78,6 +78,17 @@ __device__ __forceinline__ float e16m16_log2_ratio(int aq, int bq, int llq) {
     return (float)e + fast_lg2(m);
 }
 
+// Lengths and labels are device data nobody validates on the hot path (that would cost a D2H sync):
+// every kernel reads them through these, so out-of-range values are clamped IDENTICALLY everywhere
+// (act_lens into [1, T], label_lens into [0, U1-1], labels into [0, V-1]) -- never an out-of-bounds
+// access, never one kernel disagreeing with another about an utterance's box.
+// RNNTLoss(check_inputs=True) raises on such inputs instead (one device sync).
+__device__ __forceinline__ int len_T(const int32_t* act_lens, int b, int T) { return min(max(__ldg(act_lens + b), 1), T); }
+__device__ __forceinline__ int len_U(const int32_t* label_lens, int b, int U1) { return min(max(__ldg(label_lens + b), 0), U1 - 1); }
+__device__ __forceinline__ int label_at(const int32_t* labels, int b, int U1, int u, int V) {
+    return min(max(__ldg(labels + (size_t)b * (U1 - 1) + u), 0), V - 1);
+}
+
 inline int status_from_cuda(cudaError_t e) {
     if (e == cudaSuccess) return RNNTB200_STATUS_SUCCESS;
     if (e == cudaErrorInvalidValue || e == cudaErrorInvalidConfiguration) return RNNTB200_STATUS_INVALID_VALUE;

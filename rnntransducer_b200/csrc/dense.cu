@@ -33,7 +33,7 @@ __device__ __forceinline__ CellCoord decode_cell(long long c, long long cells, i
     const int r = (int)(c - (long long)k.b * tu);
     k.t = r / U1;
     k.u = r - k.t * U1;
-    k.valid = k.t < __ldg(act_lens + k.b) && k.u <= __ldg(label_lens + k.b);
+    k.valid = k.t < len_T(act_lens, k.b, T) && k.u <= len_U(label_lens, k.b, U1);
     return k;
 }
 
@@ -110,8 +110,8 @@ dense_lse_kernel(const T* __restrict__ logits, const int32_t* __restrict__ label
             const T* row = logits + (c0 + lane) * V;
             const float lb = fmaxf(to_f32<T>(row[blank]) - my_lse, kNegInf);
             float ll = 0.f;
-            if (my.u < __ldg(label_lens + my.b)) {
-                const int y = __ldg(labels + (size_t)my.b * (U1 - 1) + my.u);
+            if (my.u < len_U(label_lens, my.b, U1)) {
+                const int y = label_at(labels, my.b, U1, my.u, V);
                 ll = fmaxf(to_f32<T>(row[y]) - my_lse, kNegInf);
             }
             lp2[c0 + lane] = make_float2(lb, ll);
@@ -143,7 +143,7 @@ dense_grad_kernel(const T* __restrict__ logits, const int32_t* __restrict__ labe
             continue;
         }
         const T* row = logits + c * V;
-        const int Tb = __ldg(act_lens + k.b), Ub = __ldg(label_lens + k.b);
+        const int Tb = len_T(act_lens, k.b, T_), Ub = len_U(label_lens, k.b, U1);
         const int aq = alpha[c], llq = beta[(long long)k.b * T_ * U1];  // beta(0,0) = log2 P(y|x)
         const float z2 = lse[c] * kLog2e, gc = grad_costs[k.b];
         const float c_all = e16m16_log2_ratio(aq, beta[c], llq) - z2;  // log2(occupancy / partition)
@@ -154,7 +154,7 @@ dense_grad_kernel(const T* __restrict__ logits, const int32_t* __restrict__ labe
         if (k.t < Tb - 1) corr_b = fast_ex2(e16m16_log2_ratio(aq, beta[c + U1], llq) + lb2);
         else if (k.u == Ub) corr_b = fast_ex2(e16m16_log2_ratio(aq, 0, llq) + lb2);
         if (k.u < Ub) {
-            y = __ldg(labels + (size_t)k.b * (U1 - 1) + k.u);
+            y = label_at(labels, k.b, U1, k.u, V);
             const float ll2 = to_f32<T>(row[y]) * kLog2e - z2;
             corr_l = fast_ex2(e16m16_log2_ratio(aq, beta[c + 1], llq) + ll2);
         }

@@ -88,13 +88,13 @@ at_lse_simt_kernel(const float* __restrict__ enc, const float* __restrict__ dec,
     __shared__ int ylab[kUU];
 
     const int b = blockIdx.z, t0 = blockIdx.y * kTT, u0 = blockIdx.x * kUU;
-    const int Tb = min(__ldg(act_lens + b), T), Ub = min(__ldg(label_lens + b), U1 - 1);
+    const int Tb = len_T(act_lens, b, T), Ub = len_U(label_lens, b, U1);
     if (t0 >= Tb || u0 > Ub) return;
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
 
     if (threadIdx.x < kUU) {
         const int u = u0 + threadIdx.x;
-        ylab[threadIdx.x] = u < Ub ? __ldg(labels + (size_t)b * (U1 - 1) + u) : -1;
+        ylab[threadIdx.x] = u < Ub ? label_at(labels, b, U1, u, V) : -1;
     }
     if (threadIdx.x < 2 * kCells) pick[threadIdx.x] = 0.f;
     build_z<kBf16, kTT, kUU>(Z, Hs, enc, dec, b, t0, u0, T, U1, H);
@@ -197,7 +197,7 @@ at_grad_simt_kernel(const float* __restrict__ enc, const float* __restrict__ dec
     __shared__ GradCell gc_s[kCells];
 
     const int b = blockIdx.z, t0 = blockIdx.y * kTT, u0 = blockIdx.x * kUU;
-    const int Tb = min(__ldg(act_lens + b), T), Ub = min(__ldg(label_lens + b), U1 - 1);
+    const int Tb = len_T(act_lens, b, T), Ub = len_U(label_lens, b, U1);
     if (t0 >= Tb || u0 > Ub) return;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;  // rows ty*2 .. +1, cols tx + 16 j
     const float gscale = grad_costs[b];
@@ -213,7 +213,7 @@ at_grad_simt_kernel(const float* __restrict__ enc, const float* __restrict__ dec
             if (t < Tb - 1) g.corr_b = fast_ex2(e16m16_log2_ratio(aq, beta[c + U1], llq) + lp.x * kLog2e);
             else if (u == Ub) g.corr_b = fast_ex2(e16m16_log2_ratio(aq, 0, llq) + lp.x * kLog2e);
             if (u < Ub) {
-                g.y = __ldg(labels + (size_t)b * (U1 - 1) + u);
+                g.y = label_at(labels, b, U1, u, V);
                 g.corr_l = fast_ex2(e16m16_log2_ratio(aq, beta[c + 1], llq) + lp.y * kLog2e);
             }
         }

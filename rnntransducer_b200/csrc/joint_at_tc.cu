@@ -120,7 +120,7 @@ at_lse_tc_kernel(const __grid_constant__ CUtensorMap w_map, const float* __restr
         const int r = tile - b * nT * nU;
         t0 = (r / nU) * kTT;
         u0 = (r % nU) * kUU;
-        return t0 < min(__ldg(act_lens + b), T) && u0 <= min(__ldg(label_lens + b), U1 - 1);
+        return t0 < len_T(act_lens, b, T) && u0 <= len_U(label_lens, b, U1);
     };
 
     if (warp < kProducerWarps) {
@@ -254,10 +254,10 @@ at_lse_tc_kernel(const __grid_constant__ CUtensorMap w_map, const float* __restr
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             int b, t0, u0;
             if (!decode(tile, b, t0, u0)) continue;
-            const int Tb = min(__ldg(act_lens + b), T), Ub = min(__ldg(label_lens + b), U1 - 1);
+            const int Tb = len_T(act_lens, b, T), Ub = len_U(label_lens, b, U1);
             const int t = t0 + tt, u = u0 + uu;
             const bool valid = t < Tb && u <= Ub;
-            const int y = (valid && u < Ub) ? __ldg(labels + (size_t)b * (U1 - 1) + u) : -1;
+            const int y = (valid && u < Ub) ? label_at(labels, b, U1, u, V) : -1;
             float m = -INFINITY, s = 0.f, xb = 0.f, xl = 0.f;
             for (int c = 0; c < n_chunks; ++c, ++ci) {
                 const int as = ci & 1;

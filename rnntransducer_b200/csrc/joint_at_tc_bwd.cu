@@ -150,7 +150,7 @@ at_grad_tc_kernel(const __grid_constant__ CUtensorMap w_map, const float* __rest
         const int r = tile - b * nT * nU;
         t0 = (r / nU) * kTT;
         u0 = (r % nU) * kUU;
-        return t0 < min(__ldg(act_lens + b), T) && u0 <= min(__ldg(label_lens + b), U1 - 1);
+        return t0 < len_T(act_lens, b, T) && u0 <= len_U(label_lens, b, U1);
     };
 
     if (warp < kProducerWarps) {
@@ -327,7 +327,7 @@ at_grad_tc_kernel(const __grid_constant__ CUtensorMap w_map, const float* __rest
             int b, t0, u0;
             if (!decode(tile, b, t0, u0)) continue;
             const uint32_t ph = n & 1;
-            const int Tb = min(__ldg(act_lens + b), T), Ub = min(__ldg(label_lens + b), U1 - 1);
+            const int Tb = len_T(act_lens, b, T), Ub = len_U(label_lens, b, U1);
             const int t = t0 + tt, u = u0 + uu;
             // per-cell scalars (same closed form as every other gradient kernel of the library)
             float c_all = -INFINITY, corr_b = 0.f, corr_l = 0.f;
@@ -341,7 +341,7 @@ at_grad_tc_kernel(const __grid_constant__ CUtensorMap w_map, const float* __rest
                 if (t < Tb - 1) corr_b = fast_ex2(e16m16_log2_ratio(aq, beta[c + U1], llq) + lp.x * kLog2e);
                 else if (u == Ub) corr_b = fast_ex2(e16m16_log2_ratio(aq, 0, llq) + lp.x * kLog2e);
                 if (u < Ub) {
-                    y = __ldg(labels + (size_t)b * (U1 - 1) + u);
+                    y = label_at(labels, b, U1, u, V);
                     corr_l = fast_ex2(e16m16_log2_ratio(aq, beta[c + 1], llq) + lp.y * kLog2e);
                 }
             }

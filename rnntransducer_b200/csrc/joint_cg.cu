@@ -45,7 +45,7 @@ cg_lse_kernel(const float* __restrict__ penc, const float* __restrict__ pdec,
     float* pd_s = smem + kTT * Vs;  // [kUU][Vs]
     const int b = blockIdx.y;
     const int t0 = blockIdx.x * kTT;
-    const int Tb = min(__ldg(act_lens + b), T), Ub = min(__ldg(label_lens + b), U1 - 1);
+    const int Tb = len_T(act_lens, b, T), Ub = len_U(label_lens, b, U1);
     if (t0 >= Tb) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int t = t0 + warp;
@@ -75,7 +75,7 @@ cg_lse_kernel(const float* __restrict__ penc, const float* __restrict__ pdec,
             const float lb = fmaxf((pe[blank] + pd[blank] - lse2) * kLn2, kNegInf);
             float ll = 0.f;
             if (u < Ub) {
-                const int y = __ldg(labels + (size_t)b * (U1 - 1) + u);
+                const int y = label_at(labels, b, U1, u, V);
                 ll = fmaxf((pe[y] + pd[y] - lse2) * kLn2, kNegInf);
             }
             const size_t c = ((size_t)b * T + t) * U1 + u;
@@ -111,7 +111,7 @@ cg_grad_kernel(const float* __restrict__ penc, const float* __restrict__ pdec,
     const int b = blockIdx.y;
     const int tile = blockIdx.x;
     const int t0 = tile * kGT;
-    const int Tb = min(__ldg(act_lens + b), T), Ub = min(__ldg(label_lens + b), U1 - 1);
+    const int Tb = len_T(act_lens, b, T), Ub = len_U(label_lens, b, U1);
     const float gc = grad_costs[b];
     const int llq = beta[(size_t)b * T * U1];  // beta(0,0) = log2 P(y|x), e16m16
     const int n_tiles = gridDim.x;
@@ -159,7 +159,7 @@ cg_grad_kernel(const float* __restrict__ penc, const float* __restrict__ pdec,
                     if (t < Tb - 1) s.corr_b = fast_ex2(e16m16_log2_ratio(aq, beta[c + U1], llq) + lb2);
                     else if (u == Ub) s.corr_b = fast_ex2(e16m16_log2_ratio(aq, 0, llq) + lb2);
                     if (u < Ub) {
-                        const int y = __ldg(labels + (size_t)b * (U1 - 1) + u);
+                        const int y = label_at(labels, b, U1, u, V);
                         const float ll2 = (per[y] + pdr[y]) * kLog2e - z2;
                         s.corr_l = fast_ex2(e16m16_log2_ratio(aq, beta[c + 1], llq) + ll2);
                     }
@@ -168,7 +168,7 @@ cg_grad_kernel(const float* __restrict__ penc, const float* __restrict__ pdec,
             }
             for (int i = threadIdx.x; i < kGUC; i += blockDim.x) {
                 const int u = u0 + i;
-                ys[i] = (u < Ub) ? __ldg(labels + (size_t)b * (U1 - 1) + u) : -1;
+                ys[i] = (u < Ub) ? label_at(labels, b, U1, u, V) : -1;
             }
             __syncthreads();
             if (v_on) {

@@ -133,8 +133,8 @@ cg_factor_rows_kernel(const float* __restrict__ penc, const float* __restrict__ 
             mB[r] = m * kLog2e;
             lBb[r] = lb;
             const int b = r / U1, u = r - b * U1;
-            const int Ub = min(__ldg(label_lens + b), U1 - 1);
-            lBy[r] = u < Ub ? (__ldg(x + __ldg(labels + (size_t)b * (U1 - 1) + u)) - m) * kLog2e : 0.f;
+            const int Ub = len_U(label_lens, b, U1);
+            lBy[r] = u < Ub ? (__ldg(x + label_at(labels, b, U1, u, V)) - m) * kLog2e : 0.f;
         }
     }
 }
@@ -190,7 +190,7 @@ cg_lse_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec,
     float* sc0 = lAb + kFT;             // [2][3][kFUC]  per chunk: row maxima, log2 B[u][blank], log2 B[u][y_u]
     __shared__ int ys0[2][kFUC];
     const int b = blockIdx.y, t0 = blockIdx.x * kFT;
-    const int Tb = min(__ldg(act_lens + b), T), Ub = min(__ldg(label_lens + b), U1 - 1);
+    const int Tb = len_T(act_lens, b, T), Ub = len_U(label_lens, b, U1);
     if (t0 >= Tb) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, q = lane & 3;
@@ -207,7 +207,7 @@ cg_lse_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec,
         stage_scalars(sc + 2 * kFUC, F.lBy + row, n, kFUC);
         if (threadIdx.x < kFUC) {
             const int u = u0 + threadIdx.x;
-            ys0[c & 1][threadIdx.x] = u < Ub ? __ldg(labels + (size_t)b * (U1 - 1) + u) : -1;
+            ys0[c & 1][threadIdx.x] = u < Ub ? label_at(labels, b, U1, u, V) : -1;
         }
         stage_tile(Bs0 + (c & 1) * kFUC * Vs, F.Eb + row * Vk, n, kFUC, Vk, Vs);
     };
@@ -339,7 +339,7 @@ cg_grad_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec
     __shared__ int n_exact;
 
     const int b = blockIdx.y, tile = blockIdx.x, t0 = tile * kGT2;
-    const int Tb = min(__ldg(act_lens + b), T), Ub = min(__ldg(label_lens + b), U1 - 1);
+    const int Tb = len_T(act_lens, b, T), Ub = len_U(label_lens, b, U1);
     const int n_tiles = gridDim.x;
     float* slab = partial ? partial + ((size_t)b * n_tiles + tile) * U1 * V : nullptr;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -372,7 +372,7 @@ cg_grad_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec
         stage_scalars(sc + 2 * kGUC2, F.lBy + row, n, kGUC2);
         if (tid < kGUC2) {
             const int u = u0 + tid;
-            ys0[c & 1][tid] = u < Ub ? __ldg(labels + (size_t)b * (U1 - 1) + u) : -1;
+            ys0[c & 1][tid] = u < Ub ? label_at(labels, b, U1, u, V) : -1;
         }
         stage_tile(reinterpret_cast<float*>(Bs0 + (c & 1) * kGUC2 * Vs), reinterpret_cast<const float*>(F.Eb2 + row * Vk),
                    n, kGUC2, Vk, Vs);

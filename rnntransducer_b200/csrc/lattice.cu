@@ -16,7 +16,7 @@
 //     alpha(t,u) = alpha(t-1,u) * P_blank(t-1,u) + alpha(t,u-1) * P_label(t,u-1),
 // and is evaluated there with every quantity held as (mantissa in [1,2), integer exponent): two
 // FMULs, one FFMA and a handful of integer ops on the dependent chain, no MUFU, no overflow or
-// underflow for any lattice size, ~1e-7 relative error per step (the log-domain form costs two
+// underflow in the recursion itself for any lattice size (the STORED planes hold |log2| < 32768, see cost_of), ~1e-7 relative error per step (the log-domain form costs two
 // MUFUs per step on the chain and loses ulp(|alpha|) ~ 1e-4 per step once |alpha| reaches 10^3).
 //
 // Storage.  alpha / beta planes are written in a 32-bit wide-exponent float ("e16m16", see
@@ -87,6 +87,13 @@ __device__ __forceinline__ int me_pack(ME a) {  // a normalised -> e16m16, manti
 
 __device__ __forceinline__ double me_ln(ME a) {
     return ((double)a.e + (double)log2f(a.m)) * 0.6931471805599453;
+}
+
+// cost = -ln P(y|x).  The e16m16 planes hold |log2| < 32768 (utterances costing < 22 700 nats); beyond
+// that me_pack saturates and the gradients formed from the planes would be silently wrong, so the
+// cost is reported as +inf instead (the loss and every gradient of the step then show it).
+__device__ __forceinline__ float cost_of(ME p) {
+    return p.e < -32766 ? __int_as_float(0x7f800000) : (float)(-me_ln(p));
 }
 
 __device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gmem_src) {
@@ -260,7 +267,7 @@ __device__ __forceinline__ void sweep(const float2* __restrict__ lp2, int Tb, in
         if (DIR == 0) {
             if (ll_alpha) ll_alpha[b] = (float)me_ln(me_normalize(last));
         } else {
-            costs[b] = (float)(-me_ln(last));
+            costs[b] = cost_of(last);
         }
     }
 }
@@ -276,8 +283,8 @@ lattice_sweep_kernel(const float2* __restrict__ lp2, const int32_t* __restrict__
     __shared__ int2 edge[kEdgeRing][33];
     __shared__ int2 xedge[kMode == 2 ? kEdgeRingX : 1];
     const int b = kMode == 2 ? blockIdx.x / cluster_nctarank() : blockIdx.x;
-    const int Tb = min(max(act_lens[b], 1), T);
-    const int Ub = min(max(label_lens[b], 0), U1 - 1);
+    const int Tb = len_T(act_lens, b, T);
+    const int Ub = len_U(label_lens, b, U1);
     if (blockIdx.y == 0)
         sweep<0, kMode>(lp2, Tb, Ub, T, U1, b, alpha, costs, ll_alpha, ring, edge, xedge);
     else
@@ -585,7 +592,7 @@ __device__ __forceinline__ void ws_consumer(WsWarp<KB, RW>& W, const float2* __r
                 ll_alpha[b] = (float)me_ln(me_normalize(me_mul(last, me_from_log(src[(long long)t_last * G.stride].x))));
             }
         } else {
-            costs[b] = (float)(-me_ln(last));
+            costs[b] = cost_of(last);
         }
     }
 }
@@ -612,8 +619,8 @@ lattice_sweep_ws_kernel(const float2* __restrict__ lp2, const int32_t* __restric
     X.xedge = reinterpret_cast<int2*>(ws + nw);  // [xedge_slots], cluster launches only
     X.xdone = &xdone_slot;
     const int b = kCluster ? blockIdx.x / X.n_bands : blockIdx.x;
-    const int Tb = min(max(act_lens[b], 1), T);
-    const int Ub = min(max(label_lens[b], 0), U1 - 1);
+    const int Tb = len_T(act_lens, b, T);
+    const int Ub = len_U(label_lens, b, U1);
     if ((int)threadIdx.x < nw) {
         WsWarp<KB, RW>& W = ws[threadIdx.x];
         for (int i = 0; i < 4 * kWsStages; ++i) tc::mbar_init(tc::smem_u32(W.bars + i), i < kWsStages ? 2 : 1);
@@ -701,6 +708,12 @@ int launch_ws_cluster(const float2* lp2, const int32_t* act_lens, const int32_t*
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    int fits = 0;  // a cluster of n_bands CTAs with this much shared memory must be co-schedulable on one GPC
+    e = cudaOccupancyMaxActiveClusters(&fits, kern, &cfg);
+    if (e != cudaSuccess || fits < 1) {
+        (void)cudaGetLastError();
+        return -1;  // the caller falls back to the single-role sweep
+    }
     e = cudaLaunchKernelEx(&cfg, kern, lp2, act_lens, label_lens, T, U1, alpha, beta, costs, ll_alpha, slots, NW, spread);
     return e == cudaSuccess ? launch_status() : status_from_cuda(e);
 }

@@ -16,7 +16,7 @@ from __future__ import annotations
 import torch
 
 from . import _lib
-from .loss import _ptr, _stream, _validate
+from .loss import _contiguous, _ptr, _stream, _validate
 
 GEMMS = {"fp32": 0, "bf16": 1, "tf32x3": 2}
 
@@ -32,7 +32,7 @@ class _AddTanhRNNT(torch.autograd.Function):
         _validate((B, T, U1, V), enc.device, labels, act_lens, label_lens, blank)
         enc, dec = enc.contiguous().float(), dec.contiguous().float()
         weight, bias = weight.contiguous().float(), bias.contiguous().float()
-        labels = labels.contiguous()
+        labels, act_lens, label_lens = _contiguous(labels, act_lens, label_lens)
         f32 = dict(device=enc.device, dtype=torch.float32)
         costs = torch.empty(B, **f32)
         lp2 = torch.empty(B, T, U1, 2, **f32)

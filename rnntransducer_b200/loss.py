@@ -52,14 +52,27 @@ def _validate(acts_shape, acts_device, labels, act_lens, label_lens, blank, requ
         raise RuntimeError(f"blank must be in [0, {V}), got {blank}")
     if T <= 0:
         raise RuntimeError("acts must have at least one frame")
+    if U1 > 1024:
+        raise RuntimeError(f"label sequences longer than 1023 are not supported (U+1 = {U1} > 1024)")
 
 
-def check_lengths(act_lens, label_lens, T, U1):
-    """Optional debug check (DEVICE SYNC): the oracle's max(act_lens)==T / max(label_lens)+1==U1."""
+def _contiguous(*tensors):
+    """The kernels index labels / act_lens / label_lens with stride 1 from the raw pointer: a strided
+    view (``lens[:, 0]``, ``lens[::2]``) must be compacted first (no-op for contiguous tensors)."""
+    return tuple(t.contiguous() for t in tensors)
+
+
+def check_lengths(act_lens, label_lens, T, U1, labels=None, V=None):
+    """Optional debug check (DEVICE SYNC): lengths inside the padded box and -- when ``labels`` and
+    ``V`` are given -- every label inside the vocabulary.  Without it the kernels clamp such values
+    (csrc/common.cuh len_T / len_U / label_at): defined behaviour, wrong training data."""
     if int(act_lens.max()) > T or int(act_lens.min()) < 1:
         raise RuntimeError("act_lens out of range")
     if int(label_lens.max()) + 1 > U1 or int(label_lens.min()) < 0:
         raise RuntimeError("label_lens out of range")
+    if labels is not None and V is not None and labels.numel() > 0:
+        if int(labels.max()) >= V or int(labels.min()) < 0:
+            raise RuntimeError(f"labels must be in [0, {V})")
 
 
 class _DenseRNNT(torch.autograd.Function):
@@ -71,7 +84,7 @@ class _DenseRNNT(torch.autograd.Function):
             raise RuntimeError("acts must be float32, float16 or bfloat16")
         _validate(acts.shape, acts.device, labels, act_lens, label_lens, blank)
         acts = acts.contiguous()
-        labels = labels.contiguous()
+        labels, act_lens, label_lens = _contiguous(labels, act_lens, label_lens)
         B, T, U1, V = acts.shape
         dev = acts.device
         f32 = dict(device=dev, dtype=torch.float32)
@@ -114,7 +127,7 @@ class _ConcatGeluRNNT(torch.autograd.Function):
         _validate((B, T, U1, V), penc.device, labels, act_lens, label_lens, blank)
         penc = penc.contiguous().float()
         pdec = pdec.contiguous().float()
-        labels = labels.contiguous()
+        labels, act_lens, label_lens = _contiguous(labels, act_lens, label_lens)
         f32 = dict(device=penc.device, dtype=torch.float32)
         costs = torch.empty(B, **f32)
         lp2 = torch.empty(B, T, U1, 2, **f32)
@@ -159,7 +172,8 @@ class _ConcatGeluRNNT(torch.autograd.Function):
 
 class _CgProject(torch.autograd.Function):
     """penc = gelu_tanh(enc) W[:, :He]^T + b,  pdec = gelu_tanh(dec) W[:, He:]^T on the tensor cores at
-    fp32 accuracy (rnntb200_joint_cg_project).  Backward: library GEMMs on the recomputed GELU."""
+    fp32 accuracy (rnntb200_joint_cg_project); backward on the tensor cores with the same bf16 hi/lo
+    split arithmetic (rnntb200_joint_cg_project_bwd)."""
 
     @staticmethod
     def forward(ctx, enc, dec, weight, bias):
@@ -300,11 +314,11 @@ class RNNTLoss(torch.nn.Module):
         self.reduction = reduction
         self.warp_compat = warp_compat
         self.deterministic = deterministic
-        self.check_lengths = check_lengths  # debug only: costs a device sync
+        self.check_lengths = check_lengths  # debug only: costs a device sync (lengths AND label range)
 
     def forward(self, acts, labels, act_lens, label_lens):
         if self.check_lengths:
             shape = acts.shape
-            check_lengths(act_lens, label_lens, shape[1], shape[2])
+            check_lengths(act_lens, label_lens, shape[1], shape[2], labels, shape[3])
         return rnnt_loss(acts, labels, act_lens, label_lens, self.blank, self.reduction,
                          self.warp_compat, self.deterministic)

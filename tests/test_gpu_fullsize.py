@@ -1,0 +1,146 @@
+"""GPU parity at BASELINE.json's OWN sizes against the CPU oracle (not against our dense path).
+
+cfg 2 (B=32, T=400, U=80, V=73, H=512), cfg 3 (B=8, T=1500, U=300, V=73, H=512) and cfg 4 (B=16,
+T=400, U=100, V=1024, H=512), every utterance of the batch, both joints, every output: per-utterance
+costs, d_enc, d_dec, d_weight, d_bias.  The oracle is ``oracle/joint_ref.joint_loss_fwd_bwd_chunked``:
+the reference's joint (networks/transducer.py:54-71) restated cell by cell, the C restatement of
+warp-transducer's CPU loss (oracle/warp_cpu.c) and autograd, evaluated block-wise so the 13-45 GB of
+``[B,T,U1,2H]`` intermediates never exist at once.
+
+Gates (north_star): per-utterance loss 1e-5 relative, per-cell-scale gradients (d_enc, d_dec) 1e-4
+absolute, against the fp64 build of the oracle; against the fp32 build (warp-transducer's own
+precision) the same plus that build's own measured deviation from fp64.  Parameter gradients
+(d_weight, d_bias: sums over 10^6 cells, entries up to 1e2) use conftest.param_atol.  The bf16-GEMM
+variant has its own, separately stated bound (tests/test_gpu_joint_at.py header).
+
+Every test appends the errors it measured to gpurun_out/parity_r2.jsonl.
+"""
+import json
+import os
+import time
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, param_atol
+from oracle import joint_ref
+from rnntransducer_b200 import synthetic
+from test_gpu_joint_cg import fused_step
+
+pytestmark = pytest.mark.gpu
+
+KEYS = ("d_enc", "d_dec", "d_weight", "d_bias")
+
+
+def record(name, **kv):
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "parity_r2.jsonl"), "a") as f:
+        f.write(json.dumps(dict(test=name, **kv)) + "\n")
+
+
+def oracle(d, mode, dtype):
+    t0 = time.time()
+    r = joint_ref.joint_loss_fwd_bwd_chunked(
+        d["enc"], d["dec"], d["weight"], d["bias"], d["labels"].numpy(), d["act_lens"].numpy(),
+        d["label_lens"].numpy(), 0, "mean", mode, dtype=dtype)
+    r["seconds"] = time.time() - t0
+    return r
+
+
+def errors(r, ref):
+    e = {"costs_rel": float(np.max(np.abs(r["costs"] - ref["costs"]) / np.abs(ref["costs"])))}
+    for k in KEYS:
+        e[k] = float(np.abs(r[k] - ref[k]).max())
+        e[k + "_refmax"] = float(np.abs(ref[k]).max())
+    return e
+
+
+def gate_fp32_class(name, r, ref64, ref32=None):
+    e64 = errors(r, ref64)
+    rec = dict(vs_fp64=e64, oracle_seconds_fp64=ref64["seconds"])
+    if ref32 is not None:
+        rec["vs_fp32"] = errors(r, ref32)
+        rec["fp32_oracle_own_error"] = errors(ref32, ref64)
+    record(name, **rec)
+    np.testing.assert_allclose(r["costs"], ref64["costs"], rtol=1e-5)
+    for k in KEYS:
+        atol = param_atol(ref64[k]) if k in ("d_weight", "d_bias") else 1e-4
+        np.testing.assert_allclose(r[k], ref64[k], atol=atol, err_msg=f"{name} {k} vs fp64 oracle")
+    if ref32 is not None:
+        np.testing.assert_allclose(r["costs"], ref32["costs"], rtol=1e-5)
+        for k in KEYS:
+            atol = param_atol(ref32[k]) if k in ("d_weight", "d_bias") else 1e-4
+            own = float(np.abs(ref32[k] - ref64[k]).max())
+            np.testing.assert_allclose(r[k], ref32[k], atol=atol + own, err_msg=f"{name} {k} vs fp32 oracle")
+
+
+def gate_bf16(name, r, ref64):
+    record(name, vs_fp64=errors(r, ref64), oracle_seconds_fp64=ref64["seconds"],
+           bound="loss 5e-3 rel, grads 2e-2 * max|grad|")
+    np.testing.assert_allclose(r["costs"], ref64["costs"], rtol=5e-3)
+    for k in KEYS:
+        np.testing.assert_allclose(r[k], ref64[k], atol=2e-2 * max(1e-3, float(np.abs(ref64[k]).max())),
+                                   err_msg=f"{name} {k}")
+
+
+def batch(cfg, mode, ragged, seed):
+    c = synthetic.CONFIGS[cfg]
+    return synthetic.make_batch(c["B"], c["T"], c["U"], c["V"], c["H"], mode=mode, ragged=ragged, seed=seed)
+
+
+def padding_is_zero(r, d):
+    al, ll = d["act_lens"].numpy(), d["label_lens"].numpy()
+    for b in range(len(al)):
+        assert np.all(r["d_enc"][b, al[b]:] == 0)
+        assert np.all(r["d_dec"][b, ll[b] + 1:] == 0)
+
+
+@pytest.mark.parametrize("ragged", [False, True])
+def test_cfg2_concat_gelu_vs_oracle(cuda_lib, oracle_lib, ragged):
+    """The config BASELINE.json's metric is quoted on, all 32 utterances, fp32 and fp64 oracle."""
+    d = batch(2, "concat_gelu", ragged, 1236)
+    ref64, ref32 = oracle(d, "concat_gelu", torch.float64), oracle(d, "concat_gelu", torch.float32)
+    for det in (False, True):
+        r = fused_step({k: v.cuda() for k, v in d.items()}, deterministic=det)
+        gate_fp32_class(f"cfg2 concat_gelu fp32 ragged={ragged} det={det}", r, ref64, ref32)
+        padding_is_zero(r, d)
+
+
+def test_cfg2_add_tanh_vs_oracle(cuda_lib, oracle_lib):
+    d = batch(2, "add_tanh", True, 1236)
+    ref64 = oracle(d, "add_tanh", torch.float64)
+    dc = {k: v.cuda() for k, v in d.items()}
+    gate_bf16("cfg2 add_tanh bf16 ragged", fused_step(dc, mode="add_tanh", gemm="bf16"), ref64)
+
+
+def test_cfg3_long_utterances_vs_oracle(cuda_lib, oracle_lib):
+    """T=1500, U=300 (1800 anti-diagonals, ten chain warps in a cluster): every gradient against the
+    fp64 and the fp32 oracle; then the joint BASELINE names for this config (bf16 GEMM, add_tanh)."""
+    d = batch(3, "concat_gelu", True, 1237)
+    ref64, ref32 = oracle(d, "concat_gelu", torch.float64), oracle(d, "concat_gelu", torch.float32)
+    r = fused_step({k: v.cuda() for k, v in d.items()})
+    gate_fp32_class("cfg3 concat_gelu fp32 ragged", r, ref64, ref32)
+    padding_is_zero(r, d)
+    del ref64, ref32, r
+    d = batch(3, "add_tanh", True, 1237)
+    ref64 = oracle(d, "add_tanh", torch.float64)
+    r = fused_step({k: v.cuda() for k, v in d.items()}, mode="add_tanh", gemm="bf16")
+    gate_bf16("cfg3 add_tanh bf16 ragged", r, ref64)
+    padding_is_zero(r, d)
+
+
+def test_cfg4_large_vocab_vs_oracle(cuda_lib, oracle_lib):
+    """V=1024, all 16 utterances: the reference's joint (fp32) and the tensor-core add_tanh joint incl.
+    its multi-chunk backward, against the fp64 oracle."""
+    d = batch(4, "concat_gelu", True, 1238)
+    ref64 = oracle(d, "concat_gelu", torch.float64)
+    r = fused_step({k: v.cuda() for k, v in d.items()})
+    gate_fp32_class("cfg4 concat_gelu fp32 ragged", r, ref64)
+    padding_is_zero(r, d)
+    del ref64, r
+    d = batch(4, "add_tanh", True, 1238)
+    ref64 = oracle(d, "add_tanh", torch.float64)
+    r = fused_step({k: v.cuda() for k, v in d.items()}, mode="add_tanh", gemm="bf16")
+    gate_bf16("cfg4 add_tanh bf16 ragged", r, ref64)
+    padding_is_zero(r, d)
