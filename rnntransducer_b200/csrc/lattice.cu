@@ -338,6 +338,25 @@ struct WsWarp {  // shared memory of one chain warp and its helpers
                                               // plain counter, because an mbarrier parity cannot name a phase that
                                               // lies more than one completion back)
 };
+// ---- decoupled (mantissa | exponent) recursion -------------------------------------------------------
+// A lattice value is m * 2^E, E an int and m an fp32 that is NOT kept normalised: between two
+// renormalisations (one per block of KB steps) it drifts by at most 2^(1.5 KB), far inside fp32 range.
+// The exponents then obey a pure integer max-plus recurrence,
+//     E(s) = max(E_own(s-1) + e_blank, E_in(s-1) + e_label),
+// that does not depend on the mantissas at all, so it runs ONE STEP AHEAD of the mantissa recurrence
+// and the alignment scales 2^(E_term - E) are in registers before the neighbour's mantissa arrives.
+// Dependent chain of a step: FMUL -> SHFL -> FFMA (alpha) / SHFL -> FFMA (beta), with IADD -> SHFL ->
+// IMNMX running beside it -- instead of SHFL -> exponent compare -> align -> FFMA -> normalise -> FMUL.
+// No select on the chain either: lane 0 (no neighbour inside the warp) gets a bias on the shuffled
+// exponent so that term's scale is exactly 0, and the value crossing a warp boundary enters as a third
+// term whose exponent is "minus infinity" on every other lane.
+constexpr int kNoTerm = kZeroExp;  // exponent (or exponent bias) of an absent term; sums of two of these and a
+                                   // sweep's worth of factor exponents stay inside int32
+
+__device__ __forceinline__ float pow2_neg(int d) {  // 2^-d for d >= 0, exactly 0 once d >= 127
+    return __int_as_float((127 - min(d, 127)) << 23);
+}
+
 template <int DIR, bool kMulti, int KB, int RW>
 __device__ __forceinline__ void ws_chain(WsWarp<KB, RW>& W, int2 (*edge)[33], int w, int nw, int lane, int n_blocks,
                                          const WsBand& X) {
@@ -347,10 +366,19 @@ __device__ __forceinline__ void ws_chain(WsWarp<KB, RW>& W, int2 (*edge)[33], in
     const int lag = kMulti ? wg * KB + X.xlag : 0;
     const int edge_col = (kMulti && w > 0) ? w - 1 : 32;
     const bool from_band = kMulti && w == 0 && X.band > 0;  // lane 0's neighbour lives in the previous CTA
+    const bool has_edge = kMulti && lane == 0;
     const uint32_t xdone = tc::smem_u32(X.xdone);
+    const int in_bias = lane == 0 ? kNoTerm : 0;
     int es = (-lag - 1) & (kWsEdgeRing - 1);  // edge slot of diagonal d-1
-    ME own{1.f, j == 0 ? 0 : kZeroExp};
-    ME share{1.f, kZeroExp};
+    // value of the previous step (m, E) and the factors it was / will be multiplied with:
+    //   alpha: terms of step k are  val(k-1) p_blank(k-1)  and  shfl(val(k-1) p_label(k-1))
+    //   beta:  terms of step k are  val(k-1) p_blank(k)    and  shfl(val(k-1)) p_label(k)
+    // alpha's start alpha(0,0) = 1 enters as the own term of step 0 of lane j = 0 (factors 1 "before" it);
+    // beta's start is val(-1) = 1 on lane j = 0, so that beta(T-1,U) = 1 * p_blank.
+    float m = 1.f;
+    int E = j == 0 ? 0 : kZeroExp;
+    float pbm_prev = 1.f, plm_prev = 1.f;  // alpha only
+    int pbe_prev = 0, ple_prev = DIR == 0 ? kNoTerm : 0;  // alpha: nothing to hand on before the first step
 #pragma unroll 1
     for (int blk = 0; blk < n_blocks; ++blk) {
         const int st = blk % kWsStages;
@@ -366,45 +394,75 @@ __device__ __forceinline__ void ws_chain(WsWarp<KB, RW>& W, int2 (*edge)[33], in
                 __nanosleep(32);
             }
         }
-#pragma unroll 1
-        for (int h = 0; h < KB; h += kHalf) {
-            uint4 f = W.fac[st][h][lane];
-            // the previous warp is a whole block ahead: the boundary values of this block are already
-            // in the ring, fetch them off the dependent chain
-            int2 evs[kHalf];
+        // the previous warp is a whole block ahead: the boundary values of this block are already in the
+        // ring, fetch them off the dependent chain (lanes other than 0 carry an absent term)
+        float evm[KB];
+        int evE[KB];
 #pragma unroll
-            for (int k = 0; k < kHalf; ++k) {
-                evs[k] = kMulti ? edge[(es + k) & (kWsEdgeRing - 1)][edge_col] : make_int2(0x3f800000, kZeroExp);
+        for (int k = 0; k < KB; ++k) {
+            int2 ev = make_int2(0x3f800000, kNoTerm);
+            if (has_edge) {
+                ev = edge[(es + k) & (kWsEdgeRing - 1)][edge_col];
                 if (from_band) {
-                    const int q = blk * KB + h + k - lag - 1;  // the previous band's step index of diagonal d-1
-                    evs[k] = q >= 0 ? X.xedge[q] : make_int2(0x3f800000, kZeroExp);
+                    const int q = blk * KB + k - lag - 1;  // the previous band's step index of diagonal d-1
+                    ev = q >= 0 ? X.xedge[q] : make_int2(0x3f800000, kZeroExp);
                 }
             }
+            evm[k] = __int_as_float(ev.x);
+            evE[k] = ev.y;
+        }
+        uint4 f = W.fac[st][0][lane];
+        // exponent recurrence of step 0 of this block (it cannot run ahead across the renormalisation)
+        int En;
+        float c_own, c_in, c_edge;
+        {
+            const int pbe = DIR == 0 ? pbe_prev : (int)f.y, ple = DIR == 0 ? ple_prev : (int)f.w;
+            const int oE = E + pbe;
+            // (beta's seed val(-1) = 1 on lane j = 0 must not reach lane 1: no shuffled term at the very first step)
+            const int iE = __shfl_up_sync(0xffffffffu, DIR == 0 ? E + ple : E, 1) +
+                           (DIR == 0 ? in_bias : (blk == 0 ? kNoTerm : in_bias) + ple);
+            const int eE = DIR == 0 ? evE[0] : evE[0] + ple;
+            En = max(max(oE, iE), eE);
+            c_own = pow2_neg(En - oE) * (DIR == 0 ? pbm_prev : __uint_as_float(f.x));
+            c_in = pow2_neg(En - iE) * (DIR == 0 ? 1.f : __uint_as_float(f.z));
+            c_edge = pow2_neg(En - eE) * (DIR == 0 ? 1.f : __uint_as_float(f.z));
+        }
+        float shm = DIR == 0 ? m * plm_prev : m;  // what the neighbour receives
 #pragma unroll
-            for (int k = 0; k < kHalf; ++k) {
-                const uint4 fn = W.fac[st][h + (k + 1 < kHalf ? k + 1 : k)][lane];  // next step's factors, off the chain
-                ME in;
-                in.m = __shfl_up_sync(0xffffffffu, share.m, 1);
-                in.e = __shfl_up_sync(0xffffffffu, share.e, 1);
-                if (lane == 0) in = ME{__int_as_float(evs[k].x), evs[k].y};
-                const ME pb{__uint_as_float(f.x), (int)f.y}, pl{__uint_as_float(f.z), (int)f.w};
-                ME val;
-                if (DIR == 0) {
-                    val = me_normalize(me_add(own, in));
-                    own = me_mul(val, pb);
-                    share = me_mul(val, pl);
-                } else {
-                    val = me_normalize(me_add(me_mul(own, pb), me_mul(in, pl)));
-                    own = val;
-                    share = val;
-                }
-                W.val[st][h + k][lane] = make_int2(__float_as_int(val.m), val.e);
-                if (kMulti) {
-                    es = (es + 1) & (kWsEdgeRing - 1);  // now the slot of diagonal d
-                    if (lane == 31) edge[es][w] = make_int2(__float_as_int(share.m), share.e);
-                }
-                f = fn;
+        for (int k = 0; k < KB; ++k) {
+            const uint4 fn = W.fac[st][k + 1 < KB ? k + 1 : k][lane];  // next step's factors, off the chain
+            const float in_m = __shfl_up_sync(0xffffffffu, shm, 1);     // mantissa chain: the long-latency hop first
+            const float own_term = fmaf(evm[k], c_edge, m * c_own);
+            const int Ek = En;
+            const float ci = c_in;
+            const float pbm = __uint_as_float(f.x), plm = __uint_as_float(f.z);
+            const int pbe = (int)f.y, ple = (int)f.w;
+            if (k + 1 < KB) {  // exponent recurrence of step k+1, in the shadow of the shuffle above
+                const int pbe_n = DIR == 0 ? pbe : (int)fn.y, ple_n = DIR == 0 ? ple : (int)fn.w;
+                const int oE = Ek + pbe_n;
+                const int iE = __shfl_up_sync(0xffffffffu, DIR == 0 ? Ek + ple_n : Ek, 1) +
+                               (DIR == 0 ? in_bias : in_bias + ple_n);
+                const int eE = DIR == 0 ? evE[k + 1] : evE[k + 1] + ple_n;
+                En = max(max(oE, iE), eE);
+                c_own = pow2_neg(En - oE) * (DIR == 0 ? pbm : __uint_as_float(fn.x));
+                c_in = pow2_neg(En - iE) * (DIR == 0 ? 1.f : __uint_as_float(fn.z));
+                c_edge = pow2_neg(En - eE) * (DIR == 0 ? 1.f : __uint_as_float(fn.z));
             }
+            m = fmaf(in_m, ci, own_term);
+            E = Ek;
+            if (k + 1 == KB) {  // renormalise once per block: the exponent of m moves into E
+                const int bits = __float_as_int(m);
+                m = __int_as_float((bits & 0x007fffff) | 0x3f800000);
+                E += (bits >> 23) - 127;
+            }
+            W.val[st][k][lane] = make_int2(__float_as_int(m), E);
+            shm = DIR == 0 ? m * plm : m;
+            if (kMulti) {
+                es = (es + 1) & (kWsEdgeRing - 1);  // now the slot of diagonal d
+                if (lane == 31) edge[es][w] = make_int2(__float_as_int(shm), DIR == 0 ? E + ple : E);
+            }
+            pbm_prev = pbm, plm_prev = plm, pbe_prev = pbe, ple_prev = ple;
+            f = fn;
         }
         __syncwarp();  // orders every lane's shared-memory traffic before the one arrival below
         if (lane == 0) {

@@ -76,12 +76,20 @@ def gate_fp32_class(name, r, ref64, ref32=None):
 
 
 def gate_bf16(name, r, ref64):
-    record(name, vs_fp64=errors(r, ref64), oracle_seconds_fp64=ref64["seconds"],
-           bound="loss 5e-3 rel, grads 2e-2 * max|grad|")
+    """The separately stated bound of the bf16-GEMM variant (operands rounded to 8 mantissa bits, fp32
+    accumulation): loss 5e-3 relative; every gradient tensor within 5e-2 * max|grad| per element AND within
+    2e-2 in relative L2 norm.  Measured (round 2, gpurun_out/parity_r2.jsonl -> DESIGN.md section 2): loss
+    <= 2.3e-4, per-element <= 3.4e-2 * max|grad| (d_enc at cfg 3, 300 summands per element), L2 see table."""
+    e = errors(r, ref64)
+    for k in KEYS:
+        e[k + "_rel_l2"] = float(np.linalg.norm((r[k] - ref64[k]).ravel()) / max(np.linalg.norm(ref64[k].ravel()), 1e-30))
+    record(name, vs_fp64=e, oracle_seconds_fp64=ref64["seconds"],
+           bound="loss 5e-3 rel; grads 5e-2 * max|grad| per element and 2e-2 relative L2")
     np.testing.assert_allclose(r["costs"], ref64["costs"], rtol=5e-3)
     for k in KEYS:
-        np.testing.assert_allclose(r[k], ref64[k], atol=2e-2 * max(1e-3, float(np.abs(ref64[k]).max())),
+        np.testing.assert_allclose(r[k], ref64[k], atol=5e-2 * max(1e-3, float(np.abs(ref64[k]).max())),
                                    err_msg=f"{name} {k}")
+        assert e[k + "_rel_l2"] < 2e-2, f"{name} {k}: relative L2 error {e[k + '_rel_l2']:.3g}"
 
 
 def batch(cfg, mode, ragged, seed):
