@@ -776,6 +776,331 @@ int launch_ws_cluster(const float2* lp2, const int32_t* act_lens, const int32_t*
     return e == cudaSuccess ? launch_status() : status_from_cuda(e);
 }
 
+
+// =================================================================================================
+// Self-contained sweep ("tp"): one warp does everything for its 32 label positions.
+//
+// The warp-specialised kernel above buys chain latency with shared memory (179 KB per CTA at U1 = 81: one CTA
+// per SM, so a large batch runs in waves) and with helper warps that compete with the chain for the SM.
+// With the decoupled recursion the chain is short enough that ONE warp can carry all roles again, provided
+// its global accesses stay row-wise.  They do, through two lane-private FIFOs in shared memory:
+//   raw  lane l copies ITS column of every lattice row with cp.async (all lanes of one instruction on one
+//        row: 256 contiguous bytes), kTpAhead + 1 blocks ahead, and reads it back l steps later -- lane l of
+//        the wavefront is l rows behind lane 0.  A lane only ever reads its own copies: cp.async.wait_group
+//        is all the synchronisation there is.
+//   out  lane l writes its packed value and reads it back 31 - l steps later, when lane 31 has passed the
+//        row and the whole row is stored with one 128-byte instruction.
+// 24 KB per warp: three CTAs of three warps per SM at U1 = 81, a B = 512 batch is resident in 2.3 waves
+// of 9 warps per SM instead of 7 waves of one CTA.  Warps of one sweep run KB steps apart and meet at a
+// block barrier per KB steps (edge ring as in the chain warps above); longer label sequences are cut into
+// bands of kTpBandWarps warps, one CTA of a thread-block cluster each, the boundary value written by lane
+// 31 straight into the next CTA's shared memory (one slot per step of the sweep) followed by a release
+// store of the finished block count.
+constexpr int kTpKB = 8;        // steps per block = skew between consecutive warps
+constexpr int kTpAhead = 2;     // blocks of lp2 rows in flight beyond the one being converted
+constexpr int kTpRaw = 64;      // FIFO depth (rows): 31 (lane skew) + (kTpAhead + 2) * kTpKB <= 64
+constexpr int kTpOut = 64;      // FIFO depth (rows): 31 + kTpKB + 1 <= 64
+constexpr int kTpEdge = 32;     // >= 2 * kTpKB + 1 slots for warp-boundary values
+static_assert(31 + (kTpAhead + 2) * kTpKB <= kTpRaw && 32 + kTpKB <= kTpOut, "FIFO too shallow");
+
+struct TpWarp {
+    float2 raw[kTpRaw][32];
+    int32_t out[kTpOut][32];
+};
+
+template <int DIR, bool kMulti, bool kCluster>
+__device__ __forceinline__ void tp_sweep(TpWarp& W, int2 (*edge)[8], const float2* __restrict__ lp2, int Tb, int Ub,
+                                         int T, int U1, int b, int32_t* __restrict__ out, float* __restrict__ costs,
+                                         float* __restrict__ ll_alpha, int w, int nw, int lane, const WsBand& X) {
+    constexpr int KB = kTpKB;
+    const WsGeom<DIR, kMulti, KB> G(Tb, Ub, T, U1, b, X.band * nw + w, lane, X.xlag);
+    const int n_on = (Ub + 32) / 32;  // warps with cells
+    const int max_lag = kMulti ? (n_on - 1) * KB + ((n_on - 1) / nw) * (kBandSkew - KB) : 0;
+    const int n_blocks = (Tb + Ub + max_lag + KB - 1) / KB;
+    const int edge_col = (kMulti && w > 0) ? w - 1 : 4;
+    const bool from_band = kCluster && w == 0 && X.band > 0;
+    const bool to_band = kCluster && w == nw - 1 && X.band + 1 < X.n_bands && lane == 31;
+    const uint32_t xdone = tc::smem_u32(X.xdone);
+    uint32_t r_xedge = 0, r_xdone = 0;
+    if (to_band) {
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r_xedge) : "r"(tc::smem_u32(X.xedge)), "r"(X.band + 1));
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r_xdone) : "r"(xdone), "r"(X.band + 1));
+    }
+    const int in_bias = lane == 0 ? kNoTerm : 0;
+    // FIFO slot of (row r, lane l) = (r + l) mod depth: lane l meets row r at step r + base + l, so the slot
+    // index is the STEP index (minus base) -- uniform across the lanes and, base being a multiple of KB,
+    // the KB slots of a block are consecutive: the chain side addresses both FIFOs with one register and
+    // immediates.  (The row-wise sides -- cp.async in, row stores out -- pay the index arithmetic.)
+    float2* rawc = &W.raw[0][lane];   // this lane's column of the FIFOs (slot stride 32 elements)
+    int32_t* outc = &W.out[0][lane];
+
+    // ---- loader: row r_ld (the same row for every lane of an instruction), this lane's cell of it.  Rows
+    // outside [0, Tb) are CLAMPED, not skipped: a lane without a cell at some step then multiplies by a real
+    // factor instead of 1, which is harmless -- before its first cell it carries "zero" (and zero times
+    // anything finite stays zero), after its last one nothing reads it -- and it frees the conversions from
+    // any predicate.  Lanes beyond the label sequence never load: their FIFO column is zeroed once
+    // (log-probability 0 = factor 1).
+    const bool lane_on = G.Tb_eff != 0;
+    if (!lane_on)
+        for (int i = 0; i < kTpRaw; ++i) rawc[i * 32] = make_float2(0.f, 0.f);
+    int r_ld = -G.base;
+    const float2* src0 = lp2 + G.first;
+    auto load_block = [&]() {
+        if (lane_on) {
+#pragma unroll
+            for (int k = 0; k < KB; ++k) {
+                const int rc = min(max(r_ld + k, 0), Tb - 1);
+                cp_async_8(rawc + ((r_ld + k + lane) & (kTpRaw - 1)) * 32, src0 + rc * G.stride);
+            }
+        }
+        r_ld += KB;
+        cp_async_commit();
+    };
+
+    // prologue: rows of blocks 0 .. kTpAhead requested, block 0 converted
+#pragma unroll
+    for (int i = 0; i < kTpAhead + 1; ++i) load_block();
+    cp_async_wait<kTpAhead>();
+    int slot0 = (-G.base) & (kTpRaw - 1);  // slot of the first step of the current block (both FIFOs, same depth)
+    static_assert(kTpRaw == kTpOut, "one slot register serves both FIFOs");
+    float fm[KB][2];
+    int fe[KB][2];
+#pragma unroll
+    for (int k = 0; k < KB; ++k) {
+        const float2 lp = rawc[(slot0 + k) * 32];
+        const ME fb = me_from_log(lp.x), fl = me_from_log(lp.y);
+        fm[k][0] = fb.m, fe[k][0] = fb.e, fm[k][1] = fl.m, fe[k][1] = fl.e;
+    }
+
+    float m = 1.f;
+    int E = G.j == 0 ? 0 : kZeroExp;
+    float pbm_prev = 1.f, plm_prev = 1.f;
+    int pbe_prev = 0, ple_prev = DIR == 0 ? kNoTerm : 0;
+    const int edge_bias = lane == 0 ? 0 : kNoTerm;
+    int tau = G.tau0;                 // progress at the first step of the current block
+    int row_st = -G.base - 31;        // next row to be stored (complete once lane 31 has passed it)
+    int32_t* pst = out + G.first + (long long)row_st * G.stride;
+    const int t_last = (G.Tb_eff != 0 && G.j == Ub) ? Tb - 1 : -1;
+    float last_m = 1.f;
+    int last_E = kZeroExp;
+
+#pragma unroll 1
+    for (int blk = 0; blk < n_blocks; ++blk) {
+        if (kMulti) __syncthreads();  // the previous warp has finished the block this one reads boundary values of
+        load_block();                 // rows of block blk + kTpAhead + 1
+        if (from_band && blk >= kBandSkew / KB) {
+            int done;
+            for (;;) {
+                asm volatile("ld.acquire.cluster.shared::cta.s32 %0, [%1];" : "=r"(done) : "r"(xdone) : "memory");
+                if (done > blk - kBandSkew / KB) break;
+                __nanosleep(32);
+            }
+        }
+        // boundary values of this block: every lane reads them (a broadcast), lanes other than 0 push the term
+        // out of reach with an exponent bias.  Reader slots are block-aligned: the writer stores its local step
+        // p at slot p + 1, the reader of local step q wants p = q - 1, i.e. slot q = er + k.
+        float evm[KB];
+        int evE[KB];
+        if (kMulti) {
+            const int er = (blk * KB - G.lag) & (kTpEdge - 1);
+#pragma unroll
+            for (int k = 0; k < KB; ++k) {
+                int2 ev = edge[er + k][edge_col];
+                if (kCluster && from_band) {
+                    const int q = blk * KB + k - G.lag - 1;
+                    ev = q >= 0 ? X.xedge[q] : make_int2(0x3f800000, kZeroExp);
+                }
+                evm[k] = __int_as_float(ev.x);
+                evE[k] = ev.y + edge_bias;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < KB; ++k) evm[k] = 1.f, evE[k] = kNoTerm;
+        }
+        cp_async_wait<kTpAhead>();  // rows of blocks <= blk + 1 have landed (this lane's own copies)
+        const int slot1 = (slot0 + KB) & (kTpRaw - 1);
+        float2 lpn[KB];
+#pragma unroll
+        for (int k = 0; k < KB; ++k) lpn[k] = rawc[(slot1 + k) * 32];
+
+        // exponent recurrence of step 0 of this block (it cannot run ahead across the renormalisation)
+        int En;
+        float c_own, c_in, c_edge;
+        {
+            const int pbe = DIR == 0 ? pbe_prev : fe[0][0], ple = DIR == 0 ? ple_prev : fe[0][1];
+            const int oE = E + pbe;
+            const int iE = __shfl_up_sync(0xffffffffu, DIR == 0 ? E + ple : E, 1) +
+                           (DIR == 0 ? in_bias : (blk == 0 ? kNoTerm : in_bias) + ple);
+            const int eE = DIR == 0 ? evE[0] : evE[0] + ple;
+            En = max(max(oE, iE), eE);
+            c_own = pow2_neg(En - oE) * (DIR == 0 ? pbm_prev : fm[0][0]);
+            c_in = pow2_neg(En - iE) * (DIR == 0 ? 1.f : fm[0][1]);
+            c_edge = pow2_neg(En - eE) * (DIR == 0 ? 1.f : fm[0][1]);
+        }
+        float shm = DIR == 0 ? m * plm_prev : m;
+        const int ew = (blk * KB - G.lag) & (kTpEdge - 1);  // slot base of this warp's own boundary values
+#pragma unroll
+        for (int k = 0; k < KB; ++k) {
+            const float in_m = __shfl_up_sync(0xffffffffu, shm, 1);  // mantissa chain: the long-latency hop first
+            const float own_term = kMulti ? fmaf(evm[k], c_edge, m * c_own) : m * c_own;
+            const int Ek = En;
+            const float ci = c_in;
+            const float plm = fm[k][1];
+            const int ple = fe[k][1];
+            if (k + 1 < KB) {  // exponent recurrence of step k+1, in the shadow of the shuffle above
+                const int pbe_n = fe[DIR == 0 ? k : k + 1][0], ple_n = fe[DIR == 0 ? k : k + 1][1];
+                const int oE = Ek + pbe_n;
+                const int iE = __shfl_up_sync(0xffffffffu, DIR == 0 ? Ek + ple_n : Ek, 1) +
+                               (DIR == 0 ? in_bias : in_bias + ple_n);
+                const int eE = DIR == 0 ? evE[k + 1] : evE[k + 1] + ple_n;
+                En = max(max(oE, iE), eE);
+                c_own = pow2_neg(En - oE) * fm[DIR == 0 ? k : k + 1][0];
+                c_in = pow2_neg(En - iE) * (DIR == 0 ? 1.f : fm[k + 1][1]);
+                c_edge = pow2_neg(En - eE) * (DIR == 0 ? 1.f : fm[k + 1][1]);
+            } else {
+                pbm_prev = fm[k][0], plm_prev = plm, pbe_prev = fe[k][0], ple_prev = ple;
+            }
+            m = fmaf(in_m, ci, own_term);
+            E = Ek;
+            if (k + 1 == KB) {  // renormalise once per block
+                const int bits = __float_as_int(m);
+                m = __int_as_float((bits & 0x007fffff) | 0x3f800000);
+                E += (bits >> 23) - 127;
+            }
+            shm = DIR == 0 ? m * plm : m;
+            const int shE = DIR == 0 ? E + ple : E;
+            if (kMulti) {
+                if (lane == 31) edge[(ew + k + 1) & (kTpEdge - 1)][w] = make_int2(__float_as_int(shm), shE);
+                if (to_band) {  // slot q of the receiving band = this warp's step index minus its lag
+                    const int q = blk * KB + k - G.lag;
+                    if (q >= 0)
+                        asm volatile("st.shared::cluster.v2.u32 [%0], {%1, %2};" ::"r"(r_xedge + 8u * (unsigned)q),
+                                     "r"(__float_as_int(shm)), "r"(shE) : "memory");
+                }
+            }
+            // off the chain: pack and park the value; the factor registers of this step are free now and
+            // take the next block's factors of the same slot
+            outc[(slot0 + k) * 32] = me_pack(ME{m, E});
+            if (tau + k == t_last) last_m = m, last_E = E;
+            {
+                const ME fb = me_from_log(lpn[k].x), fl = me_from_log(lpn[k].y);
+                fm[k][0] = fb.m, fe[k][0] = fb.e, fm[k][1] = fl.m, fe[k][1] = fl.e;
+            }
+        }
+        if (to_band) asm volatile("st.release.cluster.shared::cluster.s32 [%0], %1;" ::"r"(r_xdone), "r"(blk + 1) : "memory");
+        // lane 31 has now passed rows row_st .. row_st + KB - 1
+        {
+            int ov[KB];
+#pragma unroll
+            for (int k = 0; k < KB; ++k) ov[k] = outc[((row_st + k + lane) & (kTpOut - 1)) * 32];
+#pragma unroll
+            for (int k = 0; k < KB; ++k) {
+                if ((unsigned)(row_st + k) < G.Tb_eff) *pst = ov[k];
+                pst += G.stride;
+            }
+            row_st += KB;
+        }
+        slot0 = slot1;
+        tau += KB;
+    }
+    cp_async_wait<0>();
+    for (; row_st < Tb; ++row_st, pst += G.stride)  // rows the last lanes finished in the final blocks
+        if ((unsigned)row_st < G.Tb_eff) *pst = outc[((row_st + lane) & (kTpOut - 1)) * 32];
+    if (t_last >= 0) {
+        const ME last{last_m, last_E};
+        if (DIR == 0) {
+            if (ll_alpha) {
+                const float2* src = lp2 + G.first;
+                ll_alpha[b] = (float)me_ln(me_normalize(me_mul(last, me_from_log(src[(long long)t_last * G.stride].x))));
+            }
+        } else {
+            costs[b] = cost_of(me_normalize(last));
+        }
+    }
+}
+
+template <bool kMulti, bool kCluster>
+__global__ void __launch_bounds__(128)
+lattice_sweep_tp_kernel(const float2* __restrict__ lp2, const int32_t* __restrict__ act_lens,
+                        const int32_t* __restrict__ label_lens, int T, int U1, int32_t* __restrict__ alpha,
+                        int32_t* __restrict__ beta, float* __restrict__ costs, float* __restrict__ ll_alpha,
+                        int xedge_slots) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TpWarp* tw = reinterpret_cast<TpWarp*>(smem_raw);
+    __shared__ int2 edge[kTpEdge][8];  // column w: written by warp w; column 4 stays "zero" (warp 0 of band 0)
+    __shared__ int xdone_slot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    WsBand X;
+    X.band = kCluster ? (int)cluster_ctarank() : 0;
+    X.n_bands = kCluster ? (int)cluster_nctarank() : 1;
+    X.xlag = X.band * (kBandSkew - kTpKB);
+    X.xedge = reinterpret_cast<int2*>(tw + nw);  // [xedge_slots], cluster launches only
+    X.xdone = &xdone_slot;
+    const int b = kCluster ? blockIdx.x / X.n_bands : blockIdx.x;
+    const int Tb = len_T(act_lens, b, T);
+    const int Ub = len_U(label_lens, b, U1);
+    if (kMulti) {
+        for (int i = threadIdx.x; i < kTpEdge * 8; i += blockDim.x) edge[i / 8][i % 8] = make_int2(0x3f800000, kZeroExp);
+        if (threadIdx.x == 0) xdone_slot = 0;
+        __syncthreads();
+    }
+    if (kCluster) cluster_barrier();  // no CTA may be written to before it has initialised its shared memory
+    (void)xedge_slots;
+    if (blockIdx.y == 0)
+        tp_sweep<0, kMulti, kCluster>(tw[warp], edge, lp2, Tb, Ub, T, U1, b, alpha, costs, ll_alpha, warp, nw, lane, X);
+    else
+        tp_sweep<1, kMulti, kCluster>(tw[warp], edge, lp2, Tb, Ub, T, U1, b, beta, costs, ll_alpha, warp, nw, lane, X);
+    if (kCluster) cluster_barrier();  // no CTA may exit while a neighbour can still write into its shared memory
+}
+
+// warps <= 4: one CTA per sweep.  More: bands of `bw` warps in a thread-block cluster.  Returns -1 when the
+// configuration cannot be launched (the caller falls back to the other kernels).
+int launch_tp(const float2* lp2, const int32_t* act_lens, const int32_t* label_lens, int B, int T, int U1,
+              int32_t* alpha, int32_t* beta, float* costs, float* ll_alpha, int warps, int bw, cudaStream_t stream) {
+    if (warps <= 4) {
+        const size_t smem = (size_t)warps * sizeof(TpWarp);
+        if (warps == 1) {
+            auto kern = lattice_sweep_tp_kernel<false, false>;
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+            kern<<<dim3(B, 2), 32, smem, stream>>>(lp2, act_lens, label_lens, T, U1, alpha, beta, costs, ll_alpha, 0);
+        } else {
+            auto kern = lattice_sweep_tp_kernel<true, false>;
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+            kern<<<dim3(B, 2), warps * 32, smem, stream>>>(lp2, act_lens, label_lens, T, U1, alpha, beta, costs, ll_alpha, 0);
+        }
+        return launch_status();
+    }
+    if (bw < 1 || bw > 4) return -1;
+    const int n_bands = (warps + bw - 1) / bw;
+    if (n_bands > 8) return -1;
+    const int max_lag = (warps - 1) * kTpKB + (n_bands - 1) * (kBandSkew - kTpKB);
+    const int slots = (T + U1 + max_lag + kTpKB - 1) / kTpKB * kTpKB;
+    const size_t smem = (size_t)bw * sizeof(TpWarp) + (size_t)slots * sizeof(int2);
+    if (smem + 4096 > 227 * 1024) return -1;
+    auto kern = lattice_sweep_tp_kernel<true, true>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(B * n_bands), 2);
+    cfg.blockDim = dim3((unsigned)(bw * 32));
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)n_bands;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int fits = 0;
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&fits, kern, &cfg);
+    if (e != cudaSuccess || fits < 1) {
+        (void)cudaGetLastError();
+        return -1;
+    }
+    e = cudaLaunchKernelEx(&cfg, kern, lp2, act_lens, label_lens, T, U1, alpha, beta, costs, ll_alpha, slots);
+    return e == cudaSuccess ? launch_status() : status_from_cuda(e);
+}
+
 }  // namespace
 
 int launch_lattice_sweep(const float2* lp2, const int32_t* act_lens, const int32_t* label_lens, int B,
@@ -785,6 +1110,15 @@ int launch_lattice_sweep(const float2* lp2, const int32_t* act_lens, const int32
     if (U1 > 1024) return RNNTB200_STATUS_INVALID_VALUE;
     const int warps = (U1 + 31) / 32;
     static const bool legacy = getenv("RNNTB200_SWEEP_LEGACY") != nullptr;  // A/B timing of the one-warp-does-all sweep
+    // A/B switch (timing experiments only): RNNTB200_SWEEP=tp | ws selects the self-contained or the
+    // warp-specialised kernel for every shape it can run; RNNTB200_SWEEP_BW = warps per band (tp, long sequences)
+    static const char* which = getenv("RNNTB200_SWEEP");
+    static const int band_warps = getenv("RNNTB200_SWEEP_BW") ? atoi(getenv("RNNTB200_SWEEP_BW")) : 2;
+    const bool force_tp = which && which[0] == 't', force_ws = which && which[0] == 'w';
+    if (!legacy && !force_ws && (force_tp || true)) {
+        const int st = launch_tp(lp2, act_lens, label_lens, B, T, U1, alpha, beta, costs, ll_alpha, warps, band_warps, stream);
+        if (st >= 0) return st;
+    }
     // Measured (sweep alone, us):  U1 = 81 (3 warps): 53 warp-specialised in one CTA / 59 single-role;
     // U1 = 101 (4 warps): 81 in one CTA (20 warps crowd the SM) / 74 as two bands / 68 single-role;
     // U1 = 301 (10 warps): 245 as five bands of two / 274 as four bands of three / 360 single-role cluster.
