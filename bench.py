@@ -46,7 +46,8 @@ def parse_args():
     p.add_argument("--steps", type=int, default=100)
     p.add_argument("--warmup", type=int, default=10)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    p.add_argument("--cfg", type=int, default=2, choices=[1, 2, 3, 4])
+    p.add_argument("--cfg", type=int, default=2, choices=[1, 2, 3, 4, 5],
+                   help="BASELINE.json configs[cfg-1]; 5 = full training step (LSTM encoder/predictor + fused joint/loss, DDP)")
     p.add_argument("--mode", default="concat_gelu", choices=["concat_gelu", "add_tanh"])
     p.add_argument("--gemm", default=None, choices=["fp32", "bf16"])
     p.add_argument("--ragged", action="store_true")
@@ -86,7 +87,7 @@ def ncu_traffic(kernel, c, args):
 
 def workload_config(args, world):
     from rnntransducer_b200 import synthetic
-    c = dict(synthetic.CONFIGS[args.cfg])
+    c = dict(synthetic.CONFIGS[2 if args.cfg == 5 else args.cfg])  # cfg 5: the cfg-2 batch per rank, full model
     if args.batch:
         c["B"] = args.batch
     gemm = args.gemm or ("fp32" if args.mode == "concat_gelu" or args.cfg == 2 else "bf16")
@@ -524,6 +525,154 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------
+# BASELINE cfg 5: the full training step under DDP
+CFG5_ENCODER = dict(input_size=80, hidden_size=1024, output_size=512, num_layers=8, rnn_type="lstm", dropout=0.0,
+                    bidirectional=True)   # reference config/config.json:3-11 with LSTM cells (BASELINE configs[4])
+CFG5_PREDICTOR = dict(embedding_size=73, hidden_size=1024, output_size=512, num_layers=2, rnn_type="lstm", dropout=0.0)
+
+
+def run_cfg5(args):
+    """Full RNNTransducer training step (reference model.py:52-60 + 110-126 under train.py:45-48): LSTM
+    encoder / predictor (cuDNN, library) -> fused joint + RNN-T loss (ours) -> backward -> DDP bucketed
+    all-reduce overlapping the cuDNN backward -> AdamW + OneCycleLR.  Per rank the cfg-2 batch (B=32, T=400
+    log-mel frames of 80 bins, U=80, V=73, joint width 512); metric = lattice cells/s of the whole step."""
+    import torch
+    import torch.distributed as dist
+
+    import rnntransducer_b200 as rb
+    from rnntransducer_b200 import _lib, synthetic
+    from rnntransducer_b200.training import synthetic_training_batch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl ours) needs a CUDA device: there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    c, gemm, config = workload_config(args, world)
+    B, T, U, V, H = c["B"], c["T"], c["U"], c["V"], c["H"]
+    torch.manual_seed(1234)  # same initial parameters on every rank (DDP broadcasts rank 0's anyway)
+    step_mod = rb.RNNTransducerStep(dict(CFG5_PREDICTOR), dict(CFG5_ENCODER), dict(num_classes=V), blank_token_id=0,
+                                    mode=args.mode, gemm=gemm, deterministic=bool(args.deterministic)).to(dev).train()
+    n_params = sum(p.numel() for p in step_mod.parameters())
+    model = step_mod
+    if world > 1:
+        model = torch.nn.parallel.DistributedDataParallel(step_mod, device_ids=[local_rank], gradient_as_bucket_view=True)
+    total_steps = max(args.warmup, 3) + 2 * args.steps + 8
+    opt, sched = rb.configure_optimizers(step_mod, learning_rate=1e-4, weight_decay=1e-2, total_steps=total_steps)
+    host = synthetic_training_batch(B, T, U, CFG5_ENCODER["input_size"], V, ragged=args.ragged, seed=1239 + rank)
+    cells = synthetic.count_cells(host[2], host[6])
+    tensors = [i for i, x in enumerate(host) if torch.is_tensor(x)]
+    pinned = {i: host[i].pin_memory() for i in tensors}
+    dev_batch = list(host)
+    for i in tensors:
+        dev_batch[i] = host[i].to(dev)
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    out = {}
+
+    def train_step(batch):
+        opt.zero_grad(set_to_none=True)
+        loss = model(*batch)
+        loss.backward()          # DDP all-reduces its buckets while cuDNN is still in the encoder's backward
+        opt.step()
+        sched.step()
+        out["loss"] = loss.detach()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        train_step(dev_batch)
+    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    with ClockSampler(local_rank) as clocks:
+        for e0, e1 in ev:
+            flush_buf.zero_()
+            e0.record()
+            train_step(dev_batch)
+            e1.record()
+        torch.cuda.synchronize()
+    total_ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
+    barrier()
+
+    # end to end: the collate's batch arrives in pinned host memory every step, the loss is read back
+    loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
+    h2d = sum(pinned[i].numel() * pinned[i].element_size() for i in tensors)
+
+    def e2e_step():
+        batch = list(host)
+        for i in tensors:
+            batch[i] = pinned[i].to(dev, non_blocking=True)
+        train_step(batch)
+        loss_host.copy_(out["loss"].reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    torch.cuda.synchronize()
+    e2e_ms = e0.elapsed_time(e1)
+    barrier()
+    total_cells = float(cells)
+    if world > 1:
+        t = torch.tensor([total_ms, e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_ms = float(t[0]), float(t[1])
+        ct = torch.tensor([cells], device=dev, dtype=torch.float64)
+        dist.all_reduce(ct)
+        total_cells = float(ct[0])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    # roofline of OUR part of the step: the joint + loss kernels on encoder / predictor outputs of this shape
+    from rnntransducer_b200.joint_add_tanh import GEMMS
+    syn = {k: v.to(dev) for k, v in synthetic.make_batch(B, T, U, V, H, mode=args.mode, ragged=args.ragged, seed=1239).items()}
+    kernels = per_kernel(lib, syn, args.mode, GEMMS[gemm], bool(args.deterministic), B, T, U + 1, V, H, cells, flush_buf)
+    peak, peak_src = hbm_peak()
+    for k in kernels.values():
+        k["GBps"] = k["bytes"] / (k["us"] * 1e-6) / 1e9
+        k["frac_hbm"] = k["GBps"] / peak
+    top = kernels["lattice_sweep_kernel"]
+    ours_us = sum(k["us"] for k in kernels.values() if k.get("ours"))
+    config.update({"workload": f"BASELINE cfg5: full training step, per GPU B={B} T={T} (80-bin log-mel) U={U} V={V}; "
+                               f"LSTM encoder 8x1024 bidirectional -> 512, LSTM predictor 2x1024 -> 512, fused joint + RNN-T "
+                               f"loss, AdamW + OneCycleLR, torch DDP ({n_params / 1e6:.0f} M parameters)",
+                   "parallelism": f"ddp{world} (torch DistributedDataParallel, NCCL bucketed all-reduce overlapping backward)",
+                   "parameters": n_params, "precision": "fp32 parameters, cuDNN RNN with TF32 tensor cores (torch default)"})
+    line = {
+        "metric": METRIC, "value": total_cells * args.steps / (total_ms * 1e-3), "unit": UNIT,
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 (TF32 cuDNN RNN)", "data": "synthetic", "config": config,
+        "utterances_per_s": B * world * args.steps / (total_ms * 1e-3), "cells_per_step": total_cells,
+        "loss": float(out["loss"]), "cuda_graph": False, "clocks": clocks.summary(),
+        "e2e": {"value": total_cells * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": (7 + int(bool(args.deterministic))) * args.steps,
+        "roofline": {"kernel": top["name"], "bound": "hbm", "achieved": top["GBps"], "peak": peak, "unit": "GB/s",
+                     "frac": top["frac_hbm"], "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": top["bytes"], "us_per_launch": top["us"]},
+        "kernels": kernels,
+        "joint_loss_share_of_step": ours_us * 1e-3 / (total_ms / args.steps),
+    }
+    emit(line)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def reference_joint_eager(enc, dec, weight, bias, mode):
     """The reference's JointNet.joint as it runs on its GPU (networks/transducer.py:54-71: unsqueeze ->
     repeat x2 -> cat -> GELU(tanh) -> Linear), materialising every [B,T,U1,2H] intermediate; add_tanh:
@@ -745,6 +894,8 @@ def main():
     os.dup2(2, 1)  # stray prints of libraries -> stderr
     if args.impl == "reference":
         run_reference(args)
+    elif args.cfg == 5:
+        run_cfg5(args)
     else:
         run_ours(args)
 

@@ -11,5 +11,7 @@ Host code is Python/PyTorch; every kernel is reached through the C ABI of ``libr
 from .loss import RNNTLoss, rnnt_costs, rnnt_loss  # noqa: F401
 from .joint import JointLogits, JointNet, joint_dense, joint_rnnt_costs, joint_rnnt_loss  # noqa: F401
 from .networks import AudioTransNet, TextPredNet  # noqa: F401
+from .training import RNNTransducerStep, configure_optimizers  # noqa: F401
+from .data import DistributedBucketSampler, collate_sorted  # noqa: F401
 
 __version__ = "0.1.0"

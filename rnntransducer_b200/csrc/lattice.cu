@@ -801,6 +801,8 @@ constexpr int kTpAhead = 2;     // blocks of lp2 rows in flight beyond the one b
 constexpr int kTpRaw = 64;      // FIFO depth (rows): 31 (lane skew) + (kTpAhead + 2) * kTpKB <= 64
 constexpr int kTpOut = 64;      // FIFO depth (rows): 31 + kTpKB + 1 <= 64
 constexpr int kTpEdge = 32;     // >= 2 * kTpKB + 1 slots for warp-boundary values
+constexpr int kTpBandSkew = 16; // steps the first warp of a band trails the last warp of the previous band
+constexpr int kTpNoValue = (int)0x80000000;  // both words of a boundary slot nobody has written yet
 static_assert(31 + (kTpAhead + 2) * kTpKB <= kTpRaw && 32 + kTpKB <= kTpOut, "FIFO too shallow");
 
 struct TpWarp {
@@ -815,17 +817,14 @@ __device__ __forceinline__ void tp_sweep(TpWarp& W, int2 (*edge)[8], const float
     constexpr int KB = kTpKB;
     const WsGeom<DIR, kMulti, KB> G(Tb, Ub, T, U1, b, X.band * nw + w, lane, X.xlag);
     const int n_on = (Ub + 32) / 32;  // warps with cells
-    const int max_lag = kMulti ? (n_on - 1) * KB + ((n_on - 1) / nw) * (kBandSkew - KB) : 0;
+    const int max_lag = kMulti ? (n_on - 1) * KB + ((n_on - 1) / nw) * (kTpBandSkew - KB) : 0;
     const int n_blocks = (Tb + Ub + max_lag + KB - 1) / KB;
     const int edge_col = (kMulti && w > 0) ? w - 1 : 4;
     const bool from_band = kCluster && w == 0 && X.band > 0;
     const bool to_band = kCluster && w == nw - 1 && X.band + 1 < X.n_bands && lane == 31;
-    const uint32_t xdone = tc::smem_u32(X.xdone);
-    uint32_t r_xedge = 0, r_xdone = 0;
-    if (to_band) {
+    uint32_t r_xedge = 0;
+    if (to_band)
         asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r_xedge) : "r"(tc::smem_u32(X.xedge)), "r"(X.band + 1));
-        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r_xdone) : "r"(xdone), "r"(X.band + 1));
-    }
     const int in_bias = lane == 0 ? kNoTerm : 0;
     // FIFO slot of (row r, lane l) = (r + l) mod depth: lane l meets row r at step r + base + l, so the slot
     // index is the STEP index (minus base) -- uniform across the lanes and, base being a multiple of KB,
@@ -888,14 +887,6 @@ __device__ __forceinline__ void tp_sweep(TpWarp& W, int2 (*edge)[8], const float
     for (int blk = 0; blk < n_blocks; ++blk) {
         if (kMulti) __syncthreads();  // the previous warp has finished the block this one reads boundary values of
         load_block();                 // rows of block blk + kTpAhead + 1
-        if (from_band && blk >= kBandSkew / KB) {
-            int done;
-            for (;;) {
-                asm volatile("ld.acquire.cluster.shared::cta.s32 %0, [%1];" : "=r"(done) : "r"(xdone) : "memory");
-                if (done > blk - kBandSkew / KB) break;
-                __nanosleep(32);
-            }
-        }
         // boundary values of this block: every lane reads them (a broadcast), lanes other than 0 push the term
         // out of reach with an exponent bias.  Reader slots are block-aligned: the writer stores its local step
         // p at slot p + 1, the reader of local step q wants p = q - 1, i.e. slot q = er + k.
@@ -907,8 +898,24 @@ __device__ __forceinline__ void tp_sweep(TpWarp& W, int2 (*edge)[8], const float
             for (int k = 0; k < KB; ++k) {
                 int2 ev = edge[er + k][edge_col];
                 if (kCluster && from_band) {
+                    // The slot IS the flag: every slot is written exactly once, by one 8-byte remote store of
+                    // the previous band's lane 31; until then both words hold kTpNoValue.  No release /
+                    // acquire pair, no progress counter: the sender never waits for anything.
                     const int q = blk * KB + k - G.lag - 1;
-                    ev = q >= 0 ? X.xedge[q] : make_int2(0x3f800000, kZeroExp);
+                    ev = make_int2(0x3f800000, kZeroExp);
+                    if (q >= 0) {
+                        const volatile int2* slot = X.xedge + q;
+                        long long t0 = 0;
+                        for (unsigned spins = 0;; ++spins) {
+                            ev.x = slot->x, ev.y = slot->y;
+                            if (ev.x != kTpNoValue && ev.y != kTpNoValue) break;
+                            if ((spins & 4095) == 4095) {  // a protocol bug must fail loudly, not hang the GPU
+                                const long long now = clock64();
+                                if (t0 == 0) t0 = now;
+                                else if (now - t0 > 4000000000LL) __trap();
+                            }
+                        }
+                    }
                 }
                 evm[k] = __int_as_float(ev.x);
                 evE[k] = ev.y + edge_bias;
@@ -970,7 +977,7 @@ __device__ __forceinline__ void tp_sweep(TpWarp& W, int2 (*edge)[8], const float
             shm = DIR == 0 ? m * plm : m;
             const int shE = DIR == 0 ? E + ple : E;
             if (kMulti) {
-                if (lane == 31) edge[(ew + k + 1) & (kTpEdge - 1)][w] = make_int2(__float_as_int(shm), shE);
+                if (lane == 31) edge[k + 1 < KB ? ew + k + 1 : (ew + KB) & (kTpEdge - 1)][w] = make_int2(__float_as_int(shm), shE);
                 if (to_band) {  // slot q of the receiving band = this warp's step index minus its lag
                     const int q = blk * KB + k - G.lag;
                     if (q >= 0)
@@ -987,7 +994,6 @@ __device__ __forceinline__ void tp_sweep(TpWarp& W, int2 (*edge)[8], const float
                 fm[k][0] = fb.m, fe[k][0] = fb.e, fm[k][1] = fl.m, fe[k][1] = fl.e;
             }
         }
-        if (to_band) asm volatile("st.release.cluster.shared::cluster.s32 [%0], %1;" ::"r"(r_xdone), "r"(blk + 1) : "memory");
         // lane 31 has now passed rows row_st .. row_st + KB - 1
         {
             int ov[KB];
@@ -1033,7 +1039,7 @@ lattice_sweep_tp_kernel(const float2* __restrict__ lp2, const int32_t* __restric
     WsBand X;
     X.band = kCluster ? (int)cluster_ctarank() : 0;
     X.n_bands = kCluster ? (int)cluster_nctarank() : 1;
-    X.xlag = X.band * (kBandSkew - kTpKB);
+    X.xlag = X.band * (kTpBandSkew - kTpKB);
     X.xedge = reinterpret_cast<int2*>(tw + nw);  // [xedge_slots], cluster launches only
     X.xdone = &xdone_slot;
     const int b = kCluster ? blockIdx.x / X.n_bands : blockIdx.x;
@@ -1044,8 +1050,10 @@ lattice_sweep_tp_kernel(const float2* __restrict__ lp2, const int32_t* __restric
         if (threadIdx.x == 0) xdone_slot = 0;
         __syncthreads();
     }
-    if (kCluster) cluster_barrier();  // no CTA may be written to before it has initialised its shared memory
-    (void)xedge_slots;
+    if (kCluster) {
+        for (int i = threadIdx.x; i < xedge_slots; i += blockDim.x) X.xedge[i] = make_int2(kTpNoValue, kTpNoValue);
+        cluster_barrier();  // no CTA may be written to before it has initialised its shared memory
+    }
     if (blockIdx.y == 0)
         tp_sweep<0, kMulti, kCluster>(tw[warp], edge, lp2, Tb, Ub, T, U1, b, alpha, costs, ll_alpha, warp, nw, lane, X);
     else
@@ -1073,7 +1081,7 @@ int launch_tp(const float2* lp2, const int32_t* act_lens, const int32_t* label_l
     if (bw < 1 || bw > 4) return -1;
     const int n_bands = (warps + bw - 1) / bw;
     if (n_bands > 8) return -1;
-    const int max_lag = (warps - 1) * kTpKB + (n_bands - 1) * (kBandSkew - kTpKB);
+    const int max_lag = (warps - 1) * kTpKB + (n_bands - 1) * (kTpBandSkew - kTpKB);
     const int slots = (T + U1 + max_lag + kTpKB - 1) / kTpKB * kTpKB;
     const size_t smem = (size_t)bw * sizeof(TpWarp) + (size_t)slots * sizeof(int2);
     if (smem + 4096 > 227 * 1024) return -1;

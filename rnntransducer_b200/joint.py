@@ -179,25 +179,62 @@ class JointNet(nn.Module):
         return self.joint(enc_state, dec_state)
 
     @torch.no_grad()
-    def recognize_greedy(self, input_audios: Tensor, audio_lengths, blank_token_id: int,
-                         max_iters: int = 3):
-        """Greedy decode, same loop structure as transducer.py:95-145 (out of the hot path; eager)."""
-        enc_states = self.encoder(input_audios, audio_lengths)
-        outputs = []
-        for b in range(enc_states.size(0)):
-            T_b = int(audio_lengths[b])
-            tokens = []
-            dec_in = torch.full((1, 1), blank_token_id, dtype=torch.long, device=enc_states.device)
-            dec_out, hidden = self.decoder(dec_in)
-            for t in range(T_b):
-                for _ in range(max_iters):
-                    logits = self.joint(enc_states[b, t].view(-1), dec_out.view(-1))
-                    pred = int(logits.argmax(dim=-1))
-                    if pred == blank_token_id:
-                        break
-                    if not tokens or tokens[-1] != pred:  # reference de-dups repeats (:130-132)
-                        tokens.append(pred)
-                    dec_in = torch.full((1, 1), pred, dtype=torch.long, device=enc_states.device)
-                    dec_out, hidden = self.decoder(dec_in, None, hidden)
-            outputs.append(tokens)
-        return outputs
+    def recognize_greedy(self, inputs: Tensor, inputs_lengths, blank_token_id: int, max_iters: int = 3,
+                         respect_lengths: bool = False) -> Tensor:
+        """Greedy decode of the whole batch at once (reference transducer.py:95-145, called from every
+        validation step, model.py:76).
+
+        The reference walks utterance by utterance, frame by frame, symbol by symbol, with an ``.item()``
+        (a device sync) per symbol.  Here all B utterances advance together: per (frame, iteration) one
+        joint evaluation ``[B, V]``, one arg-max, one predictor step for the whole batch whose new state is
+        kept only in the rows that emitted a symbol -- same tokens, no host round trip until the single
+        read of the longest hypothesis' length at the end.  In the reference's own joint the encoder half
+        of the logits, ``gelu(enc) W_e^T + b`` for all B*T frames, is computed ONCE by the fused path's
+        projection kernel (``rnntb200_joint_cg_project``); a step then costs a ``[B, Hd] x [Hd, V]``
+        product.
+
+        Like the reference: every padded frame is decoded (``respect_lengths=True`` stops each row at its
+        own length instead), at most ``max_iters`` symbols per frame, a symbol equal to the previously
+        *kept* one is fed to the predictor but not kept.  Returns ``LongTensor [B, L]`` on the inputs'
+        device, L = longest hypothesis, shorter rows padded with ``blank_token_id`` (the reference stacks
+        the rows and therefore only works when all hypotheses are equally long; then the two agree)."""
+        enc = self.encoder(inputs, inputs_lengths)
+        B, T, He = enc.shape
+        dev = enc.device
+        W, bias = self.fc.weight, self.fc.bias
+        tok = torch.full((B, 1), blank_token_id, dtype=torch.long, device=dev)
+        dec_out, hidden = self.decoder(tok)
+        dec_out = dec_out[:, 0]
+        factorised = self.mode == "concat_gelu"
+        if factorised:  # logits(t) = P_enc[:, t] + gelu(dec) W_d^T
+            penc, _ = _loss.project_concat_gelu(enc, dec_out.unsqueeze(1), W, bias)
+            W_d = W[:, He:]
+        lens = None
+        if respect_lengths:
+            lens = torch.tensor([int(n) for n in inputs_lengths], device=dev)
+        rows = torch.arange(B, device=dev)
+        kept = torch.full((B, T * max_iters + 1), blank_token_id, dtype=torch.long, device=dev)
+        count = torch.zeros(B, dtype=torch.long, device=dev)
+        last = torch.full((B,), blank_token_id, dtype=torch.long, device=dev)
+        sel = lambda m, new, old: torch.where(m.view((1, B, 1)), new, old)
+        for t in range(T):
+            active = torch.ones(B, dtype=torch.bool, device=dev) if lens is None else lens > t
+            for _ in range(max_iters):
+                if factorised:
+                    logits = penc[:, t] + F.linear(F.gelu(dec_out, approximate="tanh"), W_d)
+                else:
+                    logits = joint_dense(enc[:, t], dec_out, W, bias, self.mode)
+                pred = logits.argmax(dim=-1)
+                emit = active & (pred != blank_token_id)
+                new_out, new_hidden = self.decoder(pred.unsqueeze(1), None, hidden)
+                dec_out = torch.where(emit.unsqueeze(1), new_out[:, 0], dec_out)
+                if isinstance(hidden, tuple):
+                    hidden = tuple(sel(emit, n, o) for n, o in zip(new_hidden, hidden))
+                else:
+                    hidden = sel(emit, new_hidden, hidden)
+                keep = emit & (pred != last)
+                kept[rows, count] = torch.where(keep, pred, kept[rows, count])
+                count = count + keep
+                last = torch.where(keep, pred, last)
+                active = emit
+        return kept[:, :max(int(count.max()), 0)]  # the one device sync of the decode
