@@ -54,6 +54,9 @@ def parse_args():
     p.add_argument("--batch", type=int, default=None, help="override the config's utterances per GPU")
     p.add_argument("--eager", action="store_true", help="do not replay the step from a CUDA graph")
     p.add_argument("--deterministic", action="store_true")
+    p.add_argument("--allreduce", default="peer", choices=["peer", "nccl"],
+                   help="N>1: gradient all-reduce of the fc grads -- one-shot kernel over NVLink peer memory inside the "
+                        "step's CUDA graph (default) or torch.distributed/NCCL issued from the host after the graph")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-gpu-baseline", action="store_true",
                    help="skip the reference's own GPU path (eager joint + torchaudio CUDA rnnt_loss)")
@@ -343,12 +346,29 @@ def run_ours(args):
             st[k].grad = None
 
     out = {}
+    # N > 1: what DDP does with the gradients our kernels produce (fc.weight, fc.bias) -- averaged over the
+    # ranks every step, inside the timed bracket.  Default: ONE kernel over NVLink peer memory (csrc/comm.cu)
+    # that is part of the captured step, so a step stays one graph replay with no host work in between.
+    # --allreduce nccl: one flat bucket + one torch.distributed all_reduce issued after the graph (round 1).
+    peer_ar, ar_note = None, None
+    if world > 1 and args.allreduce == "peer":
+        try:
+            from rnntransducer_b200.comm import PeerAllReduce
+            peer_ar = PeerAllReduce(st["weight"].numel() + st["bias"].numel())
+        except Exception as e:  # cudaIpc not permitted on this box: say so and use NCCL
+            ar_note = f"peer-memory all-reduce unavailable ({e!r}); NCCL used"
+        ok = torch.tensor([int(peer_ar is not None)], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok) == 0:
+            peer_ar = None
 
     def step():
         loss = rb.joint_rnnt_loss(st["enc"], st["dec"], st["weight"], st["bias"], st["labels"],
                                   st["act_lens"], st["label_lens"], 0, "mean", mode, gemm,
                                   deterministic=det)
         loss.backward()
+        if peer_ar is not None:
+            peer_ar.all_reduce_mean_([st["weight"].grad, st["bias"].grad])
         out["loss"] = loss.detach()
 
     # eager warm-up (also JITs nothing: the library is prebuilt) on a side stream, then capture
@@ -367,9 +387,6 @@ def run_ours(args):
         with torch.cuda.graph(graph):
             step()
 
-    # what DDP does with the gradients our kernels produce: one flat bucket (fc.weight + fc.bias)
-    # and ONE all-reduce per step, inside the timed bracket (there is nothing left in this step to
-    # overlap it with: the fc gradients come out of the last kernel)
     bucket = torch.empty(st["weight"].numel() + st["bias"].numel(), device=dev)
 
     def run_step():
@@ -378,7 +395,7 @@ def run_ours(args):
         else:
             zero_grads()
             step()
-        if world > 1:
+        if world > 1 and peer_ar is None:
             torch.cat((st["weight"].grad.reshape(-1), st["bias"].grad), out=bucket)
             dist.all_reduce(bucket)
 
@@ -453,7 +470,29 @@ def run_ours(args):
     barrier()
     loss_value = float(loss_host[0])
 
+    ar_info = None
     if world > 1:
+        # the collective by itself (ranks in lock-step, CUDA events, max over ranks): what it adds to a step
+        def alone(fn, n=50):
+            for _ in range(5):
+                fn()
+            barrier()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(n):
+                fn()
+            a1.record()
+            torch.cuda.synchronize()
+            return 1e3 * a0.elapsed_time(a1) / n
+        gw, gb = st["weight"].grad.clone(), st["bias"].grad.clone()
+        us_nccl = alone(lambda: dist.all_reduce(bucket))
+        us_peer = alone(lambda: peer_ar.all_reduce_mean_([gw, gb])) if peer_ar is not None else None
+        t = torch.tensor([us_nccl, us_peer or 0.0], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ar_info = {"impl": "peer-memory one-shot kernel inside the step's CUDA graph" if peer_ar is not None
+                   else "NCCL all_reduce of one flat bucket, issued from the host after the graph",
+                   "floats": bucket.numel(), "us_alone_nccl": float(t[0]),
+                   "us_alone_peer": float(t[1]) if peer_ar is not None else None, "note": ar_note}
         t = torch.tensor([total_ms, e2e_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms, e2e_ms = float(t[0]), float(t[1])
@@ -487,6 +526,9 @@ def run_ours(args):
         sat["frac"] = sat["GBps"] / peak
         roofline["saturating_batch"] = sat
 
+    used_peer = peer_ar is not None
+    if used_peer:
+        peer_ar.close()  # collective: every rank is here
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -495,7 +537,7 @@ def run_ours(args):
     # our kernels per step: concat_gelu = weight split + projection + factor rows + lse + sweep + grad
     # + projection backward (+ slab reduction); add_tanh = weight convert + lse + sweep + (weight
     # convert +) grad
-    launches = {"concat_gelu": 7 + int(det), "add_tanh": 5 if gemm == "bf16" else 3}[mode]
+    launches = {"concat_gelu": 7 + int(det), "add_tanh": 5 if gemm == "bf16" else 3}[mode] + int(used_peer)
     line = {
         "metric": METRIC, "value": total_cells * args.steps / (total_ms * 1e-3), "unit": UNIT,
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -513,6 +555,9 @@ def run_ours(args):
         "gpu_launches": launches * args.steps,
         "roofline": roofline, "kernels": kernels,
     }
+    if ar_info is not None:
+        line["allreduce"] = ar_info
+        line["config"]["parallelism"] = f"dp{world} (utterances sharded, fc grads all-reduced: {ar_info['impl']})"
     if world == 1 and not args.no_gpu_baseline:
         torch.cuda.empty_cache()
         line["gpu_baseline"] = gpu_baseline(st, mode, cells)
