@@ -219,7 +219,8 @@ RNNTB200_API int rnntb200_joint_at_logprobs(const float* enc, const float* dec, 
  * NCCL all-reduce DDP issues for the fc gradients this path produces (reference train.py:45-48,
  * model.py:59).  Unlike every other entry point these own memory: a rank's buffer must be a cudaMalloc
  * allocation of its own so that its cudaIpc handle names exactly it.
- *   rnntb200_comm_buffer_bytes(max_floats)   size of one rank's buffer for vectors of <= max_floats
+ *   rnntb200_comm_buffer_bytes(max_floats, world)   size of one rank's buffer (one slot per source rank
+ *                                            and step parity) for vectors of <= max_floats
  *   rnntb200_comm_alloc / _free              the buffer (zeroed; synchronises the device once)
  *   rnntb200_comm_export(ptr, handle[64])    cudaIpcMemHandle_t of the buffer, to be sent to the peers
  *   rnntb200_comm_import(handle, &ptr) / rnntb200_comm_release(ptr)   map / unmap a peer's buffer
@@ -228,7 +229,7 @@ RNNTB200_API int rnntb200_joint_at_logprobs(const float* enc, const float* dec, 
  *     enqueues ONE kernel: segments (in place) <- scale * sum over ranks, summed in rank order (bit-identical
  *     on every rank).  No host synchronisation, no per-step argument changes: CUDA-graph capturable.  Every
  *     rank must call it the same number of times with the same segment sizes; world <= 8. */
-RNNTB200_API size_t rnntb200_comm_buffer_bytes(size_t max_floats);
+RNNTB200_API size_t rnntb200_comm_buffer_bytes(size_t max_floats, int world);
 RNNTB200_API int rnntb200_comm_alloc(size_t bytes, void** dev_ptr);
 RNNTB200_API int rnntb200_comm_free(void* dev_ptr);
 RNNTB200_API int rnntb200_comm_export(void* dev_ptr, unsigned char* handle64);

@@ -35,7 +35,7 @@ SIGNATURES = {
     "rnntb200_dense_logprobs": (_c_int, [_P, _c_int, _P, _P, _P] + [_c_int] * 5 + [_P] * 3),
     "rnntb200_joint_cg_logprobs": (_c_int, [_P] * 5 + [_c_int] * 5 + [_P] * 3 + [_c_size_t, _P]),
     "rnntb200_joint_at_logprobs": (_c_int, [_P] * 4 + [_c_int] + [_P] * 3 + [_c_int] * 6 + [_P] * 3 + [_c_size_t, _P]),
-    "rnntb200_comm_buffer_bytes": (_c_size_t, [_c_size_t]),
+    "rnntb200_comm_buffer_bytes": (_c_size_t, [_c_size_t, _c_int]),
     "rnntb200_comm_alloc": (_c_int, [_c_size_t, ctypes.POINTER(_c_void_p)]),
     "rnntb200_comm_free": (_c_int, [_P]),
     "rnntb200_comm_export": (_c_int, [_P, ctypes.c_char_p]),

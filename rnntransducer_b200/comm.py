@@ -29,7 +29,7 @@ class PeerAllReduce:
             raise RuntimeError("PeerAllReduce: at most 8 ranks (one NVSwitch domain)")
         self.max_floats = int(max_floats)
         self.device = torch.device("cuda", torch.cuda.current_device())
-        nbytes = self.lib.rnntb200_comm_buffer_bytes(self.max_floats)
+        nbytes = self.lib.rnntb200_comm_buffer_bytes(self.max_floats, self.world)
         own = ctypes.c_void_p()
         _lib.check(self.lib.rnntb200_comm_alloc(nbytes, ctypes.byref(own)), "rnntb200_comm_alloc")
         self.own = own.value

@@ -697,7 +697,8 @@ lattice_sweep_ws_kernel(const float2* __restrict__ lp2, const int32_t* __restric
     int n_blocks = (Tb + Ub + max_lag + KB - 1) / KB;
     if (kCluster) n_blocks = min(n_blocks, xedge_slots / KB);  // (the host sized xedge for the longest utterance)
     int w = warp % nw, role = warp / nw;
-    if (spread) {
+    if (spread == 2) role = 4 - role;  // experiment: chain warps get the HIGHEST warp ids (the issue arbiter favours them)
+    if (spread == 1) {
         w = warp & 1;
         role = warp < 2 ? 0 : (warp & 2) ? 1 + (warp >> 2) : 5;  // 2,3 loaders; 6,7 / 10,11 converters; 14,15 consumers
     }
@@ -732,8 +733,9 @@ int launch_ws(const float2* lp2, const int32_t* act_lens, const int32_t* label_l
     cudaError_t e = cudaFuncSetAttribute(lattice_sweep_ws_kernel<kMulti, KB, RW, false>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return status_from_cuda(e);
+    static const int chain_last = getenv("RNNTB200_WS_CHAIN_LAST") ? 2 : 0;
     lattice_sweep_ws_kernel<kMulti, KB, RW, false><<<dim3(B, 2), warps * 160, smem, stream>>>(
-        lp2, act_lens, label_lens, T, U1, alpha, beta, costs, ll_alpha, 0, warps, 0);
+        lp2, act_lens, label_lens, T, U1, alpha, beta, costs, ll_alpha, 0, warps, chain_last);
     return launch_status();
 }
 
