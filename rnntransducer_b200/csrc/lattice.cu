@@ -827,7 +827,6 @@ __device__ __forceinline__ void tp_sweep(TpWarp& W, int2 (*edge)[8], const float
     uint32_t r_xedge = 0;
     if (to_band)
         asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r_xedge) : "r"(tc::smem_u32(X.xedge)), "r"(X.band + 1));
-    const int in_bias = lane == 0 ? kNoTerm : 0;
     // FIFO slot of (row r, lane l) = (r + l) mod depth: lane l meets row r at step r + base + l, so the slot
     // index is the STEP index (minus base) -- uniform across the lanes and, base being a multiple of KB,
     // the KB slots of a block are consecutive: the chain side addresses both FIFOs with one register and
@@ -848,10 +847,17 @@ __device__ __forceinline__ void tp_sweep(TpWarp& W, int2 (*edge)[8], const float
     const float2* src0 = lp2 + G.first;
     auto load_block = [&]() {
         if (lane_on) {
+            if (r_ld >= 0 && r_ld + KB <= Tb) {  // (warp-uniform) every row of the block exists: no clamping
+                const float2* p = src0 + r_ld * G.stride;
 #pragma unroll
-            for (int k = 0; k < KB; ++k) {
-                const int rc = min(max(r_ld + k, 0), Tb - 1);
-                cp_async_8(rawc + ((r_ld + k + lane) & (kTpRaw - 1)) * 32, src0 + rc * G.stride);
+                for (int k = 0; k < KB; ++k, p += G.stride)
+                    cp_async_8(rawc + ((r_ld + k + lane) & (kTpRaw - 1)) * 32, p);
+            } else {
+#pragma unroll
+                for (int k = 0; k < KB; ++k) {
+                    const int rc = min(max(r_ld + k, 0), Tb - 1);
+                    cp_async_8(rawc + ((r_ld + k + lane) & (kTpRaw - 1)) * 32, src0 + rc * G.stride);
+                }
             }
         }
         r_ld += KB;
@@ -877,7 +883,6 @@ __device__ __forceinline__ void tp_sweep(TpWarp& W, int2 (*edge)[8], const float
     int E = G.j == 0 ? 0 : kZeroExp;
     float pbm_prev = 1.f, plm_prev = 1.f;
     int pbe_prev = 0, ple_prev = DIR == 0 ? kNoTerm : 0;
-    const int edge_bias = lane == 0 ? 0 : kNoTerm;
     int tau = G.tau0;                 // progress at the first step of the current block
     int row_st = -G.base - 31;        // next row to be stored (complete once lane 31 has passed it)
     int32_t* pst = out + G.first + (long long)row_st * G.stride;
@@ -889,9 +894,11 @@ __device__ __forceinline__ void tp_sweep(TpWarp& W, int2 (*edge)[8], const float
     for (int blk = 0; blk < n_blocks; ++blk) {
         if (kMulti) __syncthreads();  // the previous warp has finished the block this one reads boundary values of
         load_block();                 // rows of block blk + kTpAhead + 1
-        // boundary values of this block: every lane reads them (a broadcast), lanes other than 0 push the term
-        // out of reach with an exponent bias.  Reader slots are block-aligned: the writer stores its local step
-        // p at slot p + 1, the reader of local step q wants p = q - 1, i.e. slot q = er + k.
+        // boundary values of this block (a broadcast load; only lane 31 uses them): the hand-off is a ROTATE
+        // by one lane in which lane 31 sends, instead of its own share, the value the previous warp left for
+        // this warp's lane 0 -- no third term, no lane-0 special case in the recursion.  Reader slots are
+        // block-aligned: the writer stores its local step p at slot p + 1, the reader of local step q wants
+        // p = q - 1, i.e. slot q = er + k.
         float evm[KB];
         int evE[KB];
         if (kMulti) {
@@ -920,11 +927,11 @@ __device__ __forceinline__ void tp_sweep(TpWarp& W, int2 (*edge)[8], const float
                     }
                 }
                 evm[k] = __int_as_float(ev.x);
-                evE[k] = ev.y + edge_bias;
+                evE[k] = ev.y;
             }
         } else {
 #pragma unroll
-            for (int k = 0; k < KB; ++k) evm[k] = 1.f, evE[k] = kNoTerm;
+            for (int k = 0; k < KB; ++k) evm[k] = 1.f, evE[k] = kZeroExp;
         }
         cp_async_wait<kTpAhead>();  // rows of blocks <= blk + 1 have landed (this lane's own copies)
         const int slot1 = (slot0 + KB) & (kTpRaw - 1);
@@ -933,25 +940,26 @@ __device__ __forceinline__ void tp_sweep(TpWarp& W, int2 (*edge)[8], const float
         for (int k = 0; k < KB; ++k) lpn[k] = rawc[(slot1 + k) * 32];
 
         // exponent recurrence of step 0 of this block (it cannot run ahead across the renormalisation)
+        const bool last_lane = lane == 31;
+        const int src_lane = (lane + 31) & 31;
         int En;
-        float c_own, c_in, c_edge;
+        float c_own, c_in;
         {
             const int pbe = DIR == 0 ? pbe_prev : fe[0][0], ple = DIR == 0 ? ple_prev : fe[0][1];
             const int oE = E + pbe;
-            const int iE = __shfl_up_sync(0xffffffffu, DIR == 0 ? E + ple : E, 1) +
-                           (DIR == 0 ? in_bias : (blk == 0 ? kNoTerm : in_bias) + ple);
-            const int eE = DIR == 0 ? evE[0] : evE[0] + ple;
-            En = max(max(oE, iE), eE);
+            // (beta's seed val(-1) = 1 on lane j = 0 must not reach lane 1: no handed-on term at the very first step)
+            const int sE = last_lane ? evE[0] : (DIR == 0 ? E + ple : (blk == 0 ? kNoTerm : E));
+            const int iE = __shfl_sync(0xffffffffu, sE, src_lane) + (DIR == 0 ? 0 : ple);
+            En = max(oE, iE);
             c_own = pow2_neg(En - oE) * (DIR == 0 ? pbm_prev : fm[0][0]);
             c_in = pow2_neg(En - iE) * (DIR == 0 ? 1.f : fm[0][1]);
-            c_edge = pow2_neg(En - eE) * (DIR == 0 ? 1.f : fm[0][1]);
         }
         float shm = DIR == 0 ? m * plm_prev : m;
         const int ew = (blk * KB - G.lag) & (kTpEdge - 1);  // slot base of this warp's own boundary values
 #pragma unroll
         for (int k = 0; k < KB; ++k) {
-            const float in_m = __shfl_up_sync(0xffffffffu, shm, 1);  // mantissa chain: the long-latency hop first
-            const float own_term = kMulti ? fmaf(evm[k], c_edge, m * c_own) : m * c_own;
+            const float in_m = __shfl_sync(0xffffffffu, last_lane ? evm[k] : shm, src_lane);  // the long-latency hop first
+            const float own_term = m * c_own;
             const int Ek = En;
             const float ci = c_in;
             const float plm = fm[k][1];
@@ -959,13 +967,11 @@ __device__ __forceinline__ void tp_sweep(TpWarp& W, int2 (*edge)[8], const float
             if (k + 1 < KB) {  // exponent recurrence of step k+1, in the shadow of the shuffle above
                 const int pbe_n = fe[DIR == 0 ? k : k + 1][0], ple_n = fe[DIR == 0 ? k : k + 1][1];
                 const int oE = Ek + pbe_n;
-                const int iE = __shfl_up_sync(0xffffffffu, DIR == 0 ? Ek + ple_n : Ek, 1) +
-                               (DIR == 0 ? in_bias : in_bias + ple_n);
-                const int eE = DIR == 0 ? evE[k + 1] : evE[k + 1] + ple_n;
-                En = max(max(oE, iE), eE);
+                const int sE = last_lane ? evE[k + 1] : (DIR == 0 ? Ek + ple_n : Ek);
+                const int iE = __shfl_sync(0xffffffffu, sE, src_lane) + (DIR == 0 ? 0 : ple_n);
+                En = max(oE, iE);
                 c_own = pow2_neg(En - oE) * fm[DIR == 0 ? k : k + 1][0];
                 c_in = pow2_neg(En - iE) * (DIR == 0 ? 1.f : fm[k + 1][1]);
-                c_edge = pow2_neg(En - eE) * (DIR == 0 ? 1.f : fm[k + 1][1]);
             } else {
                 pbm_prev = fm[k][0], plm_prev = plm, pbe_prev = fe[k][0], ple_prev = ple;
             }
@@ -997,17 +1003,21 @@ __device__ __forceinline__ void tp_sweep(TpWarp& W, int2 (*edge)[8], const float
             }
         }
         // lane 31 has now passed rows row_st .. row_st + KB - 1
-        {
+        if (lane_on) {
             int ov[KB];
 #pragma unroll
             for (int k = 0; k < KB; ++k) ov[k] = outc[((row_st + k + lane) & (kTpOut - 1)) * 32];
+            if (row_st >= 0 && row_st + KB <= Tb) {  // (warp-uniform) whole block inside the utterance
 #pragma unroll
-            for (int k = 0; k < KB; ++k) {
-                if ((unsigned)(row_st + k) < G.Tb_eff) *pst = ov[k];
-                pst += G.stride;
+                for (int k = 0; k < KB; ++k) pst[k * G.stride] = ov[k];
+            } else {
+#pragma unroll
+                for (int k = 0; k < KB; ++k)
+                    if ((unsigned)(row_st + k) < (unsigned)Tb) pst[k * G.stride] = ov[k];
             }
-            row_st += KB;
         }
+        pst += KB * G.stride;
+        row_st += KB;
         slot0 = slot1;
         tau += KB;
     }
