@@ -868,7 +868,7 @@ def per_kernel(lib, st, mode, gemm, det, B, T, U1, V, H, cells, flush_buf, iters
             if pws_bytes:
                 pws = torch.empty(pws_bytes, dtype=torch.uint8, device=dev)
                 bench("proj_tc_kernel", lambda: _lib.check(lib.rnntb200_joint_cg_project(
-                    p(enc), p(dec), p(w), p(b), B * T, B * U1, He, dec.shape[-1], V, p(penc), p(pdec), p(pws),
+                    p(enc), p(dec), 0, p(w), p(b), B * T, B * U1, He, dec.shape[-1], V, p(penc), p(pdec), p(pws),
                     pws_bytes, stream)), 4 * (enc.numel() + dec.numel() + w.numel()) + io)
                 res["proj_tc_kernel"]["flops"] = 2.0 * V * (He * B * T + dec.shape[-1] * B * U1)
             else:
@@ -891,7 +891,7 @@ def per_kernel(lib, st, mode, gemm, det, B, T, U1, V, H, cells, flush_buf, iters
                 bws = torch.empty(bws_bytes, dtype=torch.uint8, device=dev)
                 d_enc, d_dec, d_w, d_b = (torch.empty_like(t) for t in (enc, dec, w, b))
                 bench("proj_tc_bwd_kernel", lambda: _lib.check(lib.rnntb200_joint_cg_project_bwd(
-                    p(enc), p(dec), p(w), p(d_penc), p(d_pdec), B * T, B * U1, He, dec.shape[-1], V, p(d_enc),
+                    p(enc), p(dec), 0, p(w), p(d_penc), p(d_pdec), B * T, B * U1, He, dec.shape[-1], V, p(d_enc),
                     p(d_dec), p(d_w), p(d_b), p(bws), bws_bytes, 0, stream)),
                     8 * (enc.numel() + dec.numel() + w.numel()) + io)
                 res["proj_tc_bwd_kernel"]["flops"] = 4.0 * V * (He * B * T + dec.shape[-1] * B * U1)

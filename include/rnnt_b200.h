@@ -125,11 +125,15 @@ RNNTB200_API int rnntb200_loss_dense_bwd(const void* logits, int dtype, const in
  * tcgen05 MMAs per product, fp32 accumulation):
  *   penc[r,:] = gelu_tanh(enc[r,:]) weight[:, :He]^T + bias,   pdec[r,:] = gelu_tanh(dec[r,:]) weight[:, He:]^T
  * enc [rows_enc, He], dec [rows_dec, Hd], weight [V, He+Hd] (the reference's fc.weight), bias [V].
+ * x_dtype (rnntb200_dtype_t) is the element type of enc / dec -- and of d_enc / d_dec in the backward: the
+ * AMP mode of the reference's shipped script (scripts/run_train.sh:32 --precision=16) hands the joint fp16
+ * activations; they are converted exactly on load and the gradients rounded to nearest on store, the
+ * arithmetic in between and every other tensor (weight, bias, penc, pdec, d_weight, d_bias) stay fp32.
  * rnntb200_joint_cg_project_workspace_bytes returns 0 when the shape is not supported (V > 80 or
  * He/Hd not multiples of 64): the caller then uses a library GEMM for this step. */
 RNNTB200_API size_t rnntb200_joint_cg_project_workspace_bytes(int V, int He, int Hd);
 
-RNNTB200_API int rnntb200_joint_cg_project(const float* enc, const float* dec, const float* weight,
+RNNTB200_API int rnntb200_joint_cg_project(const void* enc, const void* dec, int x_dtype, const float* weight,
                               const float* bias, int rows_enc, int rows_dec, int He, int Hd, int V,
                               float* penc, float* pdec, void* workspace, size_t workspace_bytes,
                               void* stream);
@@ -141,9 +145,9 @@ RNNTB200_API int rnntb200_joint_cg_project(const float* enc, const float* dec, c
  * so the bf16 split of the weight is not redone. */
 RNNTB200_API size_t rnntb200_joint_cg_project_bwd_workspace_bytes(int V, int He, int Hd);
 
-RNNTB200_API int rnntb200_joint_cg_project_bwd(const float* enc, const float* dec, const float* weight,
+RNNTB200_API int rnntb200_joint_cg_project_bwd(const void* enc, const void* dec, int x_dtype, const float* weight,
                                   const float* d_penc, const float* d_pdec, int rows_enc, int rows_dec,
-                                  int He, int Hd, int V, float* d_enc, float* d_dec, float* d_weight,
+                                  int He, int Hd, int V, void* d_enc, void* d_dec, float* d_weight,
                                   float* d_bias, void* workspace, size_t workspace_bytes,
                                   int workspace_holds_split, void* stream);
 

@@ -77,15 +77,15 @@ RNNTB200_API size_t rnntb200_joint_cg_project_workspace_bytes(int V, int He, int
     return proj_tc_supported(V, He, Hd) ? proj_tc_workspace_bytes(V, He, Hd) : 0;
 }
 
-RNNTB200_API int rnntb200_joint_cg_project(const float* enc, const float* dec, const float* weight,
+RNNTB200_API int rnntb200_joint_cg_project(const void* enc, const void* dec, int x_dtype, const float* weight,
                               const float* bias, int rows_enc, int rows_dec, int He, int Hd, int V,
                               float* penc, float* pdec, void* workspace, size_t workspace_bytes,
                               void* stream) {
-    if (rows_enc < 0 || rows_dec < 0 || V <= 0 || He <= 0 || Hd <= 0) return RNNTB200_STATUS_INVALID_VALUE;
+    if (rows_enc < 0 || rows_dec < 0 || V <= 0 || He <= 0 || Hd <= 0 || bad_dtype(x_dtype)) return RNNTB200_STATUS_INVALID_VALUE;
     if (!proj_tc_supported(V, He, Hd)) return RNNTB200_STATUS_INVALID_VALUE;
     if ((rows_enc > 0 && (!enc || !penc)) || (rows_dec > 0 && (!dec || !pdec)) || !weight || !bias)
         return RNNTB200_STATUS_INVALID_VALUE;
-    return launch_proj_tc(enc, dec, weight, bias, rows_enc, rows_dec, He, Hd, V, penc, pdec, workspace,
+    return launch_proj_tc(enc, dec, x_dtype, weight, bias, rows_enc, rows_dec, He, Hd, V, penc, pdec, workspace,
                           workspace_bytes, (cudaStream_t)stream);
 }
 
@@ -93,17 +93,17 @@ RNNTB200_API size_t rnntb200_joint_cg_project_bwd_workspace_bytes(int V, int He,
     return proj_tc_bwd_supported(V, He, Hd) ? proj_tc_bwd_workspace_bytes(V, He, Hd) : 0;
 }
 
-RNNTB200_API int rnntb200_joint_cg_project_bwd(const float* enc, const float* dec, const float* weight,
+RNNTB200_API int rnntb200_joint_cg_project_bwd(const void* enc, const void* dec, int x_dtype, const float* weight,
                                   const float* d_penc, const float* d_pdec, int rows_enc, int rows_dec,
-                                  int He, int Hd, int V, float* d_enc, float* d_dec, float* d_weight,
+                                  int He, int Hd, int V, void* d_enc, void* d_dec, float* d_weight,
                                   float* d_bias, void* workspace, size_t workspace_bytes,
                                   int workspace_holds_split, void* stream) {
-    if (rows_enc < 0 || rows_dec < 0 || V <= 0 || He <= 0 || Hd <= 0) return RNNTB200_STATUS_INVALID_VALUE;
+    if (rows_enc < 0 || rows_dec < 0 || V <= 0 || He <= 0 || Hd <= 0 || bad_dtype(x_dtype)) return RNNTB200_STATUS_INVALID_VALUE;
     if (!proj_tc_bwd_supported(V, He, Hd)) return RNNTB200_STATUS_INVALID_VALUE;
     if ((rows_enc > 0 && (!enc || !d_penc || !d_enc)) || (rows_dec > 0 && (!dec || !d_pdec || !d_dec)) ||
         !weight || !d_weight || !d_bias)
         return RNNTB200_STATUS_INVALID_VALUE;
-    return launch_proj_tc_bwd(enc, dec, weight, d_penc, d_pdec, rows_enc, rows_dec, He, Hd, V, d_enc, d_dec,
+    return launch_proj_tc_bwd(enc, dec, x_dtype, weight, d_penc, d_pdec, rows_enc, rows_dec, He, Hd, V, d_enc, d_dec,
                               d_weight, d_bias, workspace, workspace_bytes, workspace_holds_split,
                               (cudaStream_t)stream);
 }

@@ -89,6 +89,37 @@ __device__ __forceinline__ int label_at(const int32_t* labels, int b, int U1, in
     return min(max(__ldg(labels + (size_t)b * (U1 - 1) + u), 0), V - 1);
 }
 
+// Activations (enc / dec and their gradients) may be fp32, fp16 or bf16 (rnntb200_dtype_t): the projection
+// kernels read / write them through these -- four consecutive elements at element offset e (e % 4 == 0, rows
+// 16-byte aligned for fp32 / 8-byte for the half types), converted exactly on the way in and rounded to
+// nearest on the way out.  The arithmetic in between is the same fp32-class arithmetic for every dtype.
+__device__ __forceinline__ float4 ldx4(const void* x, int dt, size_t e) {
+    if (dt == RNNTB200_F32) return __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(x) + e));
+    const uint2 r = __ldg(reinterpret_cast<const uint2*>(static_cast<const uint16_t*>(x) + e));
+    if (dt == RNNTB200_F16) {
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x));
+        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+        return make_float4(a.x, a.y, b.x, b.y);
+    }
+    return make_float4(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xffff0000u),
+                       __uint_as_float(r.y << 16), __uint_as_float(r.y & 0xffff0000u));
+}
+__device__ __forceinline__ void stx4(void* x, int dt, size_t e, float4 v) {
+    if (dt == RNNTB200_F32) {
+        *reinterpret_cast<float4*>(static_cast<float*>(x) + e) = v;
+        return;
+    }
+    uint2 r;
+    if (dt == RNNTB200_F16) {
+        const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+        r.x = *reinterpret_cast<const uint32_t*>(&a), r.y = *reinterpret_cast<const uint32_t*>(&b);
+    } else {
+        const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+        r.x = *reinterpret_cast<const uint32_t*>(&a), r.y = *reinterpret_cast<const uint32_t*>(&b);
+    }
+    *reinterpret_cast<uint2*>(static_cast<uint16_t*>(x) + e) = r;
+}
+
 inline int status_from_cuda(cudaError_t e) {
     if (e == cudaSuccess) return RNNTB200_STATUS_SUCCESS;
     if (e == cudaErrorInvalidValue || e == cudaErrorInvalidConfiguration) return RNNTB200_STATUS_INVALID_VALUE;
@@ -149,11 +180,11 @@ bool proj_tc_supported(int V, int He, int Hd);
 size_t proj_tc_workspace_bytes(int V, int He, int Hd);
 bool proj_tc_bwd_supported(int V, int He, int Hd);
 size_t proj_tc_bwd_workspace_bytes(int V, int He, int Hd);
-int launch_proj_tc_bwd(const float* enc, const float* dec, const float* weight, const float* d_penc,
-                       const float* d_pdec, int rows_enc, int rows_dec, int He, int Hd, int V, float* d_enc,
-                       float* d_dec, float* d_weight, float* d_bias, void* workspace, size_t workspace_bytes,
+int launch_proj_tc_bwd(const void* enc, const void* dec, int x_dtype, const float* weight, const float* d_penc,
+                       const float* d_pdec, int rows_enc, int rows_dec, int He, int Hd, int V, void* d_enc,
+                       void* d_dec, float* d_weight, float* d_bias, void* workspace, size_t workspace_bytes,
                        int workspace_holds_split, cudaStream_t stream);
-int launch_proj_tc(const float* enc, const float* dec, const float* weight, const float* bias, int rows_enc,
+int launch_proj_tc(const void* enc, const void* dec, int x_dtype, const float* weight, const float* bias, int rows_enc,
                    int rows_dec, int He, int Hd, int V, float* penc, float* pdec, void* workspace,
                    size_t workspace_bytes, cudaStream_t stream);
 int launch_at_grad(const float* enc, const float* dec, const float* weight, const float* bias, int gemm,

@@ -30,10 +30,10 @@ constexpr int kAHalf = 128 * kKB * 2;  // 16 KiB: one K block of A_hi (A_lo foll
 constexpr int kTmemCols = 128;
 
 struct Problem {  // one projection
-    const float* x;     // [rows, K]
+    const void* x;      // [rows, K], element type xdt (rnntb200_dtype_t)
     const float* bias;  // [V] or null
     float* out;         // [rows, V]
-    int rows, K, tiles;
+    int rows, K, tiles, xdt;
 };
 
 struct SmemP {
@@ -133,7 +133,7 @@ proj_tc_kernel(const __grid_constant__ CUtensorMap w0_hi, const __grid_constant_
         // quarter warp still stores 8 rows x 16 B = one 128-byte core-matrix column, conflict-free
         const int r = warp * 8 + (lane & 7), kc0 = lane >> 3;
         const int row = min(row0 + r, P.rows - 1);  // rows past the end are computed but never stored
-        const float4* xrow = reinterpret_cast<const float4*>(P.x + (size_t)row * P.K);
+        const size_t xrow = (size_t)row * P.K;  // element offset of this thread's row
         // three register buffers take turns (K loop unrolled by three, compile-time roles, no copy
         // ever waits on a load): block kb+2 is requested while block kb is computed
         float4 xb0[4], xb1[4], xb2[4];
@@ -141,8 +141,8 @@ proj_tc_kernel(const __grid_constant__ CUtensorMap w0_hi, const __grid_constant_
             if (kb < n_kb) {
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
-                    dst[2 * i] = __ldg(xrow + kb * (kKB / 4) + (kc0 + 4 * i) * 2);
-                    dst[2 * i + 1] = __ldg(xrow + kb * (kKB / 4) + (kc0 + 4 * i) * 2 + 1);
+                    dst[2 * i] = ldx4(P.x, P.xdt, xrow + kb * kKB + (kc0 + 4 * i) * 8);
+                    dst[2 * i + 1] = ldx4(P.x, P.xdt, xrow + kb * kKB + (kc0 + 4 * i) * 8 + 4);
                 }
             }
         };
@@ -317,7 +317,7 @@ int proj_tc_prepare(const float* weight, int V, int He, int Hd, int NB, void* wo
     return launch_status();
 }
 
-int launch_proj_tc(const float* enc, const float* dec, const float* weight, const float* bias, int rows_enc,
+int launch_proj_tc(const void* enc, const void* dec, int x_dtype, const float* weight, const float* bias, int rows_enc,
                    int rows_dec, int He, int Hd, int V, float* penc, float* pdec, void* workspace,
                    size_t workspace_bytes, cudaStream_t stream) {
     if (!proj_tc_supported(V, He, Hd)) return RNNTB200_STATUS_INVALID_VALUE;
@@ -326,8 +326,8 @@ int launch_proj_tc(const float* enc, const float* dec, const float* weight, cons
     int st = proj_tc_prepare(weight, V, He, Hd, NB, workspace, workspace_bytes, false, m, stream);
     if (st != RNNTB200_STATUS_SUCCESS) return st;
     if (rows_enc + rows_dec == 0) return RNNTB200_STATUS_SUCCESS;
-    Problem p0{enc, bias, penc, rows_enc, He, (rows_enc + 127) / 128};
-    Problem p1{dec, nullptr, pdec, rows_dec, Hd, (rows_dec + 127) / 128};
+    Problem p0{enc, bias, penc, rows_enc, He, (rows_enc + 127) / 128, x_dtype};
+    Problem p1{dec, nullptr, pdec, rows_dec, Hd, (rows_dec + 127) / 128, x_dtype};
     const SmemP L = smem_layout_p(NB);
     cudaError_t e = cudaFuncSetAttribute(proj_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
     if (e != cudaSuccess) return status_from_cuda(e);

@@ -28,10 +28,10 @@ constexpr int kColDX = 320, kColDB = 448;
 constexpr int kTmemCols = 512;
 
 struct ProblemB {
-    const float* x;   // [rows, K]
+    const void* x;    // [rows, K], element type xdt (rnntb200_dtype_t)
     const float* dp;  // [rows, V]
-    float* dx;        // [rows, K]
-    int rows, K, tiles, w_col0, with_bias;
+    void* dx;         // [rows, K], same element type
+    int rows, K, tiles, w_col0, with_bias, xdt;
 };
 
 struct SmemPB {
@@ -167,8 +167,8 @@ proj_tc_bwd_kernel(const __grid_constant__ CUtensorMap w0_hi, const __grid_const
         if (lane == 0) mbar_arrive(dp_full);
         // (2) gelu(x) in 128-column blocks -> (hi, lo), [h-group][row][8 h]
         const bool row_ok0 = row0 + r8 < P.rows, row_ok1 = row0 + r8 + 8 < P.rows;
-        const float4* xrow0 = reinterpret_cast<const float4*>(P.x + (size_t)min(row0 + r8, P.rows - 1) * P.K);
-        const float4* xrow1 = reinterpret_cast<const float4*>(P.x + (size_t)min(row0 + r8 + 8, P.rows - 1) * P.K);
+        const size_t xrow0 = (size_t)min(row0 + r8, P.rows - 1) * P.K;  // element offsets of this thread's two rows
+        const size_t xrow1 = (size_t)min(row0 + r8 + 8, P.rows - 1) * P.K;
         // each 128-column block is produced as two 64-column halves from two register buffers that
         // alternate: the loads of the next half are in flight while the current one is computed.
         // Item i of a half: row r8 + 8 (i & 1), h-group 8 hf + c4 + 4 (i >> 1).
@@ -177,10 +177,10 @@ proj_tc_bwd_kernel(const __grid_constant__ CUtensorMap w0_hi, const __grid_const
             if (blk < n_blk) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const float4* xr = (i & 1) ? xrow1 : xrow0;
+                    const size_t xr = (i & 1) ? xrow1 : xrow0;
                     const int kc = 8 * hf + c4 + 4 * (i >> 1);
-                    dst[2 * i] = __ldg(xr + blk * 32 + kc * 2);
-                    dst[2 * i + 1] = __ldg(xr + blk * 32 + kc * 2 + 1);
+                    dst[2 * i] = ldx4(P.x, P.xdt, xr + blk * 128 + kc * 8);
+                    dst[2 * i + 1] = ldx4(P.x, P.xdt, xr + blk * 128 + kc * 8 + 4);
                 }
             }
         };
@@ -291,7 +291,7 @@ proj_tc_bwd_kernel(const __grid_constant__ CUtensorMap w0_hi, const __grid_const
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int grow = min(row0 + q * 32 + lr + 8 * j, P.rows - 1);
-                    xg[pc][j] = __ldg(reinterpret_cast<const float4*>(P.x + (size_t)grow * P.K + kb * kKB + pc * 16) + lc);
+                    xg[pc][j] = ldx4(P.x, P.xdt, (size_t)grow * P.K + kb * kKB + pc * 16 + lc * 4);
                 }
             mbar_wait(dx_full(buf), (kb >> 1) & 1);
             tc_fence_after();
@@ -316,8 +316,8 @@ proj_tc_bwd_kernel(const __grid_constant__ CUtensorMap w0_hi, const __grid_const
                 for (int j = 0; j < 4; ++j) {
                     const int grow = row0 + q * 32 + lr + 8 * j;
                     if (grow < P.rows)
-                        reinterpret_cast<float4*>(P.dx + (size_t)grow * P.K + kb * kKB + pc * 16)[lc] =
-                            *reinterpret_cast<const float4*>(stg + sw(lr + 8 * j, lc));
+                        stx4(P.dx, P.xdt, (size_t)grow * P.K + kb * kKB + pc * 16 + lc * 4,
+                             *reinterpret_cast<const float4*>(stg + sw(lr + 8 * j, lc)));
                 }
                 __syncwarp();
             }
@@ -364,9 +364,9 @@ bool proj_tc_bwd_supported(int V, int He, int Hd) {
 
 size_t proj_tc_bwd_workspace_bytes(int V, int He, int Hd) { return proj_tc_workspace_bytes(V, He, Hd); }
 
-int launch_proj_tc_bwd(const float* enc, const float* dec, const float* weight, const float* d_penc,
-                       const float* d_pdec, int rows_enc, int rows_dec, int He, int Hd, int V, float* d_enc,
-                       float* d_dec, float* d_weight, float* d_bias, void* workspace, size_t workspace_bytes,
+int launch_proj_tc_bwd(const void* enc, const void* dec, int x_dtype, const float* weight, const float* d_penc,
+                       const float* d_pdec, int rows_enc, int rows_dec, int He, int Hd, int V, void* d_enc,
+                       void* d_dec, float* d_weight, float* d_bias, void* workspace, size_t workspace_bytes,
                        int workspace_holds_split, cudaStream_t stream) {
     if (!proj_tc_bwd_supported(V, He, Hd)) return RNNTB200_STATUS_INVALID_VALUE;
     const int ldw = He + Hd;
@@ -378,8 +378,8 @@ int launch_proj_tc_bwd(const float* enc, const float* dec, const float* weight, 
     int st = proj_tc_prepare(weight, V, He, Hd, NB, workspace, workspace_bytes, workspace_holds_split != 0, m, stream);
     if (st != RNNTB200_STATUS_SUCCESS) return st;
     if (rows_enc + rows_dec == 0) return RNNTB200_STATUS_SUCCESS;
-    ProblemB p0{enc, d_penc, d_enc, rows_enc, He, (rows_enc + 127) / 128, 0, 1};
-    ProblemB p1{dec, d_pdec, d_dec, rows_dec, Hd, (rows_dec + 127) / 128, He, 0};
+    ProblemB p0{enc, d_penc, d_enc, rows_enc, He, (rows_enc + 127) / 128, 0, 1, x_dtype};
+    ProblemB p1{dec, d_pdec, d_dec, rows_dec, Hd, (rows_dec + 127) / 128, He, 0, x_dtype};
     const SmemPB L = smem_layout_pb(NB);
     cudaError_t e = cudaFuncSetAttribute(proj_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
     if (e != cudaSuccess) return status_from_cuda(e);

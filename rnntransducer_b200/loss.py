@@ -79,6 +79,7 @@ class _DenseRNNT(torch.autograd.Function):
     """costs[B] = -log P(y|x) from dense logits (K5 front-end + alpha/beta sweeps; K4 gradient)."""
 
     @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
     def forward(ctx, acts, labels, act_lens, label_lens, blank):
         if acts.dtype not in _DTYPES:
             raise RuntimeError("acts must be float32, float16 or bfloat16")
@@ -103,6 +104,7 @@ class _DenseRNNT(torch.autograd.Function):
         return costs
 
     @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, grad_costs):
         acts, labels, act_lens, label_lens, lse, alpha, beta = ctx.saved_tensors
         B, T, U1, V = acts.shape
@@ -121,6 +123,7 @@ class _ConcatGeluRNNT(torch.autograd.Function):
     """costs[B] from the factorised reference joint: logits(t,u) = penc[t] + pdec[u]."""
 
     @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
     def forward(ctx, penc, pdec, labels, act_lens, label_lens, blank, deterministic):
         B, T, V = penc.shape
         U1 = pdec.shape[1]
@@ -148,6 +151,7 @@ class _ConcatGeluRNNT(torch.autograd.Function):
         return costs
 
     @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, grad_costs):
         penc, pdec, labels, act_lens, label_lens, lse, alpha, beta, factors = ctx.saved_tensors
         B, T, V = penc.shape
@@ -173,28 +177,33 @@ class _ConcatGeluRNNT(torch.autograd.Function):
 class _CgProject(torch.autograd.Function):
     """penc = gelu_tanh(enc) W[:, :He]^T + b,  pdec = gelu_tanh(dec) W[:, He:]^T on the tensor cores at
     fp32 accuracy (rnntb200_joint_cg_project); backward on the tensor cores with the same bf16 hi/lo
-    split arithmetic (rnntb200_joint_cg_project_bwd)."""
+    split arithmetic (rnntb200_joint_cg_project_bwd).  enc / dec may be fp32, fp16 or bf16 (the AMP mode:
+    the kernels convert on load, d_enc / d_dec come back in the same dtype); weight, bias, penc, pdec and
+    the parameter gradients are fp32."""
 
     @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
     def forward(ctx, enc, dec, weight, bias):
         B, T, He = enc.shape
         U1, Hd = dec.shape[1], dec.shape[2]
         V = weight.shape[0]
         lib = _lib.load()
         ws_bytes = lib.rnntb200_joint_cg_project_workspace_bytes(V, He, Hd)
-        enc, dec = enc.contiguous(), dec.contiguous()
-        weight, bias = weight.contiguous(), bias.contiguous()
+        enc = enc.contiguous()
+        dec = dec.contiguous().to(enc.dtype)
+        weight, bias = weight.contiguous().float(), bias.contiguous().float()
         penc = torch.empty(B, T, V, device=enc.device, dtype=torch.float32)
         pdec = torch.empty(B, U1, V, device=enc.device, dtype=torch.float32)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=enc.device)
         with torch.cuda.device(enc.device):
             _lib.check(lib.rnntb200_joint_cg_project(
-                _ptr(enc), _ptr(dec), _ptr(weight), _ptr(bias), B * T, B * U1, He, Hd, V, _ptr(penc),
-                _ptr(pdec), _ptr(ws), ws_bytes, _stream()), "rnntb200_joint_cg_project")
+                _ptr(enc), _ptr(dec), _DTYPES[enc.dtype], _ptr(weight), _ptr(bias), B * T, B * U1, He, Hd, V,
+                _ptr(penc), _ptr(pdec), _ptr(ws), ws_bytes, _stream()), "rnntb200_joint_cg_project")
         ctx.save_for_backward(enc, dec, weight, ws)  # ws: the weight's bf16 hi/lo split, reused by backward
         return penc, pdec
 
     @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, d_penc, d_pdec):
         enc, dec, weight, ws_fwd = ctx.saved_tensors
         He, Hd = enc.shape[-1], dec.shape[-1]
@@ -209,16 +218,18 @@ class _CgProject(torch.autograd.Function):
             ws = ws_fwd if reuse else torch.empty(ws_bytes, dtype=torch.uint8, device=enc.device)
             with torch.cuda.device(enc.device):
                 _lib.check(lib.rnntb200_joint_cg_project_bwd(
-                    _ptr(enc), _ptr(dec), _ptr(weight), _ptr(d_penc), _ptr(d_pdec), enc.shape[0] * enc.shape[1],
-                    dec.shape[0] * dec.shape[1], He, Hd, V, _ptr(d_enc), _ptr(d_dec), _ptr(d_w), _ptr(d_b),
-                    _ptr(ws), ws_bytes, int(reuse), _stream()), "rnntb200_joint_cg_project_bwd")
+                    _ptr(enc), _ptr(dec), _DTYPES[enc.dtype], _ptr(weight), _ptr(d_penc), _ptr(d_pdec),
+                    enc.shape[0] * enc.shape[1], dec.shape[0] * dec.shape[1], He, Hd, V, _ptr(d_enc), _ptr(d_dec),
+                    _ptr(d_w), _ptr(d_b), _ptr(ws), ws_bytes, int(reuse), _stream()), "rnntb200_joint_cg_project_bwd")
             return d_enc, d_dec, d_w, d_b
+        # widths the tensor-core backward does not tile (not multiples of 128): library GEMMs for this step
         gelu = lambda x: torch.nn.functional.gelu(x, approximate="tanh")
-        dpe, dpd = d_penc.reshape(-1, V), d_pdec.reshape(-1, V)
-        d_w = torch.cat((dpe.t() @ gelu(enc).reshape(-1, He), dpd.t() @ gelu(dec).reshape(-1, dec.shape[-1])), 1)
+        e32, d32 = enc.float(), dec.float()
+        dpe, dpd = d_penc.reshape(-1, V).float(), d_pdec.reshape(-1, V).float()
+        d_w = torch.cat((dpe.t() @ gelu(e32).reshape(-1, He), dpd.t() @ gelu(d32).reshape(-1, Hd)), 1)
         d_b = dpe.sum(0)
-        d_enc = torch.ops.aten.gelu_backward(d_penc @ weight[:, :He], enc, approximate="tanh")
-        d_dec = torch.ops.aten.gelu_backward(d_pdec @ weight[:, He:], dec, approximate="tanh")
+        d_enc = torch.ops.aten.gelu_backward(d_penc.float() @ weight[:, :He], e32, approximate="tanh").to(enc.dtype)
+        d_dec = torch.ops.aten.gelu_backward(d_pdec.float() @ weight[:, He:], d32, approximate="tanh").to(dec.dtype)
         return d_enc, d_dec, d_w, d_b
 
 
@@ -226,7 +237,7 @@ def project_concat_gelu(enc, dec, weight, bias):
     """(P_enc, P_dec) of the factorised reference joint.  Tensor-core kernel when the shape is
     supported (V <= 80, widths multiples of 64), otherwise library GEMMs."""
     He, Hd, V = enc.size(-1), dec.size(-1), weight.shape[0]
-    if enc.is_cuda and enc.dtype == torch.float32 and weight.dtype == torch.float32 and \
+    if enc.is_cuda and enc.dtype in _DTYPES and \
             _lib.load().rnntb200_joint_cg_project_workspace_bytes(V, He, Hd) > 0:
         return _CgProject.apply(enc, dec, weight, bias)
     F = torch.nn.functional

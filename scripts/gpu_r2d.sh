@@ -2,7 +2,7 @@
 # Round-2 visit D: tp sweep after the instruction diet (edge through the rotate shuffle, fast-path loader / stores),
 # the chain-warps-last experiment on the warp-specialised sweep, one ncu capture of the tp cluster sweep at cfg 3.
 TAG=${1:-r2d}; OUT=gpurun_out; mkdir -p $OUT
-T="tests/test_gpu_loss.py tests/test_gpu_joint_cg.py tests/test_abi.py tests/test_gpu_comm.py"
+T="tests/test_gpu_loss.py tests/test_gpu_joint_cg.py tests/test_abi.py tests/test_gpu_comm.py tests/test_gpu_amp.py"
 timeout 900 python -m pytest $T -m gpu -q --timeout 600 -x > $OUT/${TAG}_pytest_tp.log 2>&1; echo "pytest tp exit $?"; tail -n 4 $OUT/${TAG}_pytest_tp.log
 RNNTB200_SWEEP=ws RNNTB200_WS_CHAIN_LAST=1 timeout 900 python -m pytest tests/test_gpu_loss.py -m gpu -q --timeout 600 -x > $OUT/${TAG}_pytest_wslast.log 2>&1; echo "pytest ws chain-last exit $?"; tail -n 3 $OUT/${TAG}_pytest_wslast.log
 RNNTB200_SWEEP=tp timeout 600 python -m pytest tests/test_gpu_loss.py -m gpu -q --timeout 600 -x -k "boundaries or long_lattice" > $OUT/${TAG}_pytest_tpcl.log 2>&1; echo "pytest tp cluster exit $?"; tail -n 3 $OUT/${TAG}_pytest_tpcl.log
