@@ -697,8 +697,7 @@ lattice_sweep_ws_kernel(const float2* __restrict__ lp2, const int32_t* __restric
     int n_blocks = (Tb + Ub + max_lag + KB - 1) / KB;
     if (kCluster) n_blocks = min(n_blocks, xedge_slots / KB);  // (the host sized xedge for the longest utterance)
     int w = warp % nw, role = warp / nw;
-    if (spread == 2) role = 4 - role;  // experiment: chain warps get the HIGHEST warp ids (the issue arbiter favours them)
-    if (spread == 1) {
+    if (spread) {
         w = warp & 1;
         role = warp < 2 ? 0 : (warp & 2) ? 1 + (warp >> 2) : 5;  // 2,3 loaders; 6,7 / 10,11 converters; 14,15 consumers
     }
@@ -733,9 +732,8 @@ int launch_ws(const float2* lp2, const int32_t* act_lens, const int32_t* label_l
     cudaError_t e = cudaFuncSetAttribute(lattice_sweep_ws_kernel<kMulti, KB, RW, false>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return status_from_cuda(e);
-    static const int chain_last = getenv("RNNTB200_WS_CHAIN_LAST") ? 2 : 0;
     lattice_sweep_ws_kernel<kMulti, KB, RW, false><<<dim3(B, 2), warps * 160, smem, stream>>>(
-        lp2, act_lens, label_lens, T, U1, alpha, beta, costs, ll_alpha, 0, warps, chain_last);
+        lp2, act_lens, label_lens, T, U1, alpha, beta, costs, ll_alpha, 0, warps, 0);
     return launch_status();
 }
 
@@ -821,12 +819,13 @@ __device__ __forceinline__ void tp_sweep(TpWarp& W, int2 (*edge)[8], const float
     const int n_on = (Ub + 32) / 32;  // warps with cells
     const int max_lag = kMulti ? (n_on - 1) * KB + ((n_on - 1) / nw) * (kTpBandSkew - KB) : 0;
     const int n_blocks = (Tb + Ub + max_lag + KB - 1) / KB;
-    const int edge_col = (kMulti && w > 0) ? w - 1 : 4;
     const bool from_band = kCluster && w == 0 && X.band > 0;
-    const bool to_band = kCluster && w == nw - 1 && X.band + 1 < X.n_bands && lane == 31;
+    const int edge_col = from_band ? 5 : (kMulti && w > 0) ? w - 1 : 4;  // 5: parked band-boundary values, 4: "zero"
+    const bool to_band = kCluster && w == nw - 1 && X.band + 1 < X.n_bands;  // this warp's lane 31 feeds the next band
     uint32_t r_xedge = 0;
     if (to_band)
         asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r_xedge) : "r"(tc::smem_u32(X.xedge)), "r"(X.band + 1));
+    const int in_bias = lane == 0 ? kNoTerm : 0;
     // FIFO slot of (row r, lane l) = (r + l) mod depth: lane l meets row r at step r + base + l, so the slot
     // index is the STEP index (minus base) -- uniform across the lanes and, base being a multiple of KB,
     // the KB slots of a block are consecutive: the chain side addresses both FIFOs with one register and
@@ -847,17 +846,10 @@ __device__ __forceinline__ void tp_sweep(TpWarp& W, int2 (*edge)[8], const float
     const float2* src0 = lp2 + G.first;
     auto load_block = [&]() {
         if (lane_on) {
-            if (r_ld >= 0 && r_ld + KB <= Tb) {  // (warp-uniform) every row of the block exists: no clamping
-                const float2* p = src0 + r_ld * G.stride;
 #pragma unroll
-                for (int k = 0; k < KB; ++k, p += G.stride)
-                    cp_async_8(rawc + ((r_ld + k + lane) & (kTpRaw - 1)) * 32, p);
-            } else {
-#pragma unroll
-                for (int k = 0; k < KB; ++k) {
-                    const int rc = min(max(r_ld + k, 0), Tb - 1);
-                    cp_async_8(rawc + ((r_ld + k + lane) & (kTpRaw - 1)) * 32, src0 + rc * G.stride);
-                }
+            for (int k = 0; k < KB; ++k) {
+                const int rc = min(max(r_ld + k, 0), Tb - 1);
+                cp_async_8(rawc + ((r_ld + k + lane) & (kTpRaw - 1)) * 32, src0 + rc * G.stride);
             }
         }
         r_ld += KB;
@@ -883,6 +875,7 @@ __device__ __forceinline__ void tp_sweep(TpWarp& W, int2 (*edge)[8], const float
     int E = G.j == 0 ? 0 : kZeroExp;
     float pbm_prev = 1.f, plm_prev = 1.f;
     int pbe_prev = 0, ple_prev = DIR == 0 ? kNoTerm : 0;
+    const int edge_bias = lane == 0 ? 0 : kNoTerm;
     int tau = G.tau0;                 // progress at the first step of the current block
     int row_st = -G.base - 31;        // next row to be stored (complete once lane 31 has passed it)
     int32_t* pst = out + G.first + (long long)row_st * G.stride;
@@ -894,24 +887,23 @@ __device__ __forceinline__ void tp_sweep(TpWarp& W, int2 (*edge)[8], const float
     for (int blk = 0; blk < n_blocks; ++blk) {
         if (kMulti) __syncthreads();  // the previous warp has finished the block this one reads boundary values of
         load_block();                 // rows of block blk + kTpAhead + 1
-        // boundary values of this block (a broadcast load; only lane 31 uses them): the hand-off is a ROTATE
-        // by one lane in which lane 31 sends, instead of its own share, the value the previous warp left for
-        // this warp's lane 0 -- no third term, no lane-0 special case in the recursion.  Reader slots are
-        // block-aligned: the writer stores its local step p at slot p + 1, the reader of local step q wants
-        // p = q - 1, i.e. slot q = er + k.
+        // boundary values of this block: every lane reads them (a broadcast), lanes other than 0 push the term
+        // out of reach with an exponent bias.  Reader slots are block-aligned: the writer stores its local step
+        // p at slot p + 1, the reader of local step q wants p = q - 1, i.e. slot q = er + k.
         float evm[KB];
         int evE[KB];
         if (kMulti) {
             const int er = (blk * KB - G.lag) & (kTpEdge - 1);
-#pragma unroll
-            for (int k = 0; k < KB; ++k) {
-                int2 ev = edge[er + k][edge_col];
-                if (kCluster && from_band) {
-                    // The slot IS the flag: every slot is written exactly once, by one 8-byte remote store of
-                    // the previous band's lane 31; until then both words hold kTpNoValue.  No release /
-                    // acquire pair, no progress counter: the sender never waits for anything.
-                    const int q = blk * KB + k - G.lag - 1;
-                    ev = make_int2(0x3f800000, kZeroExp);
+            if (kCluster && from_band) {
+                // The value crossing a BAND boundary sits in this CTA's xedge array, one slot per step of the
+                // sweep, and the slot IS the flag: it is written exactly once, by one 8-byte remote store of
+                // the previous band's lane 31; until then both words hold kTpNoValue.  No release / acquire
+                // pair, no progress counter: the sender never waits for anything.  Lanes 0..KB-1 poll the
+                // block's KB slots in parallel and park them in this warp's private column of the edge ring,
+                // from where the common path below picks them up.
+                if (lane < KB) {
+                    const int q = blk * KB + lane - G.lag - 1;
+                    int2 ev = make_int2(0x3f800000, kZeroExp);
                     if (q >= 0) {
                         const volatile int2* slot = X.xedge + q;
                         long long t0 = 0;
@@ -925,13 +917,19 @@ __device__ __forceinline__ void tp_sweep(TpWarp& W, int2 (*edge)[8], const float
                             }
                         }
                     }
+                    edge[er + lane][edge_col] = ev;
                 }
+                __syncwarp();
+            }
+#pragma unroll
+            for (int k = 0; k < KB; ++k) {
+                const int2 ev = edge[er + k][edge_col];
                 evm[k] = __int_as_float(ev.x);
-                evE[k] = ev.y;
+                evE[k] = ev.y + edge_bias;
             }
         } else {
 #pragma unroll
-            for (int k = 0; k < KB; ++k) evm[k] = 1.f, evE[k] = kZeroExp;
+            for (int k = 0; k < KB; ++k) evm[k] = 1.f, evE[k] = kNoTerm;
         }
         cp_async_wait<kTpAhead>();  // rows of blocks <= blk + 1 have landed (this lane's own copies)
         const int slot1 = (slot0 + KB) & (kTpRaw - 1);
@@ -940,26 +938,25 @@ __device__ __forceinline__ void tp_sweep(TpWarp& W, int2 (*edge)[8], const float
         for (int k = 0; k < KB; ++k) lpn[k] = rawc[(slot1 + k) * 32];
 
         // exponent recurrence of step 0 of this block (it cannot run ahead across the renormalisation)
-        const bool last_lane = lane == 31;
-        const int src_lane = (lane + 31) & 31;
         int En;
-        float c_own, c_in;
+        float c_own, c_in, c_edge;
         {
             const int pbe = DIR == 0 ? pbe_prev : fe[0][0], ple = DIR == 0 ? ple_prev : fe[0][1];
             const int oE = E + pbe;
-            // (beta's seed val(-1) = 1 on lane j = 0 must not reach lane 1: no handed-on term at the very first step)
-            const int sE = last_lane ? evE[0] : (DIR == 0 ? E + ple : (blk == 0 ? kNoTerm : E));
-            const int iE = __shfl_sync(0xffffffffu, sE, src_lane) + (DIR == 0 ? 0 : ple);
-            En = max(oE, iE);
+            const int iE = __shfl_up_sync(0xffffffffu, DIR == 0 ? E + ple : E, 1) +
+                           (DIR == 0 ? in_bias : (blk == 0 ? kNoTerm : in_bias) + ple);
+            const int eE = DIR == 0 ? evE[0] : evE[0] + ple;
+            En = max(max(oE, iE), eE);
             c_own = pow2_neg(En - oE) * (DIR == 0 ? pbm_prev : fm[0][0]);
             c_in = pow2_neg(En - iE) * (DIR == 0 ? 1.f : fm[0][1]);
+            c_edge = pow2_neg(En - eE) * (DIR == 0 ? 1.f : fm[0][1]);
         }
         float shm = DIR == 0 ? m * plm_prev : m;
         const int ew = (blk * KB - G.lag) & (kTpEdge - 1);  // slot base of this warp's own boundary values
 #pragma unroll
         for (int k = 0; k < KB; ++k) {
-            const float in_m = __shfl_sync(0xffffffffu, last_lane ? evm[k] : shm, src_lane);  // the long-latency hop first
-            const float own_term = m * c_own;
+            const float in_m = __shfl_up_sync(0xffffffffu, shm, 1);  // mantissa chain: the long-latency hop first
+            const float own_term = kMulti ? fmaf(evm[k], c_edge, m * c_own) : m * c_own;
             const int Ek = En;
             const float ci = c_in;
             const float plm = fm[k][1];
@@ -967,11 +964,13 @@ __device__ __forceinline__ void tp_sweep(TpWarp& W, int2 (*edge)[8], const float
             if (k + 1 < KB) {  // exponent recurrence of step k+1, in the shadow of the shuffle above
                 const int pbe_n = fe[DIR == 0 ? k : k + 1][0], ple_n = fe[DIR == 0 ? k : k + 1][1];
                 const int oE = Ek + pbe_n;
-                const int sE = last_lane ? evE[k + 1] : (DIR == 0 ? Ek + ple_n : Ek);
-                const int iE = __shfl_sync(0xffffffffu, sE, src_lane) + (DIR == 0 ? 0 : ple_n);
-                En = max(oE, iE);
+                const int iE = __shfl_up_sync(0xffffffffu, DIR == 0 ? Ek + ple_n : Ek, 1) +
+                               (DIR == 0 ? in_bias : in_bias + ple_n);
+                const int eE = DIR == 0 ? evE[k + 1] : evE[k + 1] + ple_n;
+                En = max(max(oE, iE), eE);
                 c_own = pow2_neg(En - oE) * fm[DIR == 0 ? k : k + 1][0];
                 c_in = pow2_neg(En - iE) * (DIR == 0 ? 1.f : fm[k + 1][1]);
+                c_edge = pow2_neg(En - eE) * (DIR == 0 ? 1.f : fm[k + 1][1]);
             } else {
                 pbm_prev = fm[k][0], plm_prev = plm, pbe_prev = fe[k][0], ple_prev = ple;
             }
@@ -986,12 +985,6 @@ __device__ __forceinline__ void tp_sweep(TpWarp& W, int2 (*edge)[8], const float
             const int shE = DIR == 0 ? E + ple : E;
             if (kMulti) {
                 if (lane == 31) edge[k + 1 < KB ? ew + k + 1 : (ew + KB) & (kTpEdge - 1)][w] = make_int2(__float_as_int(shm), shE);
-                if (to_band) {  // slot q of the receiving band = this warp's step index minus its lag
-                    const int q = blk * KB + k - G.lag;
-                    if (q >= 0)
-                        asm volatile("st.shared::cluster.v2.u32 [%0], {%1, %2};" ::"r"(r_xedge + 8u * (unsigned)q),
-                                     "r"(__float_as_int(shm)), "r"(shE) : "memory");
-                }
             }
             // off the chain: pack and park the value; the factor registers of this step are free now and
             // take the next block's factors of the same slot
@@ -1002,22 +995,28 @@ __device__ __forceinline__ void tp_sweep(TpWarp& W, int2 (*edge)[8], const float
                 fm[k][0] = fb.m, fe[k][0] = fb.e, fm[k][1] = fl.m, fe[k][1] = fl.e;
             }
         }
+        if (to_band) {  // forward this block's KB boundary values (they sit in the edge ring) to the next band:
+            __syncwarp();  // lanes 0..KB-1 each copy one slot into the receiving CTA's xedge[q], q = step - lag
+            if (lane < KB) {
+                const int q = blk * KB + lane - G.lag;
+                if (q >= 0) {
+                    const int2 ev = edge[lane + 1 < KB ? ew + lane + 1 : (ew + KB) & (kTpEdge - 1)][w];
+                    asm volatile("st.shared::cluster.v2.u32 [%0], {%1, %2};" ::"r"(r_xedge + 8u * (unsigned)q), "r"(ev.x), "r"(ev.y) : "memory");
+                }
+            }
+        }
         // lane 31 has now passed rows row_st .. row_st + KB - 1
-        if (lane_on) {
+        {
             int ov[KB];
 #pragma unroll
             for (int k = 0; k < KB; ++k) ov[k] = outc[((row_st + k + lane) & (kTpOut - 1)) * 32];
-            if (row_st >= 0 && row_st + KB <= Tb) {  // (warp-uniform) whole block inside the utterance
 #pragma unroll
-                for (int k = 0; k < KB; ++k) pst[k * G.stride] = ov[k];
-            } else {
-#pragma unroll
-                for (int k = 0; k < KB; ++k)
-                    if ((unsigned)(row_st + k) < (unsigned)Tb) pst[k * G.stride] = ov[k];
+            for (int k = 0; k < KB; ++k) {
+                if ((unsigned)(row_st + k) < G.Tb_eff) *pst = ov[k];
+                pst += G.stride;
             }
+            row_st += KB;
         }
-        pst += KB * G.stride;
-        row_st += KB;
         slot0 = slot1;
         tau += KB;
     }

@@ -3,8 +3,9 @@ model.py:28-31: fp16 autocast, torchaudio's loss).
 
 The projection kernels take fp16 / bf16 encoder / predictor outputs directly (converted exactly on load,
 gradients rounded to nearest on store, fp32 arithmetic in between), so:
-  * results on half inputs are BIT-IDENTICAL to the fp32 path fed the same values up-cast -- the AMP mode
-    inherits the fp32 path's parity, there is no separate half arithmetic to validate;
+  * results on half inputs are those of the fp32 path fed the same values up-cast (costs, d_enc, d_dec bit for
+    bit; d_weight / d_bias to fp32 atomic-accumulation order) -- the AMP mode inherits the fp32 path's parity,
+    there is no separate half arithmetic to validate;
   * under torch.autocast the drop-in module trains like the reference's --precision=16 configuration, whose
     own GPU path (eager joint under autocast + torchaudio CUDA rnnt_loss on fp16 logits) is the like-for-like
     comparison below (tolerance: fp16 rounding of the reference's logits, not of ours).
@@ -38,8 +39,10 @@ def test_half_activations_are_the_fp32_path_on_the_same_values(cuda_lib, dtype, 
     c_f, g_f = _step(d, enc_h.float(), dec_h.float())
     assert g_h["enc"].dtype == dtype and g_h["dec"].dtype == dtype and g_h["weight"].dtype == torch.float32
     assert torch.equal(c_h, c_f)
-    assert torch.equal(g_h["weight"], g_f["weight"]) and torch.equal(g_h["bias"], g_f["bias"])
     assert torch.equal(g_h["enc"], g_f["enc"].to(dtype)) and torch.equal(g_h["dec"], g_f["dec"].to(dtype))
+    # d_weight / d_bias: the same products, but summed across tiles with fp32 atomics (order varies run to run)
+    for k in ("weight", "bias"):
+        torch.testing.assert_close(g_h[k], g_f[k], rtol=0, atol=2e-6 * float(g_f[k].abs().max()) + 1e-7)
 
 
 def test_autocast_module_against_the_references_fp16_gpu_path(cuda_lib):
