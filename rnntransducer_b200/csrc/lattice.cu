@@ -1133,12 +1133,13 @@ int launch_lattice_sweep(const float2* lp2, const int32_t* act_lens, const int32
     // warp-specialised kernel for every shape it can run; RNNTB200_SWEEP_BW = warps per band (tp, long sequences)
     static const char* which = getenv("RNNTB200_SWEEP");
     static const int band_warps = getenv("RNNTB200_SWEEP_BW") ? atoi(getenv("RNNTB200_SWEEP_BW")) : 2;
-    const bool force_tp = which && which[0] == 't', force_ws = which && which[0] == 'w';
-    // Measured (round 2, sweep alone, us; tp / ws with the decoupled chain / round 1):
-    //   U1 = 81  (3 warps) B = 32: 45 / 51 / 54;  B = 512: 188 / 334 / 350
+    const bool force_ws = which && which[0] == 'w';
+    // Measured (round 2, sweep alone, us; tp / ws with the decoupled chain / round 1's ws):
+    //   U1 = 81  (3 warps) B = 32: 45 / 51 / 54;   B = 512: 188 / 334 / 350
     //   U1 = 101 (4 warps) B = 16: 49 / 67 / 68
-    //   U1 = 301 (10 warps) B = 8: 367 (bands of 2..4 over a cluster) / 237 / 236  -> ws keeps the long sequences
-    if (!legacy && !force_ws && (force_tp || warps <= 4)) {
+    //   U1 = 301 (10 warps, tp as 5 bands of 2 in a cluster) B = 8: 221 / 237 / 236;   B = 296: 1801 / 5300 / 5300
+    // -> the self-contained sweep serves every shape it can launch; the others remain as fall-backs.
+    if (!legacy && !force_ws) {
         const int st = launch_tp(lp2, act_lens, label_lens, B, T, U1, alpha, beta, costs, ll_alpha, warps, band_warps, stream);
         if (st >= 0) return st;
     }
