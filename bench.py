@@ -412,8 +412,11 @@ def run_ours(args):
             fn()
             e1.record()
         torch.cuda.synchronize()
-        return sum(e0.elapsed_time(e1) for e0, e1 in ev)  # ms
+        per_step.clear()
+        per_step.extend(e0.elapsed_time(e1) for e0, e1 in ev)
+        return sum(per_step)  # ms
 
+    per_step = []
     for _ in range(max(args.warmup, 3)):
         flush_buf.zero_()
         run_step()
@@ -421,6 +424,30 @@ def run_ours(args):
     with ClockSampler(local_rank) as clocks:
         total_ms = timed(run_step, args.steps)
     barrier()
+    step_times = sorted(per_step)
+
+    # N > 1: this rank's step WITHOUT the collective (its own graph, nobody to wait for) -- with the
+    # collective alone (below) it separates what a step costs from what waiting for the slowest rank costs
+    compute_only_ms = None
+    if world > 1:
+        saved_ar, peer_ar = peer_ar, None
+        zero_grads()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        zero_grads()
+        g2 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g2):
+            step()
+        peer_ar = saved_ar
+        for _ in range(5):
+            flush_buf.zero_()
+            g2.replay()
+        compute_only_ms = timed(g2.replay, args.steps) / args.steps
+        step_times_local = sorted(per_step)
+        barrier()
 
     # ---- end to end through the public API with host inputs ------------------------------------
     # Every step uploads its own inputs from pinned host memory and the host reads the step's loss.
@@ -489,10 +516,20 @@ def run_ours(args):
         us_peer = alone(lambda: peer_ar.all_reduce_mean_([gw, gb])) if peer_ar is not None else None
         t = torch.tensor([us_nccl, us_peer or 0.0], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        comp = [torch.zeros(1, device=dev, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(comp, torch.tensor([compute_only_ms], device=dev, dtype=torch.float64))
+        q = lambda v, f: v[min(len(v) - 1, int(f * len(v)))]
         ar_info = {"impl": "peer-memory one-shot kernel inside the step's CUDA graph" if peer_ar is not None
                    else "NCCL all_reduce of one flat bucket, issued from the host after the graph",
                    "floats": bucket.numel(), "us_alone_nccl": float(t[0]),
-                   "us_alone_peer": float(t[1]) if peer_ar is not None else None, "note": ar_note}
+                   "us_alone_peer": float(t[1]) if peer_ar is not None else None, "note": ar_note,
+                   "breakdown": {
+                       "what": "rank-0 per-step distribution of the timed steps (ms); every rank's step WITHOUT the "
+                               "collective (own graph, nobody to wait for); the collective alone is us_alone_*: "
+                               "step - (compute + collective) = waiting for the slowest rank",
+                       "step_ms_p10_p50_p90_max": [q(step_times, 0.1), q(step_times, 0.5), q(step_times, 0.9), step_times[-1]],
+                       "compute_only_ms_per_rank": [float(c[0]) for c in comp],
+                       "compute_only_ms_p50_p90_max_rank0": [q(step_times_local, 0.5), q(step_times_local, 0.9), step_times_local[-1]]}}
         t = torch.tensor([total_ms, e2e_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms, e2e_ms = float(t[0]), float(t[1])
@@ -547,6 +584,8 @@ def run_ours(args):
         "utterances_per_s": B * world * args.steps / (total_ms * 1e-3),
         "cells_per_step": total_cells, "loss": loss_value,
         "cuda_graph": graph is not None,
+        "step_ms_p10_p50_p90_max": [step_times[int(0.1 * len(step_times))], step_times[len(step_times) // 2],
+                                    step_times[min(len(step_times) - 1, int(0.9 * len(step_times)))], step_times[-1]],
         "clocks": clocks.summary(),
         "e2e": {"value": total_cells * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps,
