@@ -431,6 +431,7 @@ def run_ours(args):
     compute_only_ms = None
     if world > 1:
         saved_ar, peer_ar = peer_ar, None
+        saved_loss, saved_grads = out["loss"], {k: st[k].grad for k in ("enc", "dec", "weight", "bias")}
         zero_grads()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -442,6 +443,9 @@ def run_ours(args):
         with torch.cuda.graph(g2):
             step()
         peer_ar = saved_ar
+        out["loss"] = saved_loss  # the timed graph's own outputs again (the end-to-end leg reads them)
+        for k, g in saved_grads.items():
+            st[k].grad = g
         for _ in range(5):
             flush_buf.zero_()
             g2.replay()
@@ -821,6 +825,37 @@ def gpu_baseline(st, mode, cells, iters=10, warmup=3):
         for v in leaves.values():
             v.grad = None
         torch.cuda.empty_cache()
+    # the loss alone, like for like on the SAME dense logits (row A8: RNNTLoss as a drop-in for torchaudio's):
+    # torchaudio.functional.rnnt_loss vs rnntransducer_b200.rnnt_loss, fwd+bwd w.r.t. the logits
+    try:
+        import rnntransducer_b200 as rb
+        with torch.no_grad():
+            logits = reference_joint_eager(leaves["enc"], leaves["dec"], leaves["weight"], leaves["bias"], mode)
+        logits.requires_grad_(True)
+
+        def time_loss(fn):
+            for _ in range(warmup):
+                logits.grad = None
+                fn().backward()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                logits.grad = None
+                loss = fn()
+                loss.backward()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / iters, float(loss)
+        ta_ms, ta_loss = time_loss(lambda: torchaudio.functional.rnnt_loss(logits, lab, al, ll, blank=0, reduction="mean"))
+        our_ms, our_loss = time_loss(lambda: rb.rnnt_loss(logits, lab, al, ll, 0, "mean", warp_compat=False))
+        out["loss_only_dense_logits"] = {"torchaudio_cuda_ms": ta_ms, "ours_dense_ms": our_ms, "speedup": ta_ms / our_ms,
+                                         "loss_torchaudio": ta_loss, "loss_ours": our_loss,
+                                         "logits_GB": logits.numel() * 4 / 1e9}
+        del logits
+    except Exception as e:
+        out["loss_only_dense_logits"] = {"unavailable": repr(e)[:300]}
+    torch.cuda.empty_cache()
     return out
 
 

@@ -18,8 +18,8 @@ for path in sorted(glob.glob(os.path.join(root, f"{tag}_*.json"))):
         rows.append((name, None))
         continue
     rows.append((name, line))
-print("| run | workload | joint/gemm | ms/step | Gcells/s | utt/s | e2e Gcells/s | slowest of our kernels (us, GB/s, frac of HBM) |")
-print("|---|---|---|---|---|---|---|---|")
+print("| run | workload | joint/gemm | ms/step | Gcells/s | utt/s | e2e Gcells/s | lattice sweep alone (us, GB/s, frac of HBM; at a saturating batch) | reference GPU path ms/step (fp32 / fp16 autocast) |")
+print("|---|---|---|---|---|---|---|---|---|")
 for name, d in rows:
     if d is None:
         print(f"| {name} | (no JSON) | | | | | | |")
@@ -29,11 +29,13 @@ for name, d in rows:
     wl = f"B={c['B_per_gpu']} T={c['T']} U={c['U']} V={c['V']} H={c['H']}{' ragged' if c['ragged'] else ''}"
     if d.get("impl") == "reference":
         print(f"| {name} | {wl} | CPU oracle port, {d['cpu_baseline']['cores']} threads | {d['ms_per_step']:.1f} | "
-              f"{d['value'] / 1e9:.6f} | {d['utterances_per_s']:.1f} | - | - |")
+              f"{d['value'] / 1e9:.6f} | {d['utterances_per_s']:.1f} | - | - | - |")
         continue
     print(f"| {name} | {wl} | {c['joint']}/{c['gemm']} | {d['ms_per_step']:.3f} | {d['value'] / 1e9:.3f} | "
           f"{d['utterances_per_s']:.0f} | {d['e2e']['value'] / 1e9:.3f} | "
-          f"{rf.get('kernel', '?')} ({rf.get('us_per_launch', 0):.0f}, {rf.get('achieved', 0):.0f}, {rf.get('frac', 0):.3f}) |")
+          f"({rf.get('us_per_launch', 0):.0f}, {rf.get('achieved', 0):.0f}, {rf.get('frac', 0):.3f}; "
+          f"B={(rf.get('saturating_batch') or {}).get('B', '-')}: {(rf.get('saturating_batch') or {}).get('us', 0):.0f} us, {(rf.get('saturating_batch') or {}).get('frac', 0):.3f}) | "
+          f"{(d.get('gpu_baseline') or {}).get('ms_per_step', float('nan')):.1f} / {((d.get('gpu_baseline') or {}).get('fp16_autocast') or {}).get('ms_per_step', float('nan')):.1f} |")
     ks = d.get("kernels") or {}
     if ks:
-        print("|  | kernels (us): " + ", ".join(f"{k} {v['us']:.0f}" for k, v in ks.items()) + " | | | | | | |")
+        print("|  | kernels (us): " + ", ".join(f"{k} {v['us']:.0f}" for k, v in ks.items()) + " | | | | | | | |")
