@@ -122,6 +122,9 @@ class ClockSampler:
             self.nv = pynvml
             self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self._sample()  # first-use costs of the queries are paid here, not inside the timed region
+            self.samples.clear()
+            self.reasons.clear()
         except Exception:
             self.nv = None
 
@@ -404,8 +407,10 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    ev_pool = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+
     def timed(fn, n):
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+        ev = ev_pool[:n]
         for e0, e1 in ev:
             flush_buf.zero_()  # evict the working set from L2 (outside the timed bracket)
             e0.record()
@@ -417,11 +422,16 @@ def run_ours(args):
         return sum(per_step)  # ms
 
     per_step = []
+    # NVML is initialised and the timing events are created BEFORE the barrier: whatever a rank does between
+    # the barrier and its first timed step is rank skew that every other rank waits for in step 1's collective
+    # (nvmlInit on an 8-GPU box takes milliseconds and a different number of them on every rank: round 1's
+    # N = 8 lines each carried one ~3 ms first step, 0.36 instead of 0.21 ms per step over 20 steps)
+    clocks = ClockSampler(local_rank)
     for _ in range(max(args.warmup, 3)):
         flush_buf.zero_()
         run_step()
     barrier()
-    with ClockSampler(local_rank) as clocks:
+    with clocks:
         total_ms = timed(run_step, args.steps)
     barrier()
     step_times = sorted(per_step)
@@ -677,11 +687,12 @@ def run_cfg5(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    clocks = ClockSampler(local_rank)  # nvmlInit before the barrier (see run_ours)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     for _ in range(max(args.warmup, 3)):
         train_step(dev_batch)
     barrier()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    with ClockSampler(local_rank) as clocks:
+    with clocks:
         for e0, e1 in ev:
             flush_buf.zero_()
             e0.record()
