@@ -54,6 +54,9 @@ def parse_args():
     p.add_argument("--batch", type=int, default=None, help="override the config's utterances per GPU")
     p.add_argument("--eager", action="store_true", help="do not replay the step from a CUDA graph")
     p.add_argument("--deterministic", action="store_true")
+    p.add_argument("--act-dtype", default="fp32", choices=["fp32", "fp16", "bf16"],
+                   help="dtype of the encoder / predictor outputs handed to the joint (fp16 = the reference's shipped "
+                        "--precision=16, scripts/run_train.sh:32): concat_gelu reads them directly, H2D bytes halve")
     p.add_argument("--allreduce", default="peer", choices=["peer", "nccl"],
                    help="N>1: gradient all-reduce of the fc grads -- one-shot kernel over NVLink peer memory inside the "
                         "step's CUDA graph (default) or torch.distributed/NCCL issued from the host after the graph")
@@ -318,6 +321,14 @@ def run_ours(args):
     B, T, U, V, H = c["B"], c["T"], c["U"], c["V"], c["H"]
     U1 = U + 1
     host = synthetic.make_batch(B, T, U, V, H, mode=mode, ragged=args.ragged, seed=1234 + args.cfg + rank)
+    host32 = dict(host)  # fp32 copy for the CPU legs
+    act_dtype = {"fp32": torch.float32, "fp16": torch.float16, "bf16": torch.bfloat16}[args.act_dtype]
+    if act_dtype != torch.float32:
+        if mode != "concat_gelu":
+            raise SystemExit("--act-dtype: only the concat_gelu joint reads half activations directly")
+        host["enc"], host["dec"] = host["enc"].to(act_dtype), host["dec"].to(act_dtype)
+        host32["enc"], host32["dec"] = host["enc"].float(), host["dec"].float()  # the same values
+        config["activations"] = args.act_dtype
     cells = synthetic.count_cells(host["act_lens"], host["label_lens"])
     # Per-step inputs live in ONE slab (256-byte aligned fields): one pinned host slab, one device slab
     # whose views are the static buffers the CUDA graph is captured on -> the end-to-end leg uploads a
@@ -593,7 +604,8 @@ def run_ours(args):
         "metric": METRIC, "value": total_cells * args.steps / (total_ms * 1e-3), "unit": UNIT,
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32" if gemm == "fp32" else "bf16 GEMM / f32 lattice",
+        "vs_baseline": None, "dtype": ("f32" if gemm == "fp32" else "bf16 GEMM / f32 lattice") +
+                                      ("" if act_dtype == torch.float32 else f" ({args.act_dtype} activations, fp32 arithmetic)"),
         "data": "synthetic", "config": config,
         "utterances_per_s": B * world * args.steps / (total_ms * 1e-3),
         "cells_per_step": total_cells, "loss": loss_value,
@@ -617,7 +629,7 @@ def run_ours(args):
         if "value" in line["gpu_baseline"]:
             line["gpu_baseline"]["ours_over_baseline"] = line["value"] / line["gpu_baseline"]["value"]
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = time_cpu(host, mode, args.cpu_seconds)
+        line["cpu_baseline"] = time_cpu(host32, mode, args.cpu_seconds)
     emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -798,7 +810,7 @@ def gpu_baseline(st, mode, cells, iters=10, warmup=3):
         import torchaudio
     except Exception as e:
         return {"unavailable": f"torchaudio import failed: {e!r}"}
-    leaves = {k: st[k].detach().clone().requires_grad_(True) for k in ("enc", "dec", "weight", "bias")}
+    leaves = {k: st[k].detach().float().clone().requires_grad_(True) for k in ("enc", "dec", "weight", "bias")}
     lab, al, ll = st["labels"].contiguous(), st["act_lens"].contiguous(), st["label_lens"].contiguous()
 
     def step(fp16):
@@ -941,8 +953,10 @@ def per_kernel(lib, st, mode, gemm, det, B, T, U1, V, H, cells, flush_buf, iters
         enc, dec, w, b = st["enc"].detach(), st["dec"].detach(), st["weight"].detach(), st["bias"].detach()
         if mode == "concat_gelu":
             He = enc.shape[-1]
-            proj = lambda: (F.linear(F.gelu(enc, approximate="tanh"), w[:, :He], b),
-                            F.linear(F.gelu(dec, approximate="tanh"), w[:, He:]))
+            xdt = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}[enc.dtype]
+            xb = enc.element_size()
+            proj = lambda: (F.linear(F.gelu(enc.float(), approximate="tanh"), w[:, :He], b),
+                            F.linear(F.gelu(dec.float(), approximate="tanh"), w[:, He:]))
             penc, pdec = proj()
             penc, pdec = penc.contiguous(), pdec.contiguous()
             d_penc, d_pdec = torch.empty_like(penc), torch.empty_like(pdec)
@@ -953,8 +967,8 @@ def per_kernel(lib, st, mode, gemm, det, B, T, U1, V, H, cells, flush_buf, iters
             if pws_bytes:
                 pws = torch.empty(pws_bytes, dtype=torch.uint8, device=dev)
                 bench("proj_tc_kernel", lambda: _lib.check(lib.rnntb200_joint_cg_project(
-                    p(enc), p(dec), 0, p(w), p(b), B * T, B * U1, He, dec.shape[-1], V, p(penc), p(pdec), p(pws),
-                    pws_bytes, stream)), 4 * (enc.numel() + dec.numel() + w.numel()) + io)
+                    p(enc), p(dec), xdt, p(w), p(b), B * T, B * U1, He, dec.shape[-1], V, p(penc), p(pdec), p(pws),
+                    pws_bytes, stream)), xb * (enc.numel() + dec.numel()) + 4 * w.numel() + io)
                 res["proj_tc_kernel"]["flops"] = 2.0 * V * (He * B * T + dec.shape[-1] * B * U1)
             else:
                 bench("torch_projections(gelu+linear x2, library)", proj,
@@ -976,9 +990,9 @@ def per_kernel(lib, st, mode, gemm, det, B, T, U1, V, H, cells, flush_buf, iters
                 bws = torch.empty(bws_bytes, dtype=torch.uint8, device=dev)
                 d_enc, d_dec, d_w, d_b = (torch.empty_like(t) for t in (enc, dec, w, b))
                 bench("proj_tc_bwd_kernel", lambda: _lib.check(lib.rnntb200_joint_cg_project_bwd(
-                    p(enc), p(dec), 0, p(w), p(d_penc), p(d_pdec), B * T, B * U1, He, dec.shape[-1], V, p(d_enc),
+                    p(enc), p(dec), xdt, p(w), p(d_penc), p(d_pdec), B * T, B * U1, He, dec.shape[-1], V, p(d_enc),
                     p(d_dec), p(d_w), p(d_b), p(bws), bws_bytes, 0, stream)),
-                    8 * (enc.numel() + dec.numel() + w.numel()) + io)
+                    2 * xb * (enc.numel() + dec.numel()) + 8 * w.numel() + io)
                 res["proj_tc_bwd_kernel"]["flops"] = 4.0 * V * (He * B * T + dec.shape[-1] * B * U1)
         else:
             d_enc, d_dec = torch.empty_like(enc), torch.empty_like(dec)

@@ -1132,7 +1132,9 @@ int launch_lattice_sweep(const float2* lp2, const int32_t* act_lens, const int32
     // A/B switch (timing experiments only): RNNTB200_SWEEP=tp | ws selects the self-contained or the
     // warp-specialised kernel for every shape it can run; RNNTB200_SWEEP_BW = warps per band (tp, long sequences)
     static const char* which = getenv("RNNTB200_SWEEP");
-    static const int band_warps = getenv("RNNTB200_SWEEP_BW") ? atoi(getenv("RNNTB200_SWEEP_BW")) : 2;
+    static const int band_warps_env = getenv("RNNTB200_SWEEP_BW") ? atoi(getenv("RNNTB200_SWEEP_BW")) : 0;
+    // bands of two warps (five SMs for U1 = 301) up to 16 warps; wider bands beyond, so that 8 bands cover U1 = 1024
+    const int band_warps = band_warps_env ? band_warps_env : (warps <= 16 ? 2 : (warps <= 24 ? 3 : 4));
     const bool force_ws = which && which[0] == 'w';
     // Measured (round 2, sweep alone, us; tp / ws with the decoupled chain / round 1's ws):
     //   U1 = 81  (3 warps) B = 32: 45 / 51 / 54;   B = 512: 188 / 334 / 350
