@@ -173,6 +173,27 @@ RNNTB200_API int rnntb200_joint_cg_bwd(const float* penc, const float* pdec, con
                           float* d_pdec, int deterministic, void* workspace, size_t workspace_bytes,
                           const void* factors, size_t factors_bytes, void* stream);
 
+/* The same two calls with the reduction over the utterances folded in (what `RNNTLoss(reduction="mean" |
+ * "sum")` computes, model.py:39,57): the sweep's last-arriving utterance adds the B costs in index order
+ * (bit-reproducible) and writes loss[0] = loss_scale * sum_b costs[b] (loss_scale = 1/B for "mean"); the
+ * backward takes the ONE upstream value grad_loss[0] and uses grad_scale * grad_loss[0] for every
+ * utterance.  Saves the reduction kernel and the broadcast multiply of a step.  `ticket`: one int32 in
+ * device memory, zero before the first call; every call leaves it zero (calls sharing a ticket must be
+ * stream-ordered).  costs[B] is still written. */
+RNNTB200_API int rnntb200_joint_cg_fwd_loss(const float* penc, const float* pdec, const int32_t* labels,
+                               const int32_t* act_lens, const int32_t* label_lens, int B, int T, int U1,
+                               int V, int blank, float* costs, void* lp2, float* lse,
+                               rnntb200_e16m16_t* alpha, rnntb200_e16m16_t* beta, void* factors,
+                               size_t factors_bytes, float* loss, int32_t* ticket, float loss_scale,
+                               void* stream);
+
+RNNTB200_API int rnntb200_joint_cg_bwd_loss(const float* penc, const float* pdec, const int32_t* labels,
+                               const int32_t* act_lens, const int32_t* label_lens, int B, int T, int U1,
+                               int V, int blank, const float* lse, const rnntb200_e16m16_t* alpha,
+                               const rnntb200_e16m16_t* beta, const float* grad_loss, float grad_scale,
+                               float* d_penc, float* d_pdec, int deterministic, void* workspace,
+                               size_t workspace_bytes, const void* factors, size_t factors_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Fused joint + loss, ADD_TANH mode: logits(t,u,:) = tanh(enc_t + dec_u) W^T + bias, the one
  * dense H x V contraction per lattice cell.  enc [B,T,H], dec [B,U1,H], weight [V,H], bias [V].

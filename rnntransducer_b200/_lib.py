@@ -28,6 +28,9 @@ SIGNATURES = {
     "rnntb200_joint_cg_project_bwd": (_c_int, [_P] * 2 + [_c_int] + [_P] * 3 + [_c_int] * 5 + [_P] * 5 + [_c_size_t, _c_int, _P]),
     "rnntb200_joint_cg_factors_bytes": (_c_size_t, [_c_int] * 4),
     "rnntb200_joint_cg_fwd": (_c_int, [_P] * 5 + [_c_int] * 5 + [_P] * 6 + [_c_size_t, _P]),
+    "rnntb200_joint_cg_fwd_loss": (_c_int, [_P] * 5 + [_c_int] * 5 + [_P] * 6 + [_c_size_t, _P, _P, ctypes.c_float, _P]),
+    "rnntb200_joint_cg_bwd_loss": (_c_int, [_P] * 5 + [_c_int] * 5 + [_P] * 4 + [ctypes.c_float, _P, _P, _c_int, _P, _c_size_t,
+                                            _P, _c_size_t, _P]),
     "rnntb200_joint_cg_bwd_workspace_bytes": (_c_size_t, [_c_int] * 5),
     "rnntb200_joint_cg_bwd": (_c_int, [_P] * 5 + [_c_int] * 5 + [_P] * 6 + [_c_int, _P, _c_size_t, _P, _c_size_t, _P]),
     "rnntb200_joint_at_workspace_bytes": (_c_size_t, [_c_int] * 3),

@@ -147,7 +147,43 @@ RNNTB200_API int rnntb200_joint_cg_bwd(const float* penc, const float* pdec, con
         return RNNTB200_STATUS_INVALID_VALUE;
     if (B > 0 && U1 > 1 && !labels) return RNNTB200_STATUS_INVALID_VALUE;
     return launch_cg_grad(penc, pdec, labels, act_lens, label_lens, B, T, U1, V, blank, lse, alpha,
-                          beta, grad_costs, d_penc, d_pdec, deterministic, workspace,
+                          beta, GradCosts{grad_costs, 1, 1.f}, d_penc, d_pdec, deterministic, workspace,
+                          workspace_bytes, factors, factors_bytes, (cudaStream_t)stream);
+}
+
+RNNTB200_API int rnntb200_joint_cg_fwd_loss(const float* penc, const float* pdec, const int32_t* labels,
+                               const int32_t* act_lens, const int32_t* label_lens, int B, int T, int U1,
+                               int V, int blank, float* costs, void* lp2, float* lse,
+                               rnntb200_e16m16_t* alpha, rnntb200_e16m16_t* beta, void* factors,
+                               size_t factors_bytes, float* loss, int32_t* ticket, float loss_scale,
+                               void* stream) {
+    if (bad_shape(B, T, U1, V, blank) || B <= 0) return RNNTB200_STATUS_INVALID_VALUE;
+    if (!penc || !pdec || !act_lens || !label_lens || !costs || !lp2 || !lse || !alpha || !beta || !loss || !ticket)
+        return RNNTB200_STATUS_INVALID_VALUE;
+    if (U1 > 1 && !labels) return RNNTB200_STATUS_INVALID_VALUE;
+    cudaStream_t s = (cudaStream_t)stream;
+    int st = launch_cg_lse(penc, pdec, labels, act_lens, label_lens, B, T, U1, V, blank, (float2*)lp2,
+                           lse, factors, factors_bytes, s);
+    if (st != RNNTB200_STATUS_SUCCESS) return st;
+    LossReduce R;
+    R.out = loss, R.ticket = ticket, R.scale = loss_scale;
+    return launch_lattice_sweep((const float2*)lp2, act_lens, label_lens, B, T, U1, alpha, beta,
+                                costs, nullptr, s, &R);
+}
+
+RNNTB200_API int rnntb200_joint_cg_bwd_loss(const float* penc, const float* pdec, const int32_t* labels,
+                               const int32_t* act_lens, const int32_t* label_lens, int B, int T, int U1,
+                               int V, int blank, const float* lse, const rnntb200_e16m16_t* alpha,
+                               const rnntb200_e16m16_t* beta, const float* grad_loss, float grad_scale,
+                               float* d_penc, float* d_pdec, int deterministic, void* workspace,
+                               size_t workspace_bytes, const void* factors, size_t factors_bytes, void* stream) {
+    if (bad_shape(B, T, U1, V, blank)) return RNNTB200_STATUS_INVALID_VALUE;
+    if (B > 0 && (!penc || !pdec || !act_lens || !label_lens || !lse || !alpha || !beta ||
+                  !grad_loss || !d_penc || !d_pdec))
+        return RNNTB200_STATUS_INVALID_VALUE;
+    if (B > 0 && U1 > 1 && !labels) return RNNTB200_STATUS_INVALID_VALUE;
+    return launch_cg_grad(penc, pdec, labels, act_lens, label_lens, B, T, U1, V, blank, lse, alpha,
+                          beta, GradCosts{grad_loss, 0, grad_scale}, d_penc, d_pdec, deterministic, workspace,
                           workspace_bytes, factors, factors_bytes, (cudaStream_t)stream);
 }
 

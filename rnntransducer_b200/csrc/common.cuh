@@ -131,9 +131,10 @@ inline int status_from_cuda(cudaError_t e) {
 inline int launch_status() { return status_from_cuda(cudaGetLastError()); }
 
 // ---- internal launchers (defined in the .cu files, called from api.cu) ------------------------
+struct LossReduce;
 int launch_lattice_sweep(const float2* lp2, const int32_t* act_lens, const int32_t* label_lens, int B,
                          int T, int U1, int32_t* alpha, int32_t* beta, float* costs, float* ll_alpha,
-                         cudaStream_t stream);
+                         cudaStream_t stream, const LossReduce* reduce = nullptr);
 
 int launch_dense_lse(const void* logits, int dtype, const int32_t* labels, const int32_t* act_lens,
                      const int32_t* label_lens, int B, int T, int U1, int V, int blank, float2* lp2,
@@ -163,9 +164,28 @@ size_t cg_factors_bytes(int B, int T, int U1, int V);  // 0: V > 128, the generi
 int launch_cg_lse(const float* penc, const float* pdec, const int32_t* labels, const int32_t* act_lens,
                   const int32_t* label_lens, int B, int T, int U1, int V, int blank, float2* lp2,
                   float* lse, void* factors, size_t factors_bytes, cudaStream_t stream);
+// Upstream gradient of the per-utterance costs: a [B] vector (stride 1) or ONE value broadcast to every
+// utterance (stride 0: the backward of a fused mean / sum, scale = 1/B or 1) -- the latter saves the
+// broadcast-multiply launch between the loss reduction's backward and the gradient kernel.
+struct GradCosts {
+    const float* p;
+    int stride;
+    float scale;
+    __device__ __forceinline__ float at(int b) const { return __ldg(p + (size_t)b * stride) * scale; }
+};
+
+// Fused reduction of the costs inside the sweep (last-arriving utterance sums all B costs in index order:
+// bit-reproducible): out[0] = scale * sum_b costs[b].  ticket: one int32 in device memory, zero before the
+// first launch and left zero by every launch.  out == nullptr: off.
+struct LossReduce {
+    float* out = nullptr;
+    int* ticket = nullptr;
+    float scale = 0.f;
+};
+
 int launch_cg_grad(const float* penc, const float* pdec, const int32_t* labels, const int32_t* act_lens,
                    const int32_t* label_lens, int B, int T, int U1, int V, int blank, const float* lse,
-                   const int32_t* alpha, const int32_t* beta, const float* grad_costs,
+                   const int32_t* alpha, const int32_t* beta, GradCosts grad_costs,
                    float* d_penc, float* d_pdec, int deterministic, void* workspace,
                    size_t workspace_bytes, const void* factors, size_t factors_bytes, cudaStream_t stream);
 size_t cg_grad_workspace_bytes(int B, int T, int U1, int V, int deterministic);

@@ -24,7 +24,7 @@ int launch_cg_lse_mm(const float* penc, const float* pdec, const CgFactors& F, c
                      float2* lp2, float* lse, cudaStream_t stream);
 int launch_cg_grad_mm(const float* penc, const float* pdec, const CgFactors& F, const int32_t* labels,
                       const int32_t* act_lens, const int32_t* label_lens, int B, int T, int U1, int V, int blank,
-                      const float* lse, const int32_t* alpha, const int32_t* beta, const float* grad_costs,
+                      const float* lse, const int32_t* alpha, const int32_t* beta, GradCosts grad_costs,
                       float* d_penc, float* d_pdec, float* partial, cudaStream_t stream);
 
 namespace {
@@ -104,7 +104,7 @@ cg_grad_kernel(const float* __restrict__ penc, const float* __restrict__ pdec,
                const int32_t* __restrict__ label_lens, int T, int U1, int V, int blank,
                const float* __restrict__ lse, const int32_t* __restrict__ alpha,
                const int32_t* __restrict__ beta,
-               const float* __restrict__ grad_costs, float* __restrict__ d_penc,
+               GradCosts grad_costs, float* __restrict__ d_penc,
                float* __restrict__ d_pdec, float* __restrict__ partial /* deterministic slabs or null */) {
     __shared__ CellScalars sc[kGT][kGUC];
     __shared__ int ys[kGUC];
@@ -112,7 +112,7 @@ cg_grad_kernel(const float* __restrict__ penc, const float* __restrict__ pdec,
     const int tile = blockIdx.x;
     const int t0 = tile * kGT;
     const int Tb = len_T(act_lens, b, T), Ub = len_U(label_lens, b, U1);
-    const float gc = grad_costs[b];
+    const float gc = grad_costs.at(b);
     const int llq = beta[(size_t)b * T * U1];  // beta(0,0) = log2 P(y|x), e16m16
     const int n_tiles = gridDim.x;
     // deterministic mode: slab [b][tile][U1][V]
@@ -250,7 +250,7 @@ size_t cg_grad_workspace_bytes(int B, int T, int U1, int V, int deterministic) {
 
 int launch_cg_grad(const float* penc, const float* pdec, const int32_t* labels, const int32_t* act_lens,
                    const int32_t* label_lens, int B, int T, int U1, int V, int blank, const float* lse,
-                   const int32_t* alpha, const int32_t* beta, const float* grad_costs,
+                   const int32_t* alpha, const int32_t* beta, GradCosts grad_costs,
                    float* d_penc, float* d_pdec, int deterministic, void* workspace,
                    size_t workspace_bytes, const void* factors, size_t factors_bytes, cudaStream_t stream) {
     if ((long long)B * T * U1 == 0) return RNNTB200_STATUS_SUCCESS;

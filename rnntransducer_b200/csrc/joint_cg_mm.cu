@@ -319,7 +319,7 @@ cg_grad_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec
                   const int32_t* __restrict__ labels, const int32_t* __restrict__ act_lens,
                   const int32_t* __restrict__ label_lens, int T, int U1, int V, int Vk, int Vs, int blank,
                   const float* __restrict__ lse, const int32_t* __restrict__ alpha,
-                  const int32_t* __restrict__ beta, const float* __restrict__ grad_costs,
+                  const int32_t* __restrict__ beta, GradCosts grad_costs,
                   float* __restrict__ d_penc, float* __restrict__ d_pdec,
                   float* __restrict__ partial /* deterministic slabs or null */) {
     // operand planes hold packed (bf16 hi | bf16 lo << 16) pairs (pack_hilo): A / B arrive that way
@@ -358,7 +358,7 @@ cg_grad_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec
             for (int i = tid; i < U1 * V; i += kGThreads) slab[i] = 0.f;
         return;
     }
-    const float gc = grad_costs[b];
+    const float gc = grad_costs.at(b);
     const int llq = beta[(size_t)b * T * U1];  // beta(0,0) = P(y|x), e16m16
     const int rows_t = min(kGT2, Tb - t0);
 
@@ -605,7 +605,7 @@ inline int grad_row_stride(int Vk) { return (Vk & 15) == 8 ? Vk : Vk + 8; }  // 
 template <int NTW>
 int launch_grad_mm(const float* penc, const float* pdec, const CgFactors& F, const int32_t* labels,
                    const int32_t* act_lens, const int32_t* label_lens, int B, int T, int U1, int V, int blank,
-                   const float* lse, const int32_t* alpha, const int32_t* beta, const float* grad_costs,
+                   const float* lse, const int32_t* alpha, const int32_t* beta, GradCosts grad_costs,
                    float* d_penc, float* d_pdec, float* partial, cudaStream_t stream) {
     const int Vk = F.Vk, Vs = grad_row_stride(Vk);
     const size_t smem = ((size_t)(kGT2 + 2 * kGUC2) * Vs + 3 * kGT2 * kCs + 2 * kGT2 + 8 * kGUC2) *
@@ -672,7 +672,7 @@ int launch_cg_lse_mm(const float* penc, const float* pdec, const CgFactors& F, c
 
 int launch_cg_grad_mm(const float* penc, const float* pdec, const CgFactors& F, const int32_t* labels,
                       const int32_t* act_lens, const int32_t* label_lens, int B, int T, int U1, int V, int blank,
-                      const float* lse, const int32_t* alpha, const int32_t* beta, const float* grad_costs,
+                      const float* lse, const int32_t* alpha, const int32_t* beta, GradCosts grad_costs,
                       float* d_penc, float* d_pdec, float* partial, cudaStream_t stream) {
 #define RNNT_MM(NTW)                                                                                         \
     return launch_grad_mm<NTW>(penc, pdec, F, labels, act_lens, label_lens, B, T, U1, V, blank, lse, alpha, \

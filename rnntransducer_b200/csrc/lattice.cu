@@ -777,6 +777,33 @@ int launch_ws_cluster(const float2* lp2, const int32_t* act_lens, const int32_t*
 }
 
 
+// ---- fused reduction of the costs (LossReduce, common.cuh) ---------------------------------------------
+// Called by the one thread per utterance that has just written costs[b]: the last utterance to arrive sums
+// all B costs in index order (the same bits whatever the arrival order) and re-arms the ticket.
+struct ReduceArgs {
+    float* out;
+    int* ticket;
+    float scale;
+    int B;
+};
+__device__ __forceinline__ void reduce_costs_last_arriver(const ReduceArgs& R, const float* costs) {
+    if (R.out == nullptr) return;
+    __threadfence();  // costs[b] before the ticket
+    if (atomicAdd(R.ticket, 1) != R.B - 1) return;
+    __threadfence();
+    float s = 0.f;
+    for (int i = 0; i < R.B; ++i) s += __ldcg(costs + i);
+    R.out[0] = s * R.scale;
+    *R.ticket = 0;
+}
+__global__ void reduce_costs_kernel(const float* __restrict__ costs, int B, float scale, float* __restrict__ out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {  // fallback sweeps only (same order, same bits)
+        float s = 0.f;
+        for (int i = 0; i < B; ++i) s += costs[i];
+        out[0] = s * scale;
+    }
+}
+
 // =================================================================================================
 // Self-contained sweep ("tp"): one warp does everything for its 32 label positions.
 //
@@ -813,7 +840,8 @@ struct TpWarp {
 template <int DIR, bool kMulti, bool kCluster>
 __device__ __forceinline__ void tp_sweep(TpWarp& W, int2 (*edge)[8], const float2* __restrict__ lp2, int Tb, int Ub,
                                          int T, int U1, int b, int32_t* __restrict__ out, float* __restrict__ costs,
-                                         float* __restrict__ ll_alpha, int w, int nw, int lane, const WsBand& X) {
+                                         float* __restrict__ ll_alpha, int w, int nw, int lane, const WsBand& X,
+                                         const ReduceArgs& R) {
     constexpr int KB = kTpKB;
     const WsGeom<DIR, kMulti, KB> G(Tb, Ub, T, U1, b, X.band * nw + w, lane, X.xlag);
     const int n_on = (Ub + 32) / 32;  // warps with cells
@@ -1032,6 +1060,7 @@ __device__ __forceinline__ void tp_sweep(TpWarp& W, int2 (*edge)[8], const float
             }
         } else {
             costs[b] = cost_of(me_normalize(last));
+            reduce_costs_last_arriver(R, costs);
         }
     }
 }
@@ -1041,7 +1070,7 @@ __global__ void __launch_bounds__(128)
 lattice_sweep_tp_kernel(const float2* __restrict__ lp2, const int32_t* __restrict__ act_lens,
                         const int32_t* __restrict__ label_lens, int T, int U1, int32_t* __restrict__ alpha,
                         int32_t* __restrict__ beta, float* __restrict__ costs, float* __restrict__ ll_alpha,
-                        int xedge_slots) {
+                        int xedge_slots, ReduceArgs R) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TpWarp* tw = reinterpret_cast<TpWarp*>(smem_raw);
     __shared__ int2 edge[kTpEdge][8];  // column w: written by warp w; column 4 stays "zero" (warp 0 of band 0)
@@ -1066,26 +1095,27 @@ lattice_sweep_tp_kernel(const float2* __restrict__ lp2, const int32_t* __restric
         cluster_barrier();  // no CTA may be written to before it has initialised its shared memory
     }
     if (blockIdx.y == 0)
-        tp_sweep<0, kMulti, kCluster>(tw[warp], edge, lp2, Tb, Ub, T, U1, b, alpha, costs, ll_alpha, warp, nw, lane, X);
+        tp_sweep<0, kMulti, kCluster>(tw[warp], edge, lp2, Tb, Ub, T, U1, b, alpha, costs, ll_alpha, warp, nw, lane, X, R);
     else
-        tp_sweep<1, kMulti, kCluster>(tw[warp], edge, lp2, Tb, Ub, T, U1, b, beta, costs, ll_alpha, warp, nw, lane, X);
+        tp_sweep<1, kMulti, kCluster>(tw[warp], edge, lp2, Tb, Ub, T, U1, b, beta, costs, ll_alpha, warp, nw, lane, X, R);
     if (kCluster) cluster_barrier();  // no CTA may exit while a neighbour can still write into its shared memory
 }
 
 // warps <= 4: one CTA per sweep.  More: bands of `bw` warps in a thread-block cluster.  Returns -1 when the
 // configuration cannot be launched (the caller falls back to the other kernels).
 int launch_tp(const float2* lp2, const int32_t* act_lens, const int32_t* label_lens, int B, int T, int U1,
-              int32_t* alpha, int32_t* beta, float* costs, float* ll_alpha, int warps, int bw, cudaStream_t stream) {
+              int32_t* alpha, int32_t* beta, float* costs, float* ll_alpha, int warps, int bw, cudaStream_t stream,
+              ReduceArgs R) {
     if (warps <= 4) {
         const size_t smem = (size_t)warps * sizeof(TpWarp);
         if (warps == 1) {
             auto kern = lattice_sweep_tp_kernel<false, false>;
             if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-            kern<<<dim3(B, 2), 32, smem, stream>>>(lp2, act_lens, label_lens, T, U1, alpha, beta, costs, ll_alpha, 0);
+            kern<<<dim3(B, 2), 32, smem, stream>>>(lp2, act_lens, label_lens, T, U1, alpha, beta, costs, ll_alpha, 0, R);
         } else {
             auto kern = lattice_sweep_tp_kernel<true, false>;
             if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-            kern<<<dim3(B, 2), warps * 32, smem, stream>>>(lp2, act_lens, label_lens, T, U1, alpha, beta, costs, ll_alpha, 0);
+            kern<<<dim3(B, 2), warps * 32, smem, stream>>>(lp2, act_lens, label_lens, T, U1, alpha, beta, costs, ll_alpha, 0, R);
         }
         return launch_status();
     }
@@ -1116,15 +1146,37 @@ int launch_tp(const float2* lp2, const int32_t* act_lens, const int32_t* label_l
         (void)cudaGetLastError();
         return -1;
     }
-    e = cudaLaunchKernelEx(&cfg, kern, lp2, act_lens, label_lens, T, U1, alpha, beta, costs, ll_alpha, slots);
+    e = cudaLaunchKernelEx(&cfg, kern, lp2, act_lens, label_lens, T, U1, alpha, beta, costs, ll_alpha, slots, R);
     return e == cudaSuccess ? launch_status() : status_from_cuda(e);
 }
 
 }  // namespace
 
+namespace {
+int sweep_dispatch(const float2* lp2, const int32_t* act_lens, const int32_t* label_lens, int B, int T, int U1,
+                   int32_t* alpha, int32_t* beta, float* costs, float* ll_alpha, cudaStream_t stream,
+                   const ReduceArgs& R, bool* reduced);
+}
+
 int launch_lattice_sweep(const float2* lp2, const int32_t* act_lens, const int32_t* label_lens, int B,
                          int T, int U1, int32_t* alpha, int32_t* beta, float* costs, float* ll_alpha,
-                         cudaStream_t stream) {
+                         cudaStream_t stream, const LossReduce* reduce) {
+    ReduceArgs R{nullptr, nullptr, 0.f, B};
+    if (reduce && reduce->out) {
+        if (!reduce->ticket) return RNNTB200_STATUS_INVALID_VALUE;
+        R = ReduceArgs{reduce->out, reduce->ticket, reduce->scale, B};
+    }
+    bool reduced = false;
+    const int st = sweep_dispatch(lp2, act_lens, label_lens, B, T, U1, alpha, beta, costs, ll_alpha, stream, R, &reduced);
+    if (st != RNNTB200_STATUS_SUCCESS || R.out == nullptr || reduced || B == 0) return st;
+    reduce_costs_kernel<<<1, 32, 0, stream>>>(costs, B, R.scale, R.out);  // the fallback sweeps do not carry the ticket
+    return launch_status();
+}
+
+namespace {
+int sweep_dispatch(const float2* lp2, const int32_t* act_lens, const int32_t* label_lens, int B, int T, int U1,
+                   int32_t* alpha, int32_t* beta, float* costs, float* ll_alpha, cudaStream_t stream,
+                   const ReduceArgs& R, bool* reduced) {
     if (B == 0) return RNNTB200_STATUS_SUCCESS;
     if (U1 > 1024) return RNNTB200_STATUS_INVALID_VALUE;
     const int warps = (U1 + 31) / 32;
@@ -1142,8 +1194,11 @@ int launch_lattice_sweep(const float2* lp2, const int32_t* act_lens, const int32
     //   U1 = 301 (10 warps, tp as 5 bands of 2 in a cluster) B = 8: 221 / 237 / 236;   B = 296: 1801 / 5300 / 5300
     // -> the self-contained sweep serves every shape it can launch; the others remain as fall-backs.
     if (!legacy && !force_ws) {
-        const int st = launch_tp(lp2, act_lens, label_lens, B, T, U1, alpha, beta, costs, ll_alpha, warps, band_warps, stream);
-        if (st >= 0) return st;
+        const int st = launch_tp(lp2, act_lens, label_lens, B, T, U1, alpha, beta, costs, ll_alpha, warps, band_warps, stream, R);
+        if (st >= 0) {
+            *reduced = true;
+            return st;
+        }
     }
     // Measured (sweep alone, us):  U1 = 81 (3 warps): 53 warp-specialised in one CTA / 59 single-role;
     // U1 = 101 (4 warps): 81 in one CTA (20 warps crowd the SM) / 74 as two bands / 68 single-role;
@@ -1188,5 +1243,6 @@ int launch_lattice_sweep(const float2* lp2, const int32_t* act_lens, const int32
                                        costs, ll_alpha);
     return e == cudaSuccess ? launch_status() : status_from_cuda(e);
 }
+}  // namespace
 
 }  // namespace rnntb200

@@ -78,6 +78,17 @@ def joint_rnnt_costs(enc: Tensor, dec: Tensor, weight: Tensor, bias: Optional[Te
 def joint_rnnt_loss(enc, dec, weight, bias, labels, act_lens, label_lens, blank=0,
                     reduction="mean", mode="concat_gelu", gemm="fp32", warp_compat=True,
                     deterministic=False):
+    """Reduced loss of the fused path (``(1,)`` like warp-transducer, 0-d with ``warp_compat=False``).  In the
+    reference's own joint the mean / sum over the utterances is folded into the kernels (one autograd node:
+    no reduction kernel, no broadcast multiply in the backward)."""
+    if mode == "concat_gelu" and reduction in ("mean", "sum") and enc.is_cuda and enc.dim() == 3 and dec.dim() == 3 \
+            and weight.shape[1] == enc.size(-1) + dec.size(-1):
+        if bias is None:
+            bias = weight.new_zeros(weight.shape[0])
+        penc, pdec = _loss.project_concat_gelu(enc, dec, weight, bias)
+        loss, _ = _loss._ConcatGeluRNNTLoss.apply(penc, pdec, labels, act_lens, label_lens, int(blank),
+                                                   bool(deterministic), reduction == "mean")
+        return loss if warp_compat else loss.reshape(())
     costs = joint_rnnt_costs(enc, dec, weight, bias, labels, act_lens, label_lens, blank, mode, gemm,
                              deterministic)
     return _loss._reduce(costs, reduction, warp_compat)
@@ -96,6 +107,10 @@ class JointLogits:
     def costs(self, labels, act_lens, label_lens, blank=0, deterministic=False):
         return joint_rnnt_costs(self.enc, self.dec, self.weight, self.bias, labels, act_lens,
                                 label_lens, blank, self.mode, self.gemm, deterministic)
+
+    def loss(self, labels, act_lens, label_lens, blank=0, reduction="mean", warp_compat=True, deterministic=False):
+        return joint_rnnt_loss(self.enc, self.dec, self.weight, self.bias, labels, act_lens, label_lens, blank,
+                               reduction, self.mode, self.gemm, warp_compat, deterministic)
 
     # -- tensor-like surface ------------------------------------------------------------------
     @property

@@ -174,6 +174,79 @@ class _ConcatGeluRNNT(torch.autograd.Function):
         return d_penc, d_pdec, None, None, None, None, None
 
 
+_TICKETS = {}
+
+
+def _ticket(device):
+    """Arrival counter of the fused cost reduction: one int32 that is zero between launches (the sweep re-arms
+    it).  Calls must not share a counter unless they are stream-ordered, so every call takes the next of 1024
+    slots of a per-device pool that is zeroed once -- no memset per step, nothing keyed on streams, safe under
+    CUDA-graph capture (a captured step keeps the slot it was captured with)."""
+    pool = _TICKETS.get(device.index)
+    if pool is None:
+        pool = _TICKETS[device.index] = [torch.zeros(1024, dtype=torch.int32, device=device), 0]
+    pool[1] = (pool[1] + 1) % 1024
+    return pool[0][pool[1]:pool[1] + 1]
+
+
+class _ConcatGeluRNNTLoss(torch.autograd.Function):
+    """``RNNTLoss(reduction="mean" | "sum")`` of the factorised reference joint as ONE autograd node: the
+    sweep's last-arriving utterance adds up the costs (index order: bit-reproducible), the gradient kernel
+    takes the one upstream value and scales it itself -- no reduction kernel, no broadcast multiply between
+    our kernels (rnntb200_joint_cg_fwd_loss / _bwd_loss).  Returns (loss [1], costs [B] detached)."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
+    def forward(ctx, penc, pdec, labels, act_lens, label_lens, blank, deterministic, mean):
+        B, T, V = penc.shape
+        U1 = pdec.shape[1]
+        _validate((B, T, U1, V), penc.device, labels, act_lens, label_lens, blank)
+        penc = penc.contiguous().float()
+        pdec = pdec.contiguous().float()
+        labels, act_lens, label_lens = _contiguous(labels, act_lens, label_lens)
+        dev = penc.device
+        f32 = dict(device=dev, dtype=torch.float32)
+        costs, loss = torch.empty(B, **f32), torch.empty(1, **f32)
+        lp2 = torch.empty(B, T, U1, 2, **f32)
+        lse = torch.empty(B, T, U1, **f32)
+        alpha, beta = (torch.empty(B, T, U1, device=dev, dtype=torch.int32) for _ in range(2))
+        lib = _lib.load()
+        fac_bytes = lib.rnntb200_joint_cg_factors_bytes(B, T, U1, V)
+        factors = torch.empty(fac_bytes, dtype=torch.uint8, device=dev)
+        scale = 1.0 / B if mean else 1.0
+        with torch.cuda.device(dev):
+            _lib.check(lib.rnntb200_joint_cg_fwd_loss(
+                _ptr(penc), _ptr(pdec), _ptr(labels), _ptr(act_lens), _ptr(label_lens), B, T, U1, V,
+                blank, _ptr(costs), _ptr(lp2), _ptr(lse), _ptr(alpha), _ptr(beta),
+                _ptr(factors) if fac_bytes else None, fac_bytes, _ptr(loss), _ptr(_ticket(dev)), scale,
+                _stream()), "rnntb200_joint_cg_fwd_loss")
+        ctx.save_for_backward(penc, pdec, labels, act_lens, label_lens, lse, alpha, beta, factors)
+        ctx.blank, ctx.deterministic, ctx.scale = blank, bool(deterministic), scale
+        ctx.mark_non_differentiable(costs)
+        return loss, costs
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, grad_loss, _grad_costs):
+        penc, pdec, labels, act_lens, label_lens, lse, alpha, beta, factors = ctx.saved_tensors
+        B, T, V = penc.shape
+        U1 = pdec.shape[1]
+        grad_loss = grad_loss.reshape(1).contiguous().to(torch.float32)
+        fac_bytes = factors.numel()
+        d_penc, d_pdec = torch.empty_like(penc), torch.empty_like(pdec)
+        lib = _lib.load()
+        det = int(ctx.deterministic)
+        ws_bytes = lib.rnntb200_joint_cg_bwd_workspace_bytes(B, T, U1, V, det)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=penc.device) if ws_bytes else None
+        with torch.cuda.device(penc.device):
+            _lib.check(lib.rnntb200_joint_cg_bwd_loss(
+                _ptr(penc), _ptr(pdec), _ptr(labels), _ptr(act_lens), _ptr(label_lens), B, T, U1, V,
+                ctx.blank, _ptr(lse), _ptr(alpha), _ptr(beta), _ptr(grad_loss), ctx.scale,
+                _ptr(d_penc), _ptr(d_pdec), det, _ptr(ws), ws_bytes,
+                _ptr(factors) if fac_bytes else None, fac_bytes, _stream()), "rnntb200_joint_cg_bwd_loss")
+        return d_penc, d_pdec, None, None, None, None, None, None
+
+
 class _CgProject(torch.autograd.Function):
     """penc = gelu_tanh(enc) W[:, :He]^T + b,  pdec = gelu_tanh(dec) W[:, He:]^T on the tensor cores at
     fp32 accuracy (rnntb200_joint_cg_project); backward on the tensor cores with the same bf16 hi/lo
@@ -303,6 +376,9 @@ def rnnt_costs(acts, labels, act_lens, label_lens, blank=0, deterministic=False)
 def rnnt_loss(acts, labels, act_lens, label_lens, blank=0, reduction="mean", warp_compat=True,
               deterministic=False):
     """Functional form, warp-transducer argument order (north_star)."""
+    from .joint import JointLogits  # local import: joint imports loss
+    if isinstance(acts, JointLogits) and reduction in ("mean", "sum"):
+        return acts.loss(labels, act_lens, label_lens, blank, reduction, warp_compat, deterministic)
     costs = rnnt_costs(acts, labels, act_lens, label_lens, blank, deterministic)
     return _reduce(costs, reduction, warp_compat)
 

@@ -242,3 +242,56 @@ def test_large_vocab_cfg4_generic_kernels(cuda_lib):
         ref = t[k].grad.cpu().numpy()
         np.testing.assert_allclose(fused["d_" + k], ref, err_msg=k,
                                    atol=param_atol(ref) if k in ("weight", "bias") else GRAD_ATOL)
+
+
+@pytest.mark.parametrize("reduction", ["mean", "sum"])
+def test_fused_reduction_node_matches_costs_then_reduce(cuda_lib, reduction):
+    """RNNTLoss(reduction=mean|sum) on the fused path is ONE autograd node (the sweep's last-arriving utterance
+    adds up the costs, the gradient kernel scales the one upstream value): same loss and gradients as
+    per-utterance costs followed by torch's reduction; the arrival counter re-arms itself (repeat calls and
+    CUDA-graph replays give the same bits)."""
+    d = synthetic.make_batch(5, 70, 13, 73, 128, ragged=True, seed=91, device="cuda")
+
+    def run(fused):
+        t = {k: d[k].clone().requires_grad_(True) for k in ("enc", "dec", "weight", "bias")}
+        if fused:
+            loss = rb.joint_rnnt_loss(t["enc"], t["dec"], t["weight"], t["bias"], d["labels"], d["act_lens"],
+                                      d["label_lens"], 0, reduction, deterministic=True)
+        else:
+            costs = rb.joint_rnnt_costs(t["enc"], t["dec"], t["weight"], t["bias"], d["labels"], d["act_lens"],
+                                        d["label_lens"], 0, deterministic=True)
+            loss = (costs.mean() if reduction == "mean" else costs.sum()).reshape(1)
+        (loss * 3.0).backward()  # a non-trivial upstream gradient
+        return loss.detach(), {k: v.grad for k, v in t.items()}
+
+    l0, g0 = run(False)
+    l1, g1 = run(True)
+    l2, g2 = run(True)
+    assert l1.shape == (1,) and torch.equal(l1, l2)
+    torch.testing.assert_close(l1, l0, rtol=1e-6, atol=0)
+    for k in g0:
+        assert torch.equal(g1[k], g2[k]) or k in ("weight", "bias"), k  # (projection backward sums tiles with atomics)
+        torch.testing.assert_close(g1[k], g0[k], rtol=1e-5, atol=1e-6 * float(g0[k].abs().max()) + 1e-9, msg=k)
+    # the module form takes the same route
+    h = rb.JointLogits(d["enc"], d["dec"], d["weight"], d["bias"], "concat_gelu")
+    lm = rb.RNNTLoss(0, reduction)(h, d["labels"], d["act_lens"], d["label_lens"])
+    torch.testing.assert_close(lm, l1, rtol=1e-6, atol=0)
+    # captured in a CUDA graph: replays re-arm the counter too
+    enc, dec, w, b = (d[k].clone().requires_grad_(True) for k in ("enc", "dec", "weight", "bias"))
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        rb.joint_rnnt_loss(enc, dec, w, b, d["labels"], d["act_lens"], d["label_lens"], 0, reduction).backward()
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    for t in (enc, dec, w, b):
+        t.grad = None
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        lg = rb.joint_rnnt_loss(enc, dec, w, b, d["labels"], d["act_lens"], d["label_lens"], 0, reduction)
+        lg.backward()
+    for _ in range(3):
+        graph.replay()
+        torch.cuda.synchronize()
+        torch.testing.assert_close(lg, l1, rtol=1e-6, atol=0)
+        torch.testing.assert_close(enc.grad * 3.0, g1["enc"], rtol=1e-5, atol=1e-7)
