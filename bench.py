@@ -118,6 +118,7 @@ class ClockSampler:
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self._stop = threading.Event()
+        self._active = threading.Event()
         self._thr = None
         try:
             import pynvml
@@ -146,19 +147,31 @@ class ClockSampler:
 
     def _run(self):
         while not self._stop.is_set():
-            self._sample()
-            self._stop.wait(self.period)
+            if self._active.is_set():
+                self._sample()
+                self._stop.wait(self.period)
+            else:
+                self._active.wait(0.05)
 
-    def __enter__(self):
-        if self.nv is not None:
+    def start(self):
+        """Start the sampling thread (idle until the timed region is entered).  Called BEFORE the barrier that
+        precedes the timed region, like everything else whose duration differs from rank to rank."""
+        if self.nv is not None and self._thr is None:
             self._thr = threading.Thread(target=self._run, daemon=True)
             self._thr.start()
+        return self
+
+    def __enter__(self):
+        self.start()
+        self._active.set()
         return self
 
     def __exit__(self, *exc):
         if self._thr is not None:
             self._sample()
+            self._active.clear()
             self._stop.set()
+            self._active.set()  # wake the thread so that it sees the stop flag
             self._thr.join()
 
     def summary(self):
@@ -437,7 +450,7 @@ def run_ours(args):
     # the barrier and its first timed step is rank skew that every other rank waits for in step 1's collective
     # (nvmlInit on an 8-GPU box takes milliseconds and a different number of them on every rank: round 1's
     # N = 8 lines each carried one ~3 ms first step, 0.36 instead of 0.21 ms per step over 20 steps)
-    clocks = ClockSampler(local_rank)
+    clocks = ClockSampler(local_rank).start()
     for _ in range(max(args.warmup, 3)):
         flush_buf.zero_()
         run_step()
@@ -699,7 +712,7 @@ def run_cfg5(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    clocks = ClockSampler(local_rank)  # nvmlInit before the barrier (see run_ours)
+    clocks = ClockSampler(local_rank).start()  # nvmlInit and the sampling thread before the barrier (see run_ours)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     for _ in range(max(args.warmup, 3)):
         train_step(dev_batch)
