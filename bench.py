@@ -898,12 +898,14 @@ def gpu_baseline(st, mode, cells, iters=10, warmup=3):
 
 
 def sweep_saturating(lib, st, B, T, U1, flush_buf, iters=20):
-    """The lattice sweep alone at a batch that fills the GPU: the workload's lp2 plane replicated to
-    Bs utterances (>= 512 sweeps, <= 1 GiB of lp2), timed like per_kernel (L2 flushed, CUDA events)."""
+    """The lattice sweep alone at a batch that fills the GPU (the workload's shape and lengths, Bs ~ 2048
+    utterances, <= 2 GiB of lp2), timed like per_kernel (L2 flushed, CUDA events)."""
     import torch
     from rnntransducer_b200 import _lib
     dev = st["enc"].device
-    rep = max(1, min(512 // max(B, 1), (1 << 30) // max(B * T * U1 * 8, 1)))
+    # ~2048 utterances (about nine waves of CTAs: a 2.3-wave run at B = 512 loses a fifth to its last, third-full
+    # wave), bounded by 2 GiB of lp2
+    rep = max(1, min(2048 // max(B, 1), (2 << 30) // max(B * T * U1 * 8, 1)))
     Bs = B * rep
     f32 = dict(device=dev, dtype=torch.float32)
     stream = torch.cuda.current_stream().cuda_stream
