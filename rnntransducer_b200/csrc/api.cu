@@ -1,8 +1,17 @@
 // api.cu -- extern "C" entry points of librnnt_b200.so (see include/rnnt_b200.h).
 // Argument validation only touches host-visible scalars: lengths and labels stay on the device.
+#include <cstdlib>
+
 #include "common.cuh"
 
 using namespace rnntb200;
+
+namespace rnntb200 {
+bool pdl_ok(long long work_rows) {
+    static const bool on = !(getenv("RNNTB200_PDL") && getenv("RNNTB200_PDL")[0] == '0');
+    return on && work_rows <= 16384;  // B*T frames: grids of about one wave (cfg 1-4 of BASELINE.json)
+}
+}  // namespace rnntb200
 
 namespace {
 

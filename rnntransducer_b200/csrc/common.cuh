@@ -120,6 +120,37 @@ __device__ __forceinline__ void stx4(void* x, int dt, size_t e, float4 v) {
     *reinterpret_cast<uint2*>(static_cast<uint16_t*>(x) + e) = r;
 }
 
+// ---- programmatic dependent launch (PDL) --------------------------------------------------------------
+// The cfg-2 step is a chain of dependent one-wave kernels, 25-55 us each: the gap between two of them (drain,
+// launch, the next kernel's prologue: barrier init, TMEM allocation, FIFO / ring initialisation) is a few
+// microseconds per boundary and there are six boundaries.  Every kernel of the chain therefore
+//   * calls pdl_launch_dependents() first thing -- the NEXT kernel of the stream may then be scheduled onto
+//     whatever SM resources are free while this one is still running -- and
+//   * calls pdl_wait() after its own prologue, before it touches anything its predecessor wrote
+//     (griddepcontrol.wait returns once the preceding grid has completed and its writes are visible; it is a
+//     no-op when the kernel was launched without the attribute or behind a non-PDL predecessor).
+// The attribute is only set for small problems (pdl_ok): on a multi-wave grid early-launched dependents
+// would take SM slots from the predecessor's own later waves.  RNNTB200_PDL=0 switches it off (A/B timing).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_ok(long long work_rows);  // api.cu
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 inline int status_from_cuda(cudaError_t e) {
     if (e == cudaSuccess) return RNNTB200_STATUS_SUCCESS;
     if (e == cudaErrorInvalidValue || e == cudaErrorInvalidConfiguration) return RNNTB200_STATUS_INVALID_VALUE;

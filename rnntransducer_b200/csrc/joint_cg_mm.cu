@@ -98,6 +98,8 @@ cg_factor_rows_kernel(const float* __restrict__ penc, const float* __restrict__ 
                       float* __restrict__ mA, float* __restrict__ lAb, float* __restrict__ Eb,
                       float* __restrict__ mB, float* __restrict__ lBb, float* __restrict__ lBy,
                       uint32_t* __restrict__ Ea2, uint32_t* __restrict__ Eb2) {
+    pdl_launch_dependents();
+    pdl_wait();  // penc / pdec come from the projection kernel
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows_enc + rows_dec) return;
@@ -189,12 +191,14 @@ cg_lse_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec,
     float* lAb = mA + kFT;              // [kFT]      log2 A[t][blank]
     float* sc0 = lAb + kFT;             // [2][3][kFUC]  per chunk: row maxima, log2 B[u][blank], log2 B[u][y_u]
     __shared__ int ys0[2][kFUC];
+    pdl_launch_dependents();
     const int b = blockIdx.y, t0 = blockIdx.x * kFT;
     const int Tb = len_T(act_lens, b, T), Ub = len_U(label_lens, b, U1);
     if (t0 >= Tb) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, q = lane & 3;
     const int mt = warp & 1, nq = warp >> 1;
+    pdl_wait();  // the factor planes come from cg_factor_rows_kernel
 
     // everything chunk c needs travels as one cp.async group (+ plain stores of the labels) into
     // buffer c & 1, issued one chunk ahead
@@ -348,6 +352,8 @@ cg_grad_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec
     const int nt0 = (warp >> 1) * NTW;       // first 8-column tile of this warp (column quarter)
     const int n_nt = Vk >> 3;                // column tiles in use
     constexpr uint32_t kOnes = 0x3f803f80u;  // (1.0, 1.0) in bf16: selects hi + lo of a packed operand
+    pdl_launch_dependents();
+    pdl_wait();  // nothing in global memory is read OR written before the sweep (the predecessor) has finished
 
     if (t0 >= Tb) {  // tile entirely in the padding: exact zeros
         for (int i = tid; i < kGT2 * V; i += kGThreads) {
@@ -613,9 +619,9 @@ int launch_grad_mm(const float* penc, const float* pdec, const CgFactors& F, con
     cudaError_t e = cudaFuncSetAttribute(cg_grad_mm_kernel<NTW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return status_from_cuda(e);
     dim3 grid((T + kGT2 - 1) / kGT2, B);
-    cg_grad_mm_kernel<NTW><<<grid, kGThreads, smem, stream>>>(penc, pdec, F, labels, act_lens, label_lens, T, U1, V, Vk, Vs,
-                                                       blank, lse, alpha, beta, grad_costs, d_penc, d_pdec, partial);
-    return launch_status();
+    e = launch_pdl(pdl_ok((long long)B * T), cg_grad_mm_kernel<NTW>, grid, dim3(kGThreads), smem, stream, penc, pdec, F, labels,
+                   act_lens, label_lens, T, U1, V, Vk, Vs, blank, lse, alpha, beta, grad_costs, d_penc, d_pdec, partial);
+    return e == cudaSuccess ? launch_status() : status_from_cuda(e);
 }
 
 }  // namespace
@@ -651,10 +657,10 @@ int launch_cg_factor_rows(const float* penc, const float* pdec, const int32_t* l
                           int B, int T, int U1, int V, int blank, const CgFactors& F, cudaStream_t stream) {
     const int rows = B * (T + U1);
     if (rows == 0) return RNNTB200_STATUS_SUCCESS;
-    cg_factor_rows_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(penc, pdec, labels, label_lens, B * T, B * U1, U1, V,
-                                                             F.Vk, blank, F.Ea, F.mA, F.lAb, F.Eb, F.mB, F.lBb, F.lBy,
-                                                             F.Ea2, F.Eb2);
-    return launch_status();
+    const cudaError_t e = launch_pdl(pdl_ok((long long)B * T), cg_factor_rows_kernel, dim3((rows + 7) / 8), dim3(256), (size_t)0,
+                                     stream, penc, pdec, labels, label_lens, B * T, B * U1, U1, V, F.Vk, blank, F.Ea, F.mA, F.lAb,
+                                     F.Eb, F.mB, F.lBb, F.lBy, F.Ea2, F.Eb2);
+    return e == cudaSuccess ? launch_status() : status_from_cuda(e);
 }
 
 int launch_cg_lse_mm(const float* penc, const float* pdec, const CgFactors& F, const int32_t* labels,
@@ -665,9 +671,9 @@ int launch_cg_lse_mm(const float* penc, const float* pdec, const CgFactors& F, c
     cudaError_t e = cudaFuncSetAttribute(cg_lse_mm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return status_from_cuda(e);
     dim3 grid((T + kFT - 1) / kFT, B);
-    cg_lse_mm_kernel<<<grid, kFThreads, smem, stream>>>(penc, pdec, F, labels, act_lens, label_lens, T, U1, V, Vk, Vs, blank,
-                                                  lp2, lse);
-    return launch_status();
+    e = launch_pdl(pdl_ok((long long)B * T), cg_lse_mm_kernel, grid, dim3(kFThreads), smem, stream, penc, pdec, F, labels, act_lens,
+                   label_lens, T, U1, V, Vk, Vs, blank, lp2, lse);
+    return e == cudaSuccess ? launch_status() : status_from_cuda(e);
 }
 
 int launch_cg_grad_mm(const float* penc, const float* pdec, const CgFactors& F, const int32_t* labels,

@@ -1072,6 +1072,7 @@ lattice_sweep_tp_kernel(const float2* __restrict__ lp2, const int32_t* __restric
                         int32_t* __restrict__ beta, float* __restrict__ costs, float* __restrict__ ll_alpha,
                         int xedge_slots, ReduceArgs R) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    pdl_launch_dependents();
     TpWarp* tw = reinterpret_cast<TpWarp*>(smem_raw);
     __shared__ int2 edge[kTpEdge][8];  // column w: written by warp w; column 4 stays "zero" (warp 0 of band 0)
     __shared__ int xdone_slot;
@@ -1094,6 +1095,7 @@ lattice_sweep_tp_kernel(const float2* __restrict__ lp2, const int32_t* __restric
         for (int i = threadIdx.x; i < xedge_slots; i += blockDim.x) X.xedge[i] = make_int2(kTpNoValue, kTpNoValue);
         cluster_barrier();  // no CTA may be written to before it has initialised its shared memory
     }
+    pdl_wait();  // lp2 comes from the front-end kernel; nothing in global memory is touched before this point
     if (blockIdx.y == 0)
         tp_sweep<0, kMulti, kCluster>(tw[warp], edge, lp2, Tb, Ub, T, U1, b, alpha, costs, ll_alpha, warp, nw, lane, X, R);
     else
@@ -1111,11 +1113,15 @@ int launch_tp(const float2* lp2, const int32_t* act_lens, const int32_t* label_l
         if (warps == 1) {
             auto kern = lattice_sweep_tp_kernel<false, false>;
             if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-            kern<<<dim3(B, 2), 32, smem, stream>>>(lp2, act_lens, label_lens, T, U1, alpha, beta, costs, ll_alpha, 0, R);
+            if (launch_pdl(pdl_ok((long long)B * T), kern, dim3(B, 2), dim3(32), smem, stream, lp2, act_lens, label_lens, T, U1, alpha,
+                           beta, costs, ll_alpha, 0, R) != cudaSuccess)
+                return status_from_cuda(cudaGetLastError());
         } else {
             auto kern = lattice_sweep_tp_kernel<true, false>;
             if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-            kern<<<dim3(B, 2), warps * 32, smem, stream>>>(lp2, act_lens, label_lens, T, U1, alpha, beta, costs, ll_alpha, 0, R);
+            if (launch_pdl(pdl_ok((long long)B * T), kern, dim3(B, 2), dim3(warps * 32), smem, stream, lp2, act_lens, label_lens, T, U1,
+                           alpha, beta, costs, ll_alpha, 0, R) != cudaSuccess)
+                return status_from_cuda(cudaGetLastError());
         }
         return launch_status();
     }

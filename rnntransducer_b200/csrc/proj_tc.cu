@@ -69,6 +69,7 @@ __global__ void split_weight_kernel(const float* __restrict__ w, int V, int He, 
                                     __nv_bfloat16* __restrict__ e_hi, __nv_bfloat16* __restrict__ e_lo,
                                     __nv_bfloat16* __restrict__ d_hi, __nv_bfloat16* __restrict__ d_lo) {
     const int ldw = He + Hd;
+    pdl_launch_dependents();
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < V * ldw; i += gridDim.x * blockDim.x) {
         const int v = i / ldw, k = i - v * ldw;
         const float x = w[i];
@@ -89,6 +90,7 @@ proj_tc_kernel(const __grid_constant__ CUtensorMap w0_hi, const __grid_constant_
                const __grid_constant__ CUtensorMap w1_hi, const __grid_constant__ CUtensorMap w1_lo,
                Problem p0, Problem p1, int V, int NB) {
     extern __shared__ __align__(128) unsigned char smem[];
+    pdl_launch_dependents();
     const SmemP L = smem_layout_p(NB);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool second = (int)blockIdx.x >= p0.tiles;
@@ -125,6 +127,7 @@ proj_tc_kernel(const __grid_constant__ CUtensorMap w0_hi, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    pdl_wait();  // the prologue above overlapped the predecessor (the weight split); its output is read from here on
 
     if (warp < kProducerWarps) {
         // ===== A producers: thread = (row r, K chunks kc0 and kc0+4 of each block) =====
@@ -331,8 +334,9 @@ int launch_proj_tc(const void* enc, const void* dec, int x_dtype, const float* w
     const SmemP L = smem_layout_p(NB);
     cudaError_t e = cudaFuncSetAttribute(proj_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
     if (e != cudaSuccess) return status_from_cuda(e);
-    proj_tc_kernel<<<p0.tiles + p1.tiles, kThreads, L.total, stream>>>(m[0], m[1], m[2], m[3], p0, p1, V, NB);
-    return launch_status();
+    e = launch_pdl(pdl_ok(rows_enc), proj_tc_kernel, dim3(p0.tiles + p1.tiles), dim3(kThreads), (size_t)L.total, stream, m[0], m[1],
+                   m[2], m[3], p0, p1, V, NB);
+    return e == cudaSuccess ? launch_status() : status_from_cuda(e);
 }
 
 }  // namespace rnntb200

@@ -76,6 +76,7 @@ proj_tc_bwd_kernel(const __grid_constant__ CUtensorMap w0_hi, const __grid_const
                    ProblemB p0, ProblemB p1, int V, int NB, float* __restrict__ d_weight, int ldw,
                    float* __restrict__ d_bias) {
     extern __shared__ __align__(128) unsigned char smem[];
+    pdl_launch_dependents();
     const SmemPB L = smem_layout_pb(NB);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool second = (int)blockIdx.x >= p0.tiles;
@@ -126,6 +127,7 @@ proj_tc_bwd_kernel(const __grid_constant__ CUtensorMap w0_hi, const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    pdl_wait();  // d_penc / d_pdec of the gradient kernel are read from here on
 
     if (warp < 8) {
         // ===== producers =====
@@ -383,9 +385,9 @@ int launch_proj_tc_bwd(const void* enc, const void* dec, int x_dtype, const floa
     const SmemPB L = smem_layout_pb(NB);
     cudaError_t e = cudaFuncSetAttribute(proj_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
     if (e != cudaSuccess) return status_from_cuda(e);
-    proj_tc_bwd_kernel<<<p0.tiles + p1.tiles, kThreads, L.total, stream>>>(m[0], m[1], m[2], m[3], p0, p1, V, NB,
-                                                                           d_weight, ldw, d_bias);
-    return launch_status();
+    e = launch_pdl(pdl_ok(rows_enc), proj_tc_bwd_kernel, dim3(p0.tiles + p1.tiles), dim3(kThreads), (size_t)L.total, stream, m[0],
+                   m[1], m[2], m[3], p0, p1, V, NB, d_weight, ldw, d_bias);
+    return e == cudaSuccess ? launch_status() : status_from_cuda(e);
 }
 
 }  // namespace rnntb200
