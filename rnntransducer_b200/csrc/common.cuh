@@ -129,8 +129,10 @@ __device__ __forceinline__ void stx4(void* x, int dt, size_t e, float4 v) {
 //   * calls pdl_wait() after its own prologue, before it touches anything its predecessor wrote
 //     (griddepcontrol.wait returns once the preceding grid has completed and its writes are visible; it is a
 //     no-op when the kernel was launched without the attribute or behind a non-PDL predecessor).
-// The attribute is only set for small problems (pdl_ok): on a multi-wave grid early-launched dependents
-// would take SM slots from the predecessor's own later waves.  RNNTB200_PDL=0 switches it off (A/B timing).
+// MEASURED SLOWER (cfg 2: 0.209 vs 0.175 ms per step) -- early-resident CTAs of the next kernel disturb the running
+// one more than the hidden gap is worth -- so the attribute is OFF unless RNNTB200_PDL=1; without it the two
+// instructions are no-ops.  (With it, only small problems: on a multi-wave grid early-launched dependents
+// would also take SM slots from the predecessor's own later waves.)
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 bool pdl_ok(long long work_rows);  // api.cu
