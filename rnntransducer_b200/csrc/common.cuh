@@ -134,7 +134,11 @@ __device__ __forceinline__ void stx4(void* x, int dt, size_t e, float4 v) {
 // instructions are no-ops.  (With it, only small problems: on a multi-wave grid early-launched dependents
 // would also take SM slots from the predecessor's own later waves.)
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() {
+#ifdef RNNTB200_PDL_EARLY  // (the measured-slower variant: dependents become resident while this kernel still runs)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
 bool pdl_ok(long long work_rows);  // api.cu
 
 template <typename... KArgs, typename... Args>
