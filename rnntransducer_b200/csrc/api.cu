@@ -8,10 +8,11 @@ using namespace rnntb200;
 
 namespace rnntb200 {
 bool pdl_ok(long long work_rows) {
-    // Measured (round 2, visit I): OFF is faster.  cfg 2 step 0.173-0.177 ms without / 0.209 ms with the attribute,
-    // cfg 1 0.095 / 0.102, cfg 3 0.419 / 0.417: the early-resident CTAs of the next kernel cost the running one more
-    // than the hidden launch gap and prologue are worth.  Kept behind RNNTB200_PDL=1 as an experiment.
-    static const bool on = getenv("RNNTB200_PDL") && getenv("RNNTB200_PDL")[0] == '1';
+    // Measured (round 2, visits I and J, cfg-2 step):  no attribute 0.177 ms;  attribute + trigger at kernel entry
+    // 0.209 ms (early-resident CTAs of the next kernel disturb the running one);  attribute, no explicit trigger
+    // 0.173 ms (the next kernel is pre-launched and starts the moment its predecessor's last CTA exits) -> the
+    // last one is the default.  RNNTB200_PDL=0 switches the attribute off.
+    static const bool on = !(getenv("RNNTB200_PDL") && getenv("RNNTB200_PDL")[0] == '0');
     return on && work_rows <= 16384;  // B*T frames: grids of about one wave (cfg 1-4 of BASELINE.json)
 }
 }  // namespace rnntb200

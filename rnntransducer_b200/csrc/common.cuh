@@ -121,18 +121,16 @@ __device__ __forceinline__ void stx4(void* x, int dt, size_t e, float4 v) {
 }
 
 // ---- programmatic dependent launch (PDL) --------------------------------------------------------------
-// The cfg-2 step is a chain of dependent one-wave kernels, 25-55 us each: the gap between two of them (drain,
-// launch, the next kernel's prologue: barrier init, TMEM allocation, FIFO / ring initialisation) is a few
-// microseconds per boundary and there are six boundaries.  Every kernel of the chain therefore
-//   * calls pdl_launch_dependents() first thing -- the NEXT kernel of the stream may then be scheduled onto
-//     whatever SM resources are free while this one is still running -- and
-//   * calls pdl_wait() after its own prologue, before it touches anything its predecessor wrote
-//     (griddepcontrol.wait returns once the preceding grid has completed and its writes are visible; it is a
-//     no-op when the kernel was launched without the attribute or behind a non-PDL predecessor).
-// MEASURED SLOWER (cfg 2: 0.209 vs 0.175 ms per step) -- early-resident CTAs of the next kernel disturb the running
-// one more than the hidden gap is worth -- so the attribute is OFF unless RNNTB200_PDL=1; without it the two
-// instructions are no-ops.  (With it, only small problems: on a multi-wave grid early-launched dependents
-// would also take SM slots from the predecessor's own later waves.)
+// The cfg-2 step is a chain of dependent one-wave kernels, 25-55 us each, and the gap between two of them is a
+// microsecond or two per boundary.  The kernels of the chain are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization and call pdl_wait() (griddepcontrol.wait) after their own
+// prologue, before they touch anything in global memory: the next kernel is then PRE-LAUNCHED and starts the
+// moment its predecessor's last CTA exits (-4 us per cfg-2 step, measured).  griddepcontrol.wait returns once
+// the preceding grid has completed and its writes are visible; it is a no-op when the kernel was launched
+// without the attribute or behind a non-PDL predecessor.  An explicit early trigger
+// (griddepcontrol.launch_dependents at kernel entry, -DRNNTB200_PDL_EARLY) was measured 30 us SLOWER per step --
+// the next kernel's early-resident CTAs disturb the running one -- and is compiled out.  The attribute is only
+// set for small problems (pdl_ok); RNNTB200_PDL=0 switches it off (A/B timing).
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() {
 #ifdef RNNTB200_PDL_EARLY  // (the measured-slower variant: dependents become resident while this kernel still runs)
