@@ -99,6 +99,7 @@ __device__ __forceinline__ void seg_store(const CommArgs& A, int q, float4 v) {
 __global__ void __launch_bounds__(kCommThreads)
 peer_allreduce_kernel(CommArgs A) {
     __shared__ unsigned int s_step;
+    pdl_wait();  // the gradients come from the step's last kernel
     const int c = blockIdx.x, tid = threadIdx.x;
     CommHeader* own = reinterpret_cast<CommHeader*>(A.peer[A.rank]);
     if (tid == 0) s_step = own->step[c] + 1;
@@ -221,8 +222,9 @@ RNNTB200_API int rnntb200_comm_allreduce(void* const* peer_ptrs, int rank, int w
     if (total > max_floats || total > 0x3fffffffu) return RNNTB200_STATUS_INVALID_VALUE;
     A.n_seg = n_segments, A.rank = rank, A.world = world, A.scale = scale;
     A.slot_floats = slot_floats_for(max_floats);
-    peer_allreduce_kernel<<<kCommCtas, kCommThreads, 0, (cudaStream_t)stream>>>(A);
-    return launch_status();
+    const cudaError_t e = launch_pdl(pdl_ok(1), peer_allreduce_kernel, dim3(kCommCtas), dim3(kCommThreads), (size_t)0,
+                                     (cudaStream_t)stream, A);
+    return e == cudaSuccess ? launch_status() : status_from_cuda(e);
 }
 
 }  // extern "C"

@@ -70,6 +70,7 @@ __global__ void split_weight_kernel(const float* __restrict__ w, int V, int He, 
                                     __nv_bfloat16* __restrict__ d_hi, __nv_bfloat16* __restrict__ d_lo) {
     const int ldw = He + Hd;
     pdl_launch_dependents();
+    pdl_wait();  // the previous step's projection backward may still be reading the split this kernel overwrites
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < V * ldw; i += gridDim.x * blockDim.x) {
         const int v = i / ldw, k = i - v * ldw;
         const float x = w[i];
@@ -312,8 +313,8 @@ int proj_tc_prepare(const float* weight, int V, int He, int Hd, int NB, void* wo
     __nv_bfloat16* d_hi = reinterpret_cast<__nv_bfloat16*>(ws + 2 * align256((size_t)V * He * 2));
     __nv_bfloat16* d_lo = reinterpret_cast<__nv_bfloat16*>(ws + 2 * align256((size_t)V * He * 2) + align256((size_t)V * Hd * 2));
     if (!already_split)
-        split_weight_kernel<<<std::min((V * (He + Hd) + 255) / 256, 592), 256, 0, stream>>>(weight, V, He, Hd, e_hi,
-                                                                                           e_lo, d_hi, d_lo);
+        (void)launch_pdl(pdl_ok(1), split_weight_kernel, dim3(std::min((V * (He + Hd) + 255) / 256, 592)), dim3(256), (size_t)0,
+                         stream, weight, V, He, Hd, e_hi, e_lo, d_hi, d_lo);
     if (!make_w_map(&maps[0], e_hi, V, He, NB) || !make_w_map(&maps[1], e_lo, V, He, NB) ||
         !make_w_map(&maps[2], d_hi, V, Hd, NB) || !make_w_map(&maps[3], d_lo, V, Hd, NB))
         return RNNTB200_STATUS_EXECUTION_FAILED;

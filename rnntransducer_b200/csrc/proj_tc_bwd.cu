@@ -372,9 +372,13 @@ int launch_proj_tc_bwd(const void* enc, const void* dec, int x_dtype, const floa
                        int workspace_holds_split, cudaStream_t stream) {
     if (!proj_tc_bwd_supported(V, He, Hd)) return RNNTB200_STATUS_INVALID_VALUE;
     const int ldw = He + Hd;
-    if (cudaMemsetAsync(d_weight, 0, (size_t)V * ldw * sizeof(float), stream) != cudaSuccess ||
-        cudaMemsetAsync(d_bias, 0, (size_t)V * sizeof(float), stream) != cudaSuccess)
+    if (d_bias == d_weight + (size_t)V * ldw) {  // one flat gradient buffer (loss.py allocates it so): one memset node
+        if (cudaMemsetAsync(d_weight, 0, ((size_t)V * ldw + V) * sizeof(float), stream) != cudaSuccess)
+            return RNNTB200_STATUS_MEMOPS_FAILED;
+    } else if (cudaMemsetAsync(d_weight, 0, (size_t)V * ldw * sizeof(float), stream) != cudaSuccess ||
+               cudaMemsetAsync(d_bias, 0, (size_t)V * sizeof(float), stream) != cudaSuccess) {
         return RNNTB200_STATUS_MEMOPS_FAILED;
+    }
     const int NB = ((V + 15) / 16) * 16;
     CUtensorMap m[4];
     int st = proj_tc_prepare(weight, V, He, Hd, NB, workspace, workspace_bytes, workspace_holds_split != 0, m, stream);

@@ -286,7 +286,8 @@ class _CgProject(torch.autograd.Function):
         if ws_bytes > 0:  # tensor-core backward (same hi/lo split arithmetic as the forward)
             d_penc, d_pdec = d_penc.contiguous().float(), d_pdec.contiguous().float()
             d_enc, d_dec = torch.empty_like(enc), torch.empty_like(dec)
-            d_w, d_b = torch.empty_like(weight), torch.empty(V, device=enc.device, dtype=torch.float32)
+            flat = torch.empty(weight.numel() + V, device=enc.device, dtype=torch.float32)  # one buffer: one memset
+            d_w, d_b = flat[:weight.numel()].view_as(weight), flat[weight.numel():]
             reuse = ws_fwd.numel() >= ws_bytes
             ws = ws_fwd if reuse else torch.empty(ws_bytes, dtype=torch.uint8, device=enc.device)
             with torch.cuda.device(enc.device):
