@@ -82,7 +82,7 @@ def joint_rnnt_loss(enc, dec, weight, bias, labels, act_lens, label_lens, blank=
     reference's own joint the mean / sum over the utterances is folded into the kernels (one autograd node:
     no reduction kernel, no broadcast multiply in the backward)."""
     if mode == "concat_gelu" and reduction in ("mean", "sum") and enc.is_cuda and enc.dim() == 3 and dec.dim() == 3 \
-            and weight.shape[1] == enc.size(-1) + dec.size(-1):
+            and enc.shape[0] > 0 and weight.shape[1] == enc.size(-1) + dec.size(-1):
         if bias is None:
             bias = weight.new_zeros(weight.shape[0])
         penc, pdec = _loss.project_concat_gelu(enc, dec, weight, bias)
