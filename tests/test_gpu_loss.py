@@ -193,15 +193,48 @@ def test_lattice_sweep_abi_alpha_beta(cuda_lib, oracle_lib):
 
 @pytest.mark.parametrize("U", [0, 1, 30, 31, 32, 62, 63, 64, 94, 95, 96, 126, 127, 128, 160, 200, 520, 800])
 def test_sweep_warp_boundaries(cuda_lib, oracle_lib, U):
-    """Label lengths around every multiple of 32 and in every regime of the sweep dispatch: one / two /
-    three chain warps of the warp-specialised kernel, four warps (single-role kernel), bands of two
-    (U1 <= 512) and of three chain warps in a thread-block cluster, and the single-role cluster kernel
-    beyond; T shorter and longer than the helpers' windows, ragged lengths included."""
+    """Label lengths around every multiple of 32 and in every regime of the sweep dispatch: one to four warps
+    of the self-contained sweep in one CTA, bands of two / three / four warps in a thread-block cluster beyond
+    (U1 <= 512 / 768 / 1024); T shorter and longer than the FIFOs, ragged lengths included.  (The round's GPU
+    visits ran the same test under RNNTB200_SWEEP=ws and RNNTB200_SWEEP_BW=2,3,4 as well.)"""
     for T in (3, 45, 150):
         d = synthetic.make_dense_logits(3, T, U, 6, ragged=True, seed=100 + U + T)
         r32, r64 = oracle_pair(oracle_lib, d)
         costs, grads = run_dense(d["logits"], d["labels"], d["act_lens"], d["label_lens"])
         check_against_oracles(costs, grads, r32, r64)
+
+
+def test_sweep_many_utterances(cuda_lib, oracle_lib):
+    """Several waves of CTAs (B = 400 utterances, two warps each): every utterance against the oracle, and the
+    fused mean over the batch against the sum of the per-utterance costs."""
+    d = synthetic.make_dense_logits(400, 24, 40, 5, ragged=True, seed=77)
+    r32, r64 = oracle_pair(oracle_lib, d)
+    costs, grads = run_dense(d["logits"], d["labels"], d["act_lens"], d["label_lens"])
+    check_against_oracles(costs, grads, r32, r64)
+
+
+def test_out_of_range_lengths_and_labels_are_clamped_identically(cuda_lib):
+    """Nobody validates device-side lengths / labels on the hot path; every kernel clamps them the same way
+    (csrc/common.cuh), so garbage gives the result of the clamped inputs -- finite, no out-of-bounds access --
+    and RNNTLoss(check_lengths=True) raises instead."""
+    d = synthetic.make_batch(4, 30, 7, 11, 128, ragged=True, seed=8, device="cuda")
+    bad = {k: v.clone() for k, v in d.items()}
+    bad["act_lens"][1], bad["act_lens"][2] = 0, 1000       # -> 1, T
+    bad["label_lens"][0], bad["label_lens"][3] = -5, 99     # -> 0, U
+    bad["labels"][2, 0], bad["labels"][2, 1] = 500, -3      # -> V-1, 0
+    good = {k: v.clone() for k, v in d.items()}
+    good["act_lens"][1], good["act_lens"][2] = 1, 30
+    good["label_lens"][0], good["label_lens"][3] = 0, 7
+    good["labels"][2, 0], good["labels"][2, 1] = 10, 0
+    run = lambda x: rb.joint_rnnt_costs(x["enc"], x["dec"], x["weight"], x["bias"], x["labels"], x["act_lens"],
+                                        x["label_lens"], 0, deterministic=True)
+    a, b = run(bad), run(good)
+    assert torch.isfinite(a).all() and torch.equal(a, b)
+    logits = rb.joint_dense(d["enc"], d["dec"], d["weight"], d["bias"])
+    assert torch.equal(rb.rnnt_costs(logits, bad["labels"], bad["act_lens"], bad["label_lens"]),
+                       rb.rnnt_costs(logits, good["labels"], good["act_lens"], good["label_lens"]))
+    with pytest.raises(RuntimeError, match="out of range|labels must be"):
+        rb.RNNTLoss(0, "mean", check_lengths=True)(logits, bad["labels"], bad["act_lens"], bad["label_lens"])
 
 
 def test_long_lattice_matches_oracle(cuda_lib, oracle_lib):
