@@ -4,34 +4,33 @@
 // ComputeAlphasBetasCosts -- written from the recursion, not from
 // either implementation.
 //
-// Mapping.  ONE launch, grid (B, 2): blockIdx.y = 0 sweeps alpha, 1 sweeps beta, so both
-// directions of every utterance are in flight together.  One thread per label position walks the
-// anti-diagonals d = t + u; the working diagonal lives in registers and is handed to the u+1
-// neighbour with warp shuffles.  A CTA has W = ceil(U1/32) warps; warp w runs kLag diagonals
-// behind warp w-1, so the value crossing a warp boundary is produced kLag+1 steps before it is
-// consumed and travels through a small shared-memory ring that needs a block barrier only every
-// kLag steps (not one per diagonal).
-//
-// Arithmetic.  The recursion is linear in the probability domain,
+// Common to every kernel of this file.  ONE launch, grid (B, 2): blockIdx.y = 0 sweeps alpha, 1 sweeps beta,
+// so both directions of every utterance are in flight together.  One thread per label position walks the
+// anti-diagonals d = t + u; the working diagonal lives in registers and is handed to the u+1 neighbour with
+// warp shuffles; warp w runs a few diagonals behind warp w-1 and the value crossing a warp boundary travels
+// through a small shared-memory ring.  The recursion is linear in the probability domain,
 //     alpha(t,u) = alpha(t-1,u) * P_blank(t-1,u) + alpha(t,u-1) * P_label(t,u-1),
-// and is evaluated there with every quantity held as (mantissa in [1,2), integer exponent): two
-// FMULs, one FFMA and a handful of integer ops on the dependent chain, no MUFU, no overflow or
-// underflow in the recursion itself for any lattice size (the STORED planes hold |log2| < 32768, see cost_of), ~1e-7 relative error per step (the log-domain form costs two
-// MUFUs per step on the chain and loses ulp(|alpha|) ~ 1e-4 per step once |alpha| reaches 10^3).
-//
-// Storage.  alpha / beta planes are written in a 32-bit wide-exponent float ("e16m16", see
-// common.cuh): signed 16-bit binary exponent in the high half, 16 mantissa bits in the low half.
-// 4 bytes per cell like fp32, 2^-17 relative precision at ANY magnitude (|log2| < 32768), so the
-// occupancy alpha * beta / P(y|x) the gradient needs is formed from exact integer exponents
+// and is evaluated there with every quantity held as (fp32 mantissa, integer exponent): no MUFU on the chain,
+// no overflow or underflow in the recursion for any lattice size, ~1e-7 relative error per step (the
+// log-domain form costs two MUFUs per step on the chain and loses ulp(|alpha|) ~ 1e-4 per step once |alpha|
+// reaches 10^3).  alpha / beta planes are written in a 32-bit wide-exponent float ("e16m16", common.cuh):
+// signed 16-bit binary exponent in the high half, 16 mantissa bits in the low half -- 4 bytes per cell like
+// fp32, 2^-17 relative precision at ANY magnitude (|log2| < 32768; beyond, the cost is reported as +inf, see
+// cost_of), so the occupancy alpha * beta / P(y|x) the gradient needs is formed from exact integer exponents
 // instead of cancelling three fp32 logs of magnitude 10^3.  beta[b,0,0] is P(y|x) in that format.
 //
-// Loads.  The (lp_blank, lp_label) pair of a cell is one 8-byte cp.async into a per-thread slot
-// of a shared-memory ring, issued kDepth-1 diagonals ahead (the loads do not depend on the
-// recursion), so HBM latency is off the dependent chain.
-//
-// Label sequences of up to 128 positions run the warp-specialised variant in the second half of
-// this file (chain warps that only do the recursion + helper warps for everything else); the
-// kernel described above serves longer sequences, spread over a thread-block cluster.
+// The file, top to bottom:
+//   1. the single-role sweep of round 1 (`lattice_sweep_kernel`: one warp per 32 positions does everything,
+//      every lane touches its own lattice row) -- last fall-back, RNNTB200_SWEEP_LEGACY;
+//   2. the warp-specialised sweep of round 1 (`lattice_sweep_ws_kernel`: a chain warp + loader + two converters
+//      + consumer per 32 positions, mbarrier rings, cluster bands) -- fall-back, RNNTB200_SWEEP=ws;
+//   3. the decoupled (mantissa | exponent) recursion both newer kernels use (`ws_chain`, `tp_sweep`): the
+//      exponents follow an integer max-plus recurrence that runs one step ahead of the mantissas;
+//   4. the fused reduction of the costs (last-arriving utterance sums them in index order);
+//   5. THE DEFAULT: the self-contained sweep (`lattice_sweep_tp_kernel`): one warp per 32 positions again, but
+//      with row-wise global accesses through two lane-private FIFOs, 24 KB per warp, thread-block-cluster
+//      bands for long label sequences;
+//   6. the dispatch (`launch_lattice_sweep`) with the measurements that decide it.
 #include <cstdlib>
 
 #include "tc_common.cuh"
