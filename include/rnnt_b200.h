@@ -152,7 +152,7 @@ RNNTB200_API int rnntb200_joint_cg_project_bwd(const void* enc, const void* dec,
                                   int workspace_holds_split, void* stream);
 
 /* `factors` (rnntb200_joint_cg_factors_bytes, 16-byte aligned; the query returns 0 and NULL is
- * accepted for V > 128) receives the factor planes of this step -- 2^((P - rowmax) log2 e) of both
+ * accepted only when RNNTB200_CG_GENERIC selects the generic per-cell kernels) receives the factor planes of this step -- 2^((P - rowmax) log2 e) of both
  * projections plus per-row scalars, computed once instead of per frame tile.  The forward (or
  * rnntb200_joint_cg_logprobs) writes them; rnntb200_joint_cg_bwd for the same penc / pdec reads
  * them: like lse / alpha / beta they are state saved between the two passes, owned by the caller. */

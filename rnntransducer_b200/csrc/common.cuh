@@ -179,7 +179,7 @@ int launch_dense_grad(const void* logits, int dtype, const int32_t* labels, cons
                       const float* lse, const int32_t* alpha, const int32_t* beta,
                       const float* grad_costs, void* grad_logits, cudaStream_t stream);
 
-// Factor planes of the factorised concat-GELU joint (joint_cg_mm.cu), V <= 128: written once per
+// Factor planes of the factorised concat-GELU joint (joint_cg_mm.cu): written once per
 // step by the forward into caller memory (cg_factors_bytes), read by the cell kernels of both passes.
 struct CgFactors {
     float* Ea;   // [B*T][Vk]   2^((P_enc - rowmax) log2e), pad columns zero
@@ -193,7 +193,7 @@ struct CgFactors {
     float* lBy;  // [B*U1]  log2 Eb[u][y_u], 0 for u >= U_b
     int Vk;      // V rounded up to a multiple of 8
 };
-size_t cg_factors_bytes(int B, int T, int U1, int V);  // 0: V > 128, the generic kernels need no factors
+size_t cg_factors_bytes(int B, int T, int U1, int V);  // 0: RNNTB200_CG_GENERIC, the generic kernels need no factors
 
 // factors == nullptr is allowed only when cg_factors_bytes(...) == 0
 int launch_cg_lse(const float* penc, const float* pdec, const int32_t* labels, const int32_t* act_lens,

@@ -13,7 +13,7 @@
 
 namespace rnntb200 {
 
-// joint_cg_mm.cu: the factorised (exp(a+b) = exp(a) exp(b)) kernels used for V <= 128
+// joint_cg_mm.cu: the factorised (exp(a+b) = exp(a) exp(b)) kernels used by default
 bool cg_mm_supported(int V);
 int cg_mm_tile_rows();
 CgFactors cg_factors_layout(void* mem, int B, int T, int U1, int V);

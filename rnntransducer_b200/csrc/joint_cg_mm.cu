@@ -26,7 +26,14 @@
 // with S < 2^-66 (logit ranges beyond ~45 nats in BOTH rows, never seen with real activations) take
 // an exact per-cell path instead (log-sum-exp with the true maximum / explicit V-wide gradient).
 //
-// Used for V <= 128; larger vocabularies run the generic kernels of joint_cg.cu.
+// V <= 128: a CTA holds whole rows of the factor planes.  V > 128 ("wide"): the same products in
+// 128-column chunks -- the partition accumulates over the chunks in the MMA accumulators (the vocabulary is
+// its K dimension), the gradient takes one CTA per (utterance, 32 frames, 128 columns): the vocabulary is its
+// N dimension and the per-cell scalars are cheap enough to recompute per chunk.  With RNNTB200_CG_GENERIC
+// set: the generic per-cell kernels of joint_cg.cu (one exponential per cell and column; kept as an
+// independent evaluation for the tests).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace rnntb200 {
@@ -141,6 +148,47 @@ cg_factor_rows_kernel(const float* __restrict__ penc, const float* __restrict__ 
     }
 }
 
+// The same for rows wider than 128 columns: two passes over the (L2-resident) row instead of registers.
+__global__ void __launch_bounds__(256)
+cg_factor_rows_wide_kernel(const float* __restrict__ penc, const float* __restrict__ pdec,
+                           const int32_t* __restrict__ labels, const int32_t* __restrict__ label_lens, int rows_enc,
+                           int rows_dec, int U1, int V, int Vk, int blank, float* __restrict__ Ea,
+                           float* __restrict__ mA, float* __restrict__ lAb, float* __restrict__ Eb,
+                           float* __restrict__ mB, float* __restrict__ lBb, float* __restrict__ lBy,
+                           uint32_t* __restrict__ Ea2, uint32_t* __restrict__ Eb2) {
+    pdl_launch_dependents();
+    pdl_wait();  // penc / pdec come from the projections
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows_enc + rows_dec) return;
+    const bool is_dec = row >= rows_enc;
+    const int r = is_dec ? row - rows_enc : row;
+    const float* x = (is_dec ? pdec : penc) + (size_t)r * V;
+    float* e = (is_dec ? Eb : Ea) + (size_t)r * Vk;
+    uint32_t* e2 = (is_dec ? Eb2 : Ea2) + (size_t)r * Vk;
+    float m = -INFINITY;
+    for (int v = lane; v < V; v += 32) m = fmaxf(m, __ldg(x + v));
+    m = warp_max(m);
+    for (int v = lane; v < Vk; v += 32) {
+        const float ev = v < V ? fast_ex2((__ldg(x + v) - m) * kLog2e) : 0.f;
+        e[v] = ev;
+        e2[v] = pack_hilo(ev);
+    }
+    if (lane == 0) {
+        const float lb = (__ldg(x + blank) - m) * kLog2e;
+        if (!is_dec) {
+            mA[r] = m * kLog2e;
+            lAb[r] = lb;
+        } else {
+            mB[r] = m * kLog2e;
+            lBb[r] = lb;
+            const int b = r / U1, u = r - b * U1;
+            const int Ub = len_U(label_lens, b, U1);
+            lBy[r] = u < Ub ? (__ldg(x + label_at(labels, b, U1, u, V)) - m) * kLog2e : 0.f;
+        }
+    }
+}
+
 __device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
     const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gmem_src) : "memory");
@@ -159,6 +207,21 @@ __device__ __forceinline__ void stage_tile(float* dst, const float* __restrict__
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
+// columns [0, width) (width a multiple of 8, <= 128) of rows [0, n_copy) of a plane with row stride
+// src_stride -> shared memory (row stride Vs), rows [n_copy, n_rows) -> zeros.  Does NOT commit: the caller
+// groups several tiles into one cp.async group.
+__device__ __forceinline__ void stage_cols(float* dst, const float* __restrict__ src, int n_copy, int n_rows,
+                                           int src_stride, int width, int Vs) {
+    const int cpr = width >> 2;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    if (lane < cpr) {
+        for (int r = warp; r < n_rows; r += n_warps) {
+            if (r < n_copy) cp_async_16(dst + r * Vs + 4 * lane, src + (size_t)r * src_stride + 4 * lane);
+            else *reinterpret_cast<float4*>(dst + r * Vs + 4 * lane) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+}
+__device__ __forceinline__ void stage_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 // per-row scalars of the same rows (0 beyond n_copy); joins the cp.async group committed next
 __device__ __forceinline__ void stage_scalars(float* dst, const float* __restrict__ src, int n_copy, int n_rows) {
@@ -301,6 +364,132 @@ cg_lse_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec,
 }
 
 // =================================================================================================
+// forward, wide vocabulary (128 < V): the same CTA / warp tiling; the factor rows no longer fit, so the
+// partition's K dimension (the vocabulary) is walked in 128-column chunks -- per (64-position chunk,
+// 128-column chunk) step one A tile [32][128] and one B tile [64][128] land (double-buffered, one step
+// ahead) and the accumulators carry over the column chunks of a position chunk.  The per-row scalars and
+// A[t][y] of the epilogue come straight from the (L2-resident) factor planes.
+constexpr int kWC = 128;       // vocabulary columns per staged chunk
+constexpr int kWCs = kWC + 4;  // shared-memory row stride (4 mod 32: conflict-free fragment loads)
+
+__global__ void __launch_bounds__(kFThreads)
+cg_lse_mmw_kernel(const float* __restrict__ penc, const float* __restrict__ pdec, const CgFactors F,
+                  const int32_t* __restrict__ labels, const int32_t* __restrict__ act_lens,
+                  const int32_t* __restrict__ label_lens, int T, int U1, int V, int Vk, int blank,
+                  float2* __restrict__ lp2, float* __restrict__ lse_out) {
+    extern __shared__ float smem[];  // [2] x { A [kFT][kWCs], B [kFUC][kWCs] }
+    constexpr int kBuf = (kFT + kFUC) * kWCs;
+    pdl_launch_dependents();
+    const int b = blockIdx.y, t0 = blockIdx.x * kFT;
+    const int Tb = len_T(act_lens, b, T), Ub = len_U(label_lens, b, U1);
+    if (t0 >= Tb) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    const int mt = warp & 1, nq = warp >> 1;
+    pdl_wait();  // the factor planes come from cg_factor_rows_wide_kernel
+
+    const int n_vc = (Vk + kWC - 1) / kWC;  // column chunks
+    const int n_uc = Ub / kFUC + 1;         // position chunks covering u = 0 .. Ub
+    const int n_steps = n_uc * n_vc;
+    auto issue = [&](int s) {  // both tiles of step s, one cp.async group, into buffer s & 1
+        const int uc = s / n_vc, vc = s - uc * n_vc;
+        const int v0 = vc * kWC, w = min(kWC, Vk - v0);
+        float* Ad = smem + (s & 1) * kBuf;
+        float* Bd = Ad + kFT * kWCs;
+        stage_cols(Ad, F.Ea + ((size_t)b * T + t0) * Vk + v0, min(kFT, Tb - t0), kFT, Vk, w, kWCs);
+        stage_cols(Bd, F.Eb + ((size_t)b * U1 + uc * kFUC) * Vk + v0, min(kFUC, Ub + 1 - uc * kFUC), kFUC, Vk, w,
+                   kWCs);
+        stage_commit();
+    };
+    issue(0);
+    float acc[2][4], acs[2][4];  // hi*hi / the two cross terms
+    int uc = 0, vc = 0;
+    for (int s = 0; s < n_steps; ++s) {
+        const int u0 = uc * kFUC;
+        const bool last_vc = vc == n_vc - 1;
+        const int w = min(kWC, Vk - vc * kWC);
+        const float* As = smem + (s & 1) * kBuf;
+        const float* Bs = As + kFT * kWCs;
+        stage_wait();
+        __syncthreads();  // this step's tiles have landed; every warp is done with the previous step's
+        if (s + 1 < n_steps) issue(s + 1);
+
+        const int un0 = nq * 16;  // first position (within the chunk) of this warp's column tiles
+        const bool warp_on = t0 + mt * 16 < Tb && u0 + un0 <= Ub;  // warp-uniform, the same for every vc of this uc
+        const bool n_on1 = u0 + un0 + 8 <= Ub;
+        if (warp_on) {
+            if (vc == 0) {
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) acc[i][k] = acs[i][k] = 0.f;
+            }
+            const float* arow = As + (mt * 16 + g) * kWCs + q;
+            const float* brow = Bs + (un0 + g) * kWCs + q;
+#pragma unroll 2
+            for (int k0 = 0; k0 < w; k0 += 8) {
+                uint32_t ah[4], al[4];
+                split_tf32(arow[k0], ah[0], al[0]);
+                split_tf32(arow[k0 + 8 * kWCs], ah[1], al[1]);
+                split_tf32(arow[k0 + 4], ah[2], al[2]);
+                split_tf32(arow[k0 + 8 * kWCs + 4], ah[3], al[3]);
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    if (i == 1 && !n_on1) continue;
+                    uint32_t bh[2], bl[2];
+                    split_tf32(brow[i * 8 * kWCs + k0], bh[0], bl[0]);
+                    split_tf32(brow[i * 8 * kWCs + k0 + 4], bh[1], bl[1]);
+                    mma_tf32(acc[i], ah, bh);
+                    mma_tf32(acs[i], ah, bl);
+                    mma_tf32(acs[i], al, bh);
+                }
+            }
+            if (last_vc) {
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    if (i == 1 && !n_on1) continue;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) {
+                            const int r = mt * 16 + g + 8 * h, uu = un0 + 8 * i + 2 * q + k;
+                            const int t = t0 + r, u = u0 + uu;
+                            if (t >= Tb || u > Ub) continue;
+                            const size_t ra = (size_t)b * T + t, rb = (size_t)b * U1 + u;
+                            const float mAr = __ldg(F.mA + ra), mm = mAr + __ldg(F.mB + rb);
+                            const float* pe = penc + ra * V;
+                            float lgs = fast_lg2(acc[i][2 * h + k] + acs[i][2 * h + k]);
+                            const int y = u < Ub ? label_at(labels, b, U1, u, V) : blank;
+                            if (lgs < kTinyLog2) {
+                                // exact path: the row peaks do not line up, redo this cell in the log domain
+                                const float* pd = pdec + rb * V;
+                                float mx = -INFINITY;
+                                for (int v = 0; v < V; ++v) mx = fmaxf(mx, (pe[v] + pd[v]) * kLog2e);
+                                float se = 0.f;
+                                for (int v = 0; v < V; ++v) se += fast_ex2((pe[v] + pd[v]) * kLog2e - mx);
+                                lgs = mx + fast_lg2(se) - mm;
+                            }
+                            const float lb2 = __ldg(F.lAb + ra) + __ldg(F.lBb + rb) - lgs;
+                            const float ay = __ldg(F.Ea + ra * Vk + y);  // A[t][y]: its log unless it underflowed
+                            const float lay = ay > 1e-30f ? fast_lg2(ay) : __ldg(pe + y) * kLog2e - mAr;
+                            const float ll2 = lay + __ldg(F.lBy + rb) - lgs;
+                            const size_t c = ra * U1 + u;
+                            lp2[c] = make_float2(fmaxf(lb2 * kLn2, kNegInf), u < Ub ? fmaxf(ll2 * kLn2, kNegInf) : 0.f);
+                            lse_out[c] = (mm + lgs) * kLn2;
+                        }
+                }
+            }
+        }
+        if (last_vc) {
+            vc = 0;
+            ++uc;
+        } else {
+            ++vc;
+        }
+    }
+}
+
+// =================================================================================================
 // backward: CTA = (utterance, 32 frames), 8 warps.  Per 48-position chunk: the per-cell scalars
 // (C and the blank / label corrections) go to shared memory, then on tensor cores
 //   E += C B     (32 x Vk, K = 48 positions; warp w: row tile w & 1, column quarter w >> 1; the
@@ -317,7 +506,10 @@ constexpr int kGThreads = 256;
 constexpr int kCs = 52;    // row stride of the C planes (4 mod 8: conflict-free A fragments of C B)
 static_assert(kGT2 * kGUC2 == 6 * kGThreads, "thread (rr, cc) owns 2 rows x 3 columns of the cell block");
 
-template <int NTW>  // 8-column tiles per warp: ceil(Vk / 32)
+// kWide (128 < V): blockIdx.z selects a 128-column chunk of the vocabulary; the CTA stages only those columns
+// of A and B, recomputes the per-cell scalars (cheap next to the products) and owns those columns of d_penc /
+// d_pdec / the slab.  Everything indexed by a column below is local to the chunk unless it says v_off.
+template <int NTW, bool kWide>  // NTW: 8-column tiles per warp, ceil(columns of the CTA / 32)
 __global__ void __launch_bounds__(kGThreads, 3)
 cg_grad_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec, const CgFactors F,
                   const int32_t* __restrict__ labels, const int32_t* __restrict__ act_lens,
@@ -345,23 +537,38 @@ cg_grad_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec
     const int b = blockIdx.y, tile = blockIdx.x, t0 = tile * kGT2;
     const int Tb = len_T(act_lens, b, T), Ub = len_U(label_lens, b, U1);
     const int n_tiles = gridDim.x;
+    const int v_off = kWide ? (int)blockIdx.z * kWC : 0;  // first vocabulary column of this CTA
+    const int Vc = kWide ? min(kWC, Vk - v_off) : Vk;      // its column count (a multiple of 8)
     float* slab = partial ? partial + ((size_t)b * n_tiles + tile) * U1 * V : nullptr;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, q = lane & 3;
     const int mt = warp & 1;                 // 16-frame row tile of E
     const int nt0 = (warp >> 1) * NTW;       // first 8-column tile of this warp (column quarter)
-    const int n_nt = Vk >> 3;                // column tiles in use
+    const int n_nt = Vc >> 3;                // column tiles in use
     constexpr uint32_t kOnes = 0x3f803f80u;  // (1.0, 1.0) in bf16: selects hi + lo of a packed operand
     pdl_launch_dependents();
     pdl_wait();  // nothing in global memory is read OR written before the sweep (the predecessor) has finished
 
     if (t0 >= Tb) {  // tile entirely in the padding: exact zeros
-        for (int i = tid; i < kGT2 * V; i += kGThreads) {
-            const int r = i / V, v = i - r * V;
-            if (t0 + r < T) d_penc[((size_t)b * T + t0 + r) * V + v] = 0.f;
+        if constexpr (kWide) {
+            const int nv = min(Vc, V - v_off);  // real columns of this chunk
+            for (int i = tid; i < kGT2 * nv; i += kGThreads) {
+                const int r = i / nv, v = v_off + i - r * nv;
+                if (t0 + r < T) d_penc[((size_t)b * T + t0 + r) * V + v] = 0.f;
+            }
+            if (slab)
+                for (int i = tid; i < U1 * nv; i += kGThreads) {
+                    const int u = i / nv, v = v_off + i - u * nv;
+                    slab[(size_t)u * V + v] = 0.f;
+                }
+        } else {
+            for (int i = tid; i < kGT2 * V; i += kGThreads) {
+                const int r = i / V, v = i - r * V;
+                if (t0 + r < T) d_penc[((size_t)b * T + t0 + r) * V + v] = 0.f;
+            }
+            if (slab)
+                for (int i = tid; i < U1 * V; i += kGThreads) slab[i] = 0.f;
         }
-        if (slab)
-            for (int i = tid; i < U1 * V; i += kGThreads) slab[i] = 0.f;
         return;
     }
     const float gc = grad_costs.at(b);
@@ -380,14 +587,26 @@ cg_grad_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec
             const int u = u0 + tid;
             ys0[c & 1][tid] = u < Ub ? label_at(labels, b, U1, u, V) : -1;
         }
-        stage_tile(reinterpret_cast<float*>(Bs0 + (c & 1) * kGUC2 * Vs), reinterpret_cast<const float*>(F.Eb2 + row * Vk),
-                   n, kGUC2, Vk, Vs);
+        if constexpr (kWide) {
+            stage_cols(reinterpret_cast<float*>(Bs0 + (c & 1) * kGUC2 * Vs),
+                       reinterpret_cast<const float*>(F.Eb2 + row * Vk + v_off), n, kGUC2, Vk, Vc, Vs);
+            stage_commit();
+        } else {
+            stage_tile(reinterpret_cast<float*>(Bs0 + (c & 1) * kGUC2 * Vs), reinterpret_cast<const float*>(F.Eb2 + row * Vk),
+                       n, kGUC2, Vk, Vs);
+        }
     };
     {
         const size_t row = (size_t)b * T + t0;
         stage_scalars(mA, F.mA + row, rows_t, kGT2);
         stage_scalars(lAb, F.lAb + row, rows_t, kGT2);
-        stage_tile(reinterpret_cast<float*>(As), reinterpret_cast<const float*>(F.Ea2 + row * Vk), rows_t, kGT2, Vk, Vs);
+        if constexpr (kWide) {
+            stage_cols(reinterpret_cast<float*>(As), reinterpret_cast<const float*>(F.Ea2 + row * Vk + v_off), rows_t, kGT2,
+                       Vk, Vc, Vs);
+            stage_commit();
+        } else {
+            stage_tile(reinterpret_cast<float*>(As), reinterpret_cast<const float*>(F.Ea2 + row * Vk), rows_t, kGT2, Vk, Vs);
+        }
     }
     issue_chunk(0);
     int chunk = 0;
@@ -440,7 +659,9 @@ cg_grad_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec
                         if (t < Tb - 1) bdn[k] = beta[c + U1];
                         if (u < Ub) {
                             brt[k] = beta[c + 1];
-                            const float ay = unpack_hilo(As[r * Vs + ys[uu]]);  // log2 A[t][y_u]; gather if it underflowed
+                            // log2 A[t][y_u]; gather if it underflowed (wide: y_u may lie outside this CTA's columns)
+                            const float ay = kWide ? __ldg(F.Ea + ((size_t)b * T + t) * Vk + ys[uu])
+                                                   : unpack_hilo(As[r * Vs + ys[uu]]);
                             pey[k] = ay > 1e-30f ? fast_lg2(ay)
                                                  : __ldg(penc + ((size_t)b * T + t) * V + ys[uu]) * kLog2e - mA[r];
                         }
@@ -502,10 +723,10 @@ cg_grad_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec
                 for (int i = 0; i < NTW; ++i) {
                     if (nt0 + i >= n_nt) continue;
                     mma_hilo(E[i], ca, bcol[8 * i], bcol[8 * i + 4 * Vs]);
-                    const int col = (nt0 + i) * 8 + g;
+                    const int col = v_off + (nt0 + i) * 8 + g;
                     const uint32_t yh[2] = {y0 == col ? kOnes : 0u, y1 == col ? kOnes : 0u};
                     mma_bf16(X[i], la, yh);
-                    if ((blank >> 3) == nt0 + i) {  // warp-uniform
+                    if ((blank >> 3) == (v_off >> 3) + nt0 + i) {  // warp-uniform
                         const uint32_t yb[2] = {col == blank ? kOnes : 0u, col == blank ? kOnes : 0u};
                         mma_bf16(X[i], ba, yb);
                     }
@@ -549,11 +770,11 @@ cg_grad_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec
                     if (u >= U1) continue;
 #pragma unroll
                     for (int k = 0; k < 2; ++k) {
-                        const int v = (nt0 + i) * 8 + 2 * q + k;
+                        const int v = v_off + (nt0 + i) * 8 + 2 * q + k;
                         if (v >= V) continue;
                         float gv = 0.f;
                         if (uu < rows_u) {
-                            gv = unpack_hilo(Bs[uu * Vs + v]) * D[i][2 * h + k];
+                            gv = unpack_hilo(Bs[uu * Vs + v - v_off]) * D[i][2 * h + k];
                             if (v == blank) gv -= ub[uu];
                             if (v == ys[uu]) gv -= ul[uu];
                         }
@@ -575,10 +796,10 @@ cg_grad_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec
             if (t0 + r >= T) continue;
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
-                const int v = (nt0 + i) * 8 + 2 * q + k;
+                const int v = v_off + (nt0 + i) * 8 + 2 * q + k;
                 if (v >= V) continue;
                 d_penc[((size_t)b * T + t0 + r) * V + v] =
-                    fmaf(unpack_hilo(As[r * Vs + v]), E[i][2 * h + k], -X[i][2 * h + k]);
+                    fmaf(unpack_hilo(As[r * Vs + v - v_off]), E[i][2 * h + k], -X[i][2 * h + k]);
             }
         }
     }
@@ -596,7 +817,7 @@ cg_grad_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec
             const float occ = e16m16_log2_ratio(alpha[c], beta[c], llq) - zz;
             const float* pe = penc + ((size_t)b * T + t) * V;
             const float* pd = pdec + ((size_t)b * U1 + u) * V;
-            for (int v = 0; v < V; ++v) {
+            for (int v = v_off; v < min(V, v_off + Vc); ++v) {  // this CTA's columns
                 const float gg = gc * fast_ex2((pe[v] + pd[v]) * kLog2e + occ);
                 atomicAdd(d_penc + ((size_t)b * T + t) * V + v, gg);
                 if (slab) atomicAdd(slab + (size_t)u * V + v, gg);
@@ -608,30 +829,31 @@ cg_grad_mm_kernel(const float* __restrict__ penc, const float* __restrict__ pdec
 
 inline int grad_row_stride(int Vk) { return (Vk & 15) == 8 ? Vk : Vk + 8; }  // 8 mod 16
 
-template <int NTW>
+template <int NTW, bool kWide>
 int launch_grad_mm(const float* penc, const float* pdec, const CgFactors& F, const int32_t* labels,
                    const int32_t* act_lens, const int32_t* label_lens, int B, int T, int U1, int V, int blank,
                    const float* lse, const int32_t* alpha, const int32_t* beta, GradCosts grad_costs,
                    float* d_penc, float* d_pdec, float* partial, cudaStream_t stream) {
-    const int Vk = F.Vk, Vs = grad_row_stride(Vk);
+    const int Vk = F.Vk, Vs = grad_row_stride(kWide ? kWC : Vk);
     const size_t smem = ((size_t)(kGT2 + 2 * kGUC2) * Vs + 3 * kGT2 * kCs + 2 * kGT2 + 8 * kGUC2) *
                         sizeof(float);  // 65 KiB at V = 73: three CTAs per SM, the whole cfg-2 grid in one wave
-    cudaError_t e = cudaFuncSetAttribute(cg_grad_mm_kernel<NTW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(cg_grad_mm_kernel<NTW, kWide>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return status_from_cuda(e);
-    dim3 grid((T + kGT2 - 1) / kGT2, B);
-    e = launch_pdl(pdl_ok((long long)B * T), cg_grad_mm_kernel<NTW>, grid, dim3(kGThreads), smem, stream, penc, pdec, F, labels,
+    dim3 grid((T + kGT2 - 1) / kGT2, B, kWide ? (Vk + kWC - 1) / kWC : 1);
+    e = launch_pdl(pdl_ok((long long)B * T), cg_grad_mm_kernel<NTW, kWide>, grid, dim3(kGThreads), smem, stream, penc, pdec, F, labels,
                    act_lens, label_lens, T, U1, V, Vk, Vs, blank, lse, alpha, beta, grad_costs, d_penc, d_pdec, partial);
     return e == cudaSuccess ? launch_status() : status_from_cuda(e);
 }
 
 }  // namespace
 
-bool cg_mm_supported(int V) { return V <= 128; }
+// every V; RNNTB200_CG_GENERIC selects the per-cell kernels of joint_cg.cu (an independent evaluation, kept for the tests; V <~ 1400)
+bool cg_mm_supported(int V) { return V >= 1 && !std::getenv("RNNTB200_CG_GENERIC"); }
 int cg_mm_tile_rows() { return kGT2; }
 
 // factor planes: E_enc [B*T][Vk], E_dec [B*U1][Vk], then the per-row scalars
 size_t cg_factors_bytes(int B, int T, int U1, int V) {
-    if (!cg_mm_supported(V)) return 0;
+    if (!cg_mm_supported(V)) return 0;  // the generic kernels need no factors
     const size_t Vk = (V + 7) & ~7, re = (size_t)B * T, rd = (size_t)B * U1;
     return (2 * (re + rd) * Vk + 2 * re + 3 * rd) * sizeof(float);
 }
@@ -657,9 +879,13 @@ int launch_cg_factor_rows(const float* penc, const float* pdec, const int32_t* l
                           int B, int T, int U1, int V, int blank, const CgFactors& F, cudaStream_t stream) {
     const int rows = B * (T + U1);
     if (rows == 0) return RNNTB200_STATUS_SUCCESS;
-    const cudaError_t e = launch_pdl(pdl_ok((long long)B * T), cg_factor_rows_kernel, dim3((rows + 7) / 8), dim3(256), (size_t)0,
-                                     stream, penc, pdec, labels, label_lens, B * T, B * U1, U1, V, F.Vk, blank, F.Ea, F.mA, F.lAb,
-                                     F.Eb, F.mB, F.lBb, F.lBy, F.Ea2, F.Eb2);
+    const cudaError_t e =
+        V > 128 ? launch_pdl(pdl_ok((long long)B * T), cg_factor_rows_wide_kernel, dim3((rows + 7) / 8), dim3(256), (size_t)0,
+                             stream, penc, pdec, labels, label_lens, B * T, B * U1, U1, V, F.Vk, blank, F.Ea, F.mA, F.lAb,
+                             F.Eb, F.mB, F.lBb, F.lBy, F.Ea2, F.Eb2)
+                : launch_pdl(pdl_ok((long long)B * T), cg_factor_rows_kernel, dim3((rows + 7) / 8), dim3(256), (size_t)0,
+                             stream, penc, pdec, labels, label_lens, B * T, B * U1, U1, V, F.Vk, blank, F.Ea, F.mA, F.lAb,
+                             F.Eb, F.mB, F.lBb, F.lBy, F.Ea2, F.Eb2);
     return e == cudaSuccess ? launch_status() : status_from_cuda(e);
 }
 
@@ -667,6 +893,15 @@ int launch_cg_lse_mm(const float* penc, const float* pdec, const CgFactors& F, c
                      const int32_t* act_lens, const int32_t* label_lens, int B, int T, int U1, int V, int blank,
                      float2* lp2, float* lse, cudaStream_t stream) {
     const int Vk = F.Vk, Vs = Vk + 4;
+    if (V > 128) {
+        const size_t smem = (size_t)2 * (kFT + kFUC) * kWCs * sizeof(float);  // 99 KiB: two CTAs per SM
+        cudaError_t e = cudaFuncSetAttribute(cg_lse_mmw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return status_from_cuda(e);
+        dim3 grid((T + kFT - 1) / kFT, B);
+        e = launch_pdl(pdl_ok((long long)B * T), cg_lse_mmw_kernel, grid, dim3(kFThreads), smem, stream, penc, pdec, F, labels,
+                       act_lens, label_lens, T, U1, V, Vk, blank, lp2, lse);
+        return e == cudaSuccess ? launch_status() : status_from_cuda(e);
+    }
     const size_t smem = ((size_t)(kFT + 2 * kFUC) * Vs + 2 * kFT + 6 * kFUC) * sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(cg_lse_mm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return status_from_cuda(e);
@@ -680,12 +915,13 @@ int launch_cg_grad_mm(const float* penc, const float* pdec, const CgFactors& F, 
                       const int32_t* act_lens, const int32_t* label_lens, int B, int T, int U1, int V, int blank,
                       const float* lse, const int32_t* alpha, const int32_t* beta, GradCosts grad_costs,
                       float* d_penc, float* d_pdec, float* partial, cudaStream_t stream) {
-#define RNNT_MM(NTW)                                                                                         \
-    return launch_grad_mm<NTW>(penc, pdec, F, labels, act_lens, label_lens, B, T, U1, V, blank, lse, alpha, \
-                               beta, grad_costs, d_penc, d_pdec, partial, stream)
-    if (V <= 32) RNNT_MM(1);
-    if (V <= 96) RNNT_MM(3);
-    RNNT_MM(4);
+#define RNNT_MM(NTW, WIDE)                                                                                         \
+    return launch_grad_mm<NTW, WIDE>(penc, pdec, F, labels, act_lens, label_lens, B, T, U1, V, blank, lse, alpha, \
+                                     beta, grad_costs, d_penc, d_pdec, partial, stream)
+    if (V <= 32) RNNT_MM(1, false);
+    if (V <= 96) RNNT_MM(3, false);
+    if (V <= 128) RNNT_MM(4, false);
+    RNNT_MM(4, true);
 #undef RNNT_MM
 }
 

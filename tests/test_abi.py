@@ -67,12 +67,14 @@ def test_argument_validation_needs_no_gpu(cuda_lib):
                                             None, None, None, None) == 2  # bad dtype
     assert cuda_lib.rnntb200_lattice_sweep(None, None, None, 1, 0, 3, None, None, None, None, None) == 2
     assert cuda_lib.rnntb200_joint_cg_bwd_workspace_bytes(2, 16, 5, 7, 0) == 0
-    # deterministic mode: one [U1, V] slab per (utterance, 32-frame tile) for V <= 128, 8-frame tile above
+    # deterministic mode: one [U1, V] slab per (utterance, 32-frame tile)
     assert cuda_lib.rnntb200_joint_cg_bwd_workspace_bytes(2, 16, 5, 7, 1) == 2 * 1 * 5 * 7 * 4
-    assert cuda_lib.rnntb200_joint_cg_bwd_workspace_bytes(2, 16, 5, 200, 1) == 2 * 2 * 5 * 200 * 4
+    assert cuda_lib.rnntb200_joint_cg_bwd_workspace_bytes(2, 16, 5, 200, 1) == 2 * 1 * 5 * 200 * 4
+    assert cuda_lib.rnntb200_joint_cg_bwd_workspace_bytes(2, 16, 5, 5000, 1) == 2 * 1 * 5 * 5000 * 4
     # factor planes: four [rows, Vk] planes (Vk = V rounded up to 8) + 2 scalars per encoder row and 3
     # per predictor row; none for vocabularies the factorised kernels do not serve
     assert cuda_lib.rnntb200_joint_cg_factors_bytes(2, 16, 5, 73) == (2 * (32 + 10) * 80 + 2 * 32 + 3 * 10) * 4
-    assert cuda_lib.rnntb200_joint_cg_factors_bytes(2, 16, 5, 200) == 0
+    assert cuda_lib.rnntb200_joint_cg_factors_bytes(2, 16, 5, 200) == (2 * (32 + 10) * 200 + 2 * 32 + 3 * 10) * 4
+    assert cuda_lib.rnntb200_joint_cg_factors_bytes(2, 16, 5, 5000) == (2 * (32 + 10) * 5000 + 2 * 32 + 3 * 10) * 4
     assert cuda_lib.rnntb200_joint_cg_fwd(None, None, None, None, None, 1, 4, 3, 5, 7, None, None, None, None,
                                           None, None, 0, None) == 2  # blank >= V

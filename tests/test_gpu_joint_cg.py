@@ -227,11 +227,16 @@ def test_full_size_cfg3_long_utterances(cuda_lib):
         assert np.all(fused["d_enc"][b, al[b]:] == 0)
 
 
-def test_large_vocab_cfg4_generic_kernels(cuda_lib):
-    """V = 1024 (BASELINE cfg 4's vocabulary) takes the generic concat-GELU kernels (the factorised
-    ones keep <= 128 columns in registers): fused against the dense path at B = 3."""
+@pytest.mark.parametrize("generic", [False, True])
+def test_large_vocab_cfg4_kernels(cuda_lib, monkeypatch, generic):
+    """V = 1024 (BASELINE cfg 4's vocabulary): the wide factorised kernels (128-column chunks,
+    joint_cg_mm.cu) and, with RNNTB200_CG_GENERIC set, the generic per-cell kernels (joint_cg.cu):
+    fused against the dense path at B = 3."""
+    if generic:
+        monkeypatch.setenv("RNNTB200_CG_GENERIC", "1")
     c = synthetic.CONFIGS[4]
     d = synthetic.make_batch(3, c["T"], c["U"], c["V"], c["H"], ragged=True, seed=1238, device="cuda")
+    assert (cuda_lib.rnntb200_joint_cg_factors_bytes(3, c["T"], c["U"] + 1, c["V"]) == 0) == generic
     fused = fused_step(d)
     t = {k: d[k].clone().requires_grad_(True) for k in ("enc", "dec", "weight", "bias")}
     logits = rb.joint_dense(t["enc"], t["dec"], t["weight"], t["bias"])
