@@ -51,7 +51,11 @@ class PeerAllReduce:
 
     def all_reduce_mean_(self, tensors: Sequence[torch.Tensor], average: bool = True) -> None:
         """In place: every tensor <- mean (or sum) over ranks.  fp32, contiguous, CUDA, <= 4 tensors."""
+        if self.own is None:
+            raise RuntimeError("PeerAllReduce: used after close()")
         n = len(tensors)
+        if not 1 <= n <= 4:
+            raise RuntimeError("PeerAllReduce: between 1 and 4 tensors per call")
         segs = (ctypes.c_void_p * n)()
         sizes = (ctypes.c_int * n)()
         for i, t in enumerate(tensors):
