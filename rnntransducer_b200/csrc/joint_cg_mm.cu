@@ -65,7 +65,14 @@ __device__ __forceinline__ float unpack_hilo(uint32_t p) {
 // instruction's k index runs over (element, half): lane (g, q) then holds for A the elements
 // [g][q], [g+8][q], [g][q+4], [g+8][q+4] and for B [q][g], [q+4][g] -- the same addressing as the
 // TF32 fragments -- and one instruction covers 8 elements of the real K dimension.
+// RNNTB200_EXP_NO_MMA (scripts/build_exp_nomma.sh, never the product build): the products and with them their
+// operand loads / conversions disappear -- what remains is staging, per-cell scalars and epilogues, i.e. what
+// ANY tensor-core formulation (mma.sync or tcgen05) of these kernels would still have to do.
 __device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+#ifdef RNNTB200_EXP_NO_MMA
+    d[0] += 1e-3f;
+    return;
+#endif
     asm volatile(
         "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
         : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
@@ -84,6 +91,10 @@ __device__ __forceinline__ void mma_hilo(float (&d)[4], const uint32_t (&a)[4], 
 //   a0 = A[g][q]  a1 = A[g+8][q]  a2 = A[g][q+4]  a3 = A[g+8][q+4];  b0 = B[q][g]  b1 = B[q+4][g];
 //   d0 = D[g][2q]  d1 = D[g][2q+1]  d2 = D[g+8][2q]  d3 = D[g+8][2q+1]
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+#ifdef RNNTB200_EXP_NO_MMA
+    d[0] += 1e-3f, d[1] += 1e-3f, d[2] += 1e-3f, d[3] += 1e-3f;
+    return;
+#endif
     asm volatile(
         "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
         : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
